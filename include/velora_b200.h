@@ -1,0 +1,149 @@
+/* velora_b200 — C ABI of the B200-native Liquid-NN hot path (libvelora_b200.so).
+ *
+ * This is the drop-in boundary for the path named in BASELINE.json: everything the reference computes with ATen
+ * call chains inside
+ *     velora/models/lnn/sparse.py:71-81     SparseLinear.forward      (masked linear)
+ *     velora/models/lnn/cell.py:113-169     NCPLiquidCell.forward     (five heads + closed-form gating)
+ *     velora/models/lnn/ncp.py:129-178      LiquidNCPNetwork.forward  (inter -> Mish -> cell -> Mish -> motor)
+ *     velora/models/lnn/ncp.py:299-328      NCPNetwork.forward        (three masked linears, Mish between)
+ *     velora/buffer/replay.py:79-88         ReplayBuffer.sample       (six row gathers)
+ * and the autograd backward of each, is one entry point here.  The reference has no FFI of its own (it is pure
+ * Python over torch); INTEGRATION.md shows the ctypes binding a maintainer adds at those call sites.
+ *
+ * Conventions
+ *   - extern "C"; plain pointers and sizes; no torch types.
+ *   - every pointer is a DEVICE pointer owned by the caller (contiguous, row-major, float32 unless stated),
+ *     except arrays-of-pointers arguments (`const float* const*`), which are HOST arrays of device pointers.
+ *   - nothing is allocated, nothing is synchronised: each call only enqueues work on `stream`
+ *     (a cudaStream_t passed as void*; NULL = legacy default stream).  Scratch memory is passed in by the caller;
+ *     its size comes from the matching *_workspace_bytes() query.
+ *   - return value: 0 = ok; negative = argument error (VB_ERR_*); positive = cudaError_t.
+ *     vb_last_error() returns a thread-local description of the last failure on the calling thread.
+ *   - re-entrant: may be called concurrently from several host threads (autograd's backward runs on its own
+ *     thread) and on several streams.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with a cudaError_t.
+ *
+ * Packed parameter block ("packed", float32).  The seven SparseLinear layers of a LiquidNCPNetwork stay the
+ * optimizer-visible truth in the host framework; the kernels read one pre-masked, transposed, padded copy
+ * produced by vb_liquid_pack().  With NIp = ceil4(Ni), NCp = ceil4(Nc), Op = ceil4(O), Ip = ceil4(I), K = Ni+Nc,
+ * head order {g, h, f (= f_head_to_g + f_head_to_h, only ever used summed: cell.py:130-133), proj}:
+ *
+ *   F section (forward orientation; also the layout of every gradient block "dpacked")
+ *     win_t [I ][NIp]      W_in^T (*) mask          b_in [NIp]
+ *     wh_t  [K ][4*NCp]    row i = weights of input i to (head, neuron)      b_h [4*NCp]
+ *     wout  [O ][NCp]                                b_out[Op]
+ *   D section (transposed copies used by the data-gradient of the generic kernels)
+ *     win   [Ni][Ip]       wh [4*NCp][Kp] (Kp = ceil4(K))      wout_t [Nc][Op]
+ *
+ * NCPNetwork uses the same scheme with three layers: w1_t [I][NIp] b1 [NIp] | w2_t [Ni][NCp] b2 [NCp] |
+ * w3 [O][NCp] b3 [Op]  and D section  w1 [Ni][Ip]  w2 [Nc][NIp]  w3_t [Nc][Op].
+ */
+#ifndef VELORA_B200_H
+#define VELORA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VB_ABI_VERSION 1
+
+/* argument errors */
+#define VB_ERR_NULL_POINTER (-1)
+#define VB_ERR_BAD_DIMS (-2)
+#define VB_ERR_WORKSPACE (-3)
+#define VB_ERR_TOO_LARGE (-4)   /* network does not fit the on-chip budget of any compiled kernel */
+#define VB_ERR_ALIGNMENT (-5)
+
+/* mask element types accepted by the pack/unpack entry points (wiring masks are int32, cell masks float32:
+ * velora/wiring.py:132-149, velora/models/lnn/cell.py:109-111) */
+#define VB_MASK_I32 0
+#define VB_MASK_F32 1
+
+/* flags */
+#define VB_FLAG_FORCE_GENERIC 1   /* skip the specialised 20-neuron-class kernels (used by the parity tests) */
+
+/* vb_query() keys */
+#define VB_Q_ABI_VERSION 0
+#define VB_Q_BUILT_SM 1           /* 100 => compiled for sm_100a */
+#define VB_Q_DEVICE_SMS 2
+#define VB_Q_DEVICE_CC 3          /* major*10+minor of the current device */
+#define VB_Q_MAX_SMEM_OPTIN 4
+
+int vb_query(int what);
+const char* vb_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------ liquid network */
+int64_t vb_liquid_packed_floats(int I, int Ni, int Nc, int O);   /* F + D sections */
+int64_t vb_liquid_grad_floats(int I, int Ni, int Nc, int O);     /* F section only */
+/* 1 if (I,Ni,Nc,O) is served by a specialised constant-bank kernel, else 0 */
+int vb_liquid_has_fast_path(int I, int Ni, int Nc, int O);
+
+/* Replaces the per-forward `weight * mask` of sparse.py:81 for all seven layers of ncp.py:79-102.
+ * w_heads/b_heads/m_heads: host arrays of 5 device pointers in the order
+ * {g_head, h_head, f_head_to_g, f_head_to_h, proj} (cell.py:61-69). */
+int vb_liquid_pack(const float* w_in, const float* b_in, const void* m_in, int m_in_type,
+                   const float* const* w_heads, const float* const* b_heads, const void* const* m_heads, int m_heads_type,
+                   const float* w_out, const float* b_out, const void* m_out, int m_out_type,
+                   int I, int Ni, int Nc, int O, float* packed, void* stream);
+
+int64_t vb_liquid_fwd_workspace_bytes(int I, int Ni, int Nc, int O, int64_t B, int T);
+int64_t vb_liquid_bwd_workspace_bytes(int I, int Ni, int Nc, int O, int64_t B, int T);
+
+/* T-fold LiquidNCPNetwork.forward (ncp.py:129-178) with the time loop on chip.
+ *   x [B,T,I]; h0 [B,Nc] or NULL (= zeros, ncp.py:162-166); y [B,T,O]; h_traj [B,T,Nc] (h_traj[:,t] is the h'
+ *   returned by step t).  T = 1 is exactly one reference forward call. */
+int vb_liquid_fwd(const float* packed, const float* x, const float* h0, float* y, float* h_traj,
+                  int64_t B, int T, int I, int Ni, int Nc, int O,
+                  void* workspace, int64_t workspace_bytes, int flags, void* stream);
+
+/* Backward of the above (what autograd does over the reference's op graph), gates recomputed from x and h_traj.
+ *   dy [B,T,O]; dh_traj [B,T,Nc] or NULL; dh_last [B,Nc] or NULL (extra gradient on h_traj[:,T-1]);
+ *   dx [B,T,I] or NULL; dh0 [B,Nc] or NULL; dpacked: F-section layout, overwritten with the parameter gradients
+ *   of the PACKED (pre-masked) weights — vb_liquid_unpack_grads() maps them back to the seven layers. */
+int vb_liquid_bwd(const float* packed, const float* x, const float* h0, const float* h_traj,
+                  const float* dy, const float* dh_traj, const float* dh_last,
+                  float* dx, float* dh0, float* dpacked,
+                  int64_t B, int T, int I, int Ni, int Nc, int O,
+                  void* workspace, int64_t workspace_bytes, int flags, void* stream);
+
+/* dW_layer = dW_packed (*) mask_layer (masked entries exactly 0: reference tests/models/test_lnn.py:570-576);
+ * both f heads receive the same gradient.  accumulate != 0 adds into the outputs (torch .grad semantics). */
+int vb_liquid_unpack_grads(const float* dpacked, const void* m_in, int m_in_type,
+                           const void* const* m_heads, int m_heads_type, const void* m_out, int m_out_type,
+                           float* g_w_in, float* g_b_in, float* const* g_w_heads, float* const* g_b_heads,
+                           float* g_w_out, float* g_b_out,
+                           int I, int Ni, int Nc, int O, int accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ NCP network (critic) */
+int64_t vb_ncp_packed_floats(int I, int Ni, int Nc, int O);
+int64_t vb_ncp_grad_floats(int I, int Ni, int Nc, int O);
+/* w/b/m: host arrays of 3 device pointers, layers ncp.0, ncp.2, ncp.4 (ncp.py:250-274) */
+int vb_ncp_pack(const float* const* w, const float* const* b, const void* const* m, int m_type,
+                int I, int Ni, int Nc, int O, float* packed, void* stream);
+int64_t vb_ncp_bwd_workspace_bytes(int I, int Ni, int Nc, int O, int64_t B);
+/* NCPNetwork.forward (ncp.py:299-328): x [B,I] -> y [B,O] */
+int vb_ncp_fwd(const float* packed, const float* x, float* y, int64_t B, int I, int Ni, int Nc, int O,
+               int flags, void* stream);
+/* backward with recompute: dy [B,O] -> dx [B,I] (or NULL), dpacked (F layout, overwritten) */
+int vb_ncp_bwd(const float* packed, const float* x, const float* dy, float* dx, float* dpacked,
+               int64_t B, int I, int Ni, int Nc, int O,
+               void* workspace, int64_t workspace_bytes, int flags, void* stream);
+int vb_ncp_unpack_grads(const float* dpacked, const void* const* m, int m_type,
+                        float* const* g_w, float* const* g_b,
+                        int I, int Ni, int Nc, int O, int accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ replay buffer */
+/* ReplayBuffer.sample's six gathers (replay.py:81-88) in one launch: dst[k][b,:] = src[k][idx[b],:].
+ * src/dst: host arrays of n_arrays (<= 8) device pointers; row_floats[k] = floats per row of array k;
+ * idx: int64 [B] (drawn by the caller with torch.randint so that indices stay bit-exact with the reference);
+ * n_rows = valid rows in src (indices are checked against it: out-of-range rows are written as NaN and the call
+ * still returns 0 — the host wrapper validates the range the way torch indexing would). */
+int vb_gather_rows(const float* const* src, float* const* dst, const int* row_floats, int n_arrays,
+                   const int64_t* idx, int64_t B, int64_t n_rows, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VELORA_B200_H */

@@ -1,0 +1,179 @@
+"""Parity of the CUDA liquid path (through the public modules -> autograd.Function -> C ABI) with the reference
+goldens and the oracle.  Run on the B200 box: pytest -m gpu."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import liquid_oracle as lo
+from vb_testutil import FP32_RTOL, assert_close_to_reference, liquid_case_params, rel_err
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["fixture", "actor_t1", "actor_seq", "actor_seq_allh", "fixture_seq", "odd", "mid", "wide"]
+
+
+def _build(d, name, flags=0):
+    import velora_b200 as vb
+    from velora_b200.models.lnn import LiquidNCPNetwork
+
+    i, n, o, sp, seed, B, T, allh = d[f"{name}_meta"]
+    vb.set_seed(int(seed))
+    net = LiquidNCPNetwork(int(i), int(n), int(o), sparsity_level=float(sp), device=torch.device("cuda"))
+    # constructed from the same seed => identical parameters and masks (checked on CPU in test_host.py);
+    # load the golden state anyway so that this test only measures the kernels
+    net.load_state_dict({k: torch.tensor(v) for k, v in liquid_case_params(d, name).items()})
+    net.kernel_flags = flags
+    return net
+
+
+@pytest.mark.parametrize("flags", [0, 1], ids=["specialised", "generic"])
+@pytest.mark.parametrize("name", CASES)
+def test_forward_backward_vs_reference(golden, name, flags):
+    d = golden("liquid")
+    net = _build(d, name, flags)
+    dev = torch.device("cuda")
+    x = torch.tensor(d[f"{name}_x"], device=dev, requires_grad=True)
+    h0 = torch.tensor(d[f"{name}_h0"], device=dev, requires_grad=True)
+    ry = torch.tensor(d[f"{name}_ry"], device=dev)
+    rh = torch.tensor(d[f"{name}_rh"], device=dev)
+    y, ht = net.forward_seq(x, h0)
+    assert_close_to_reference(y.detach().cpu().numpy(), d[f"{name}_f32_y"], d[f"{name}_f64_y"], "y")
+    assert_close_to_reference(ht.detach().cpu().numpy(), d[f"{name}_f32_htraj"], d[f"{name}_f64_htraj"], "h_traj")
+    ((y * ry).sum() + (ht * rh).sum()).backward()
+    assert_close_to_reference(x.grad.cpu().numpy(), d[f"{name}_f32_dx"], d[f"{name}_f64_dx"], "dx")
+    assert_close_to_reference(h0.grad.cpu().numpy(), d[f"{name}_f32_dh0"], d[f"{name}_f64_dh0"], "dh0")
+    for k, p in net.named_parameters():
+        g = p.grad.cpu().numpy()
+        assert_close_to_reference(g, d[f"{name}_f32_grad_{k}"], d[f"{name}_f64_grad_{k}"], f"grad {k}")
+        if k.endswith("weight"):
+            mask = net.state_dict()[k.replace("weight", "mask")].cpu().numpy()
+            assert np.all(g[mask == 0] == 0.0), f"{k}: masked gradient entries must be exactly zero"
+
+
+@pytest.mark.parametrize("name", ["actor_seq", "fixture_seq"])
+def test_h_last_output_matches_dense_dh(golden, name):
+    """Loss on h_T through the separate h_last output == loss on h_traj[:, -1]."""
+    d = golden("liquid")
+    dev = torch.device("cuda")
+    x = torch.tensor(d[f"{name}_x"], device=dev)
+    h0 = torch.tensor(d[f"{name}_h0"], device=dev)
+    r = torch.tensor(d[f"{name}_rh"], device=dev)[:, -1]
+    grads = []
+    for use_last in (True, False):
+        net = _build(d, name)
+        y, ht, hl = net.forward_seq(x, h0, return_last=True)
+        assert torch.equal(hl, ht[:, -1])
+        ((hl if use_last else ht[:, -1]) * r).sum().backward()
+        grads.append(torch.cat([p.grad.flatten() for p in net.parameters()]).cpu().numpy())
+    assert rel_err(grads[0], grads[1]) < 1e-6
+
+
+def test_forward_api_conventions(golden):
+    """T=1 API of ncp.py:129-178: h=None => zeros, B==1 squeeze, CPU input moved to the device, ValueError on 3-D."""
+    d = golden("liquid")
+    net = _build(d, "fixture")
+    x = torch.tensor(d["fixture_x"][:, 0])
+    y, h = net(x, None)          # CPU input, like reference tests/models/test_lnn.py:367-381
+    assert y.is_cuda and h.is_cuda and y.shape == (7, 5) and h.shape == (7, 8)
+    assert rel_err(y.detach().cpu().numpy(), d["fixture_f32_y_h0none"]) < FP32_RTOL
+    assert rel_err(h.detach().cpu().numpy(), d["fixture_f32_h_h0none"]) < FP32_RTOL
+    y1, h1 = net(x[:1])
+    assert y1.shape == (5,) and h1.shape == (1, 8)     # reference tests/models/test_lnn.py:331-340
+    with pytest.raises(ValueError):
+        net(torch.zeros(2, 3, 10))
+    # anchors of SURVEY.md 8c
+    xa = torch.tensor(d["fixture_x"][:, 0], device="cuda")
+    ha = torch.tensor(d["fixture_h0"], device="cuda")
+    ya, _ = net(xa, ha)
+    assert abs(float(ya.sum()) - float(d["anchor_sum_y"][0])) < 2e-5
+    assert np.allclose(ya[0].detach().cpu().numpy(), d["anchor_y0"], atol=2e-6)
+
+
+def test_deepcopy_and_jit_script_run_on_gpu(golden):
+    """velora/models/nf/modules.py:370-392 deep-copies then jit.scripts the networks."""
+    d = golden("liquid")
+    net = _build(d, "actor_t1")
+    x = torch.tensor(d["actor_t1_x"][:, 0], device="cuda")
+    h = torch.tensor(d["actor_t1_h0"], device="cuda")
+    y0, h0 = net(x, h)
+    twin = torch.jit.script(copy.deepcopy(net))
+    assert isinstance(twin, torch.jit.RecursiveScriptModule)
+    y1, h1 = twin(x, h)
+    assert torch.equal(y0, y1) and torch.equal(h0, h1)
+    (y1.sum() + h1.sum()).backward()
+    assert all(p.grad is not None for p in twin.parameters())
+    assert list(twin.state_dict().keys()) == list(net.state_dict().keys())
+
+
+def test_seq_equals_looped_single_steps(golden):
+    d = golden("liquid")
+    net = _build(d, "actor_seq")
+    x = torch.tensor(d["actor_seq_x"], device="cuda")
+    h = torch.tensor(d["actor_seq_h0"], device="cuda")
+    y, ht = net.forward_seq(x, h)
+    for t in range(x.shape[1]):
+        yt, h = net(x[:, t], h)
+        assert torch.equal(yt, y[:, t]) and torch.equal(h, ht[:, t])
+
+
+@pytest.mark.parametrize("B,T", [(1, 1), (31, 3), (33, 9), (257, 5), (4096, 32)])
+def test_ragged_batches_vs_oracle(golden, B, T):
+    """Batch sizes around the 32-row warp tiles, time lengths around the staging chunks; oracle = numpy fp64."""
+    d = golden("liquid")
+    net = _build(d, "actor_seq")
+    p = liquid_case_params(d, "actor_seq")
+    g = torch.Generator().manual_seed(B * 1000 + T)
+    x = torch.randn(B, T, 4, generator=g)
+    h0 = 0.5 * torch.randn(B, 8, generator=g)
+    ry = torch.randn(B, T, 2, generator=g)
+    rh = torch.randn(B, 8, generator=g)
+    yo, hto, caches = lo.liquid_seq_forward(p, x.numpy(), h0.numpy(), np.float64)
+    dh = np.zeros_like(hto)
+    dh[:, -1] = rh.numpy()
+    dxo, dh0o, go = lo.liquid_seq_backward(p, caches, ry.numpy(), dh, np.float64)
+    for flags in (0, 1):
+        net.kernel_flags = flags
+        net.zero_grad()
+        xc = x.cuda().requires_grad_(True)
+        hc = h0.cuda().requires_grad_(True)
+        y, ht, hl = net.forward_seq(xc, hc, return_last=True)
+        ((y * ry.cuda()).sum() + (hl * rh.cuda()).sum()).backward()
+        assert rel_err(y.detach().cpu().numpy(), yo) < FP32_RTOL
+        assert rel_err(ht.detach().cpu().numpy(), hto) < FP32_RTOL
+        assert rel_err(xc.grad.cpu().numpy(), dxo) < FP32_RTOL
+        assert rel_err(hc.grad.cpu().numpy(), dh0o) < FP32_RTOL
+        for k, pr in net.named_parameters():
+            assert rel_err(pr.grad.cpu().numpy(), go[k]) < FP32_RTOL, (k, flags)
+
+
+def test_full_size_properties():
+    """BASELINE config 3 at full size (B=65536, T=32): two independent kernels agree, gradients are linear in the
+    upstream gradient, and the run is bit-reproducible (no atomics on the specialised path)."""
+    import velora_b200 as vb
+    from velora_b200.models.lnn import LiquidNCPNetwork
+
+    vb.set_seed(64)
+    net = LiquidNCPNetwork(4, 20, 2, device=torch.device("cuda"))
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    B, T = 65536, 32
+    x = torch.randn(B, T, 4, device="cuda", generator=g)
+    ry = torch.randn(B, T, 2, device="cuda", generator=g)
+
+    def run(flags, scale):
+        net.kernel_flags = flags
+        net.zero_grad()
+        y, ht, hl = net.forward_seq(x, None, return_last=True)
+        ((y * ry).sum() * scale).backward()
+        return y.detach(), ht.detach(), torch.cat([p.grad.flatten() for p in net.parameters()])
+
+    y0, h0, g0 = run(0, 1.0)
+    y1, h1, g1 = run(1, 1.0)
+    assert rel_err(y0.cpu().numpy(), y1.cpu().numpy()) < 2e-6
+    assert rel_err(h0.cpu().numpy(), h1.cpu().numpy()) < 2e-6
+    assert rel_err(g0.cpu().numpy(), g1.cpu().numpy()) < FP32_RTOL
+    _, _, g2 = run(0, 2.0)
+    assert rel_err(g2.cpu().numpy(), 2.0 * g0.cpu().numpy()) < 1e-6
+    y3, h3, g3 = run(0, 1.0)
+    assert torch.equal(y0, y3) and torch.equal(h0, h3) and torch.equal(g0, g3)

@@ -1,0 +1,77 @@
+"""Parity of the CUDA NCPNetwork (critic) path with the reference goldens."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import liquid_oracle as lo
+from vb_testutil import FP32_RTOL, assert_close_to_reference, liquid_case_params, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _build(d, name):
+    import velora_b200 as vb
+    from velora_b200.models.lnn import NCPNetwork
+
+    i, n, o, sp, seed, B = d[f"{name}_meta"]
+    vb.set_seed(int(seed))
+    net = NCPNetwork(int(i), int(n), int(o), sparsity_level=float(sp), device=torch.device("cuda"))
+    net.load_state_dict({k: torch.tensor(v) for k, v in liquid_case_params(d, name).items()})
+    return net
+
+
+@pytest.mark.parametrize("name", ["critic_ct", "critic_disc", "small", "odd"])
+def test_ncp_vs_reference(golden, name):
+    d = golden("ncp")
+    net = _build(d, name)
+    x = torch.tensor(d[f"{name}_x"], device="cuda", requires_grad=True)
+    r = torch.tensor(d[f"{name}_r"], device="cuda")
+    y = net(x)
+    assert list(y.shape) == list(d[f"{name}_api_shape"])          # B == 1 squeeze (ncp.py:325-326)
+    y2 = y.reshape(r.shape)
+    assert_close_to_reference(y2.detach().cpu().numpy(), d[f"{name}_f32_y"], d[f"{name}_f64_y"], "y")
+    (y2 * r).sum().backward()
+    assert_close_to_reference(x.grad.cpu().numpy(), d[f"{name}_f32_dx"], d[f"{name}_f64_dx"], "dx")
+    for k, p in net.named_parameters():
+        g = p.grad.cpu().numpy()
+        assert_close_to_reference(g, d[f"{name}_f32_grad_{k}"], d[f"{name}_f64_grad_{k}"], f"grad {k}")
+        if k.endswith("weight"):
+            mask = net.state_dict()[k.replace("weight", "mask")].cpu().numpy()
+            assert np.all(g[mask == 0] == 0.0)
+    with pytest.raises(ValueError):
+        net(torch.zeros(2, 2, 2))
+
+
+@pytest.mark.parametrize("B", [1, 33, 1000, 65536])
+def test_ncp_ragged_vs_oracle(golden, B):
+    d = golden("ncp")
+    net = _build(d, "critic_ct")
+    p = liquid_case_params(d, "critic_ct")
+    g = torch.Generator().manual_seed(B)
+    x = torch.randn(B, 5, generator=g)
+    r = torch.randn(B, 1, generator=g)
+    yo, cache = lo.ncp_forward(p, x.numpy(), np.float64)
+    dxo, go = lo.ncp_backward(p, cache, r.numpy(), np.float64)
+    xc = x.cuda().requires_grad_(True)
+    y = net(xc).reshape(B, 1)
+    (y * r.cuda()).sum().backward()
+    assert rel_err(y.detach().cpu().numpy(), yo) < FP32_RTOL
+    assert rel_err(xc.grad.cpu().numpy(), dxo) < FP32_RTOL
+    for k, pr in net.named_parameters():
+        assert rel_err(pr.grad.cpu().numpy(), go[k]) < FP32_RTOL, k
+
+
+def test_ncp_script_and_determinism(golden):
+    d = golden("ncp")
+    net = _build(d, "critic_ct")
+    x = torch.tensor(d["critic_ct_x"], device="cuda")
+    twin = torch.jit.script(copy.deepcopy(net))
+    assert torch.equal(twin(x), net(x))
+    outs = []
+    for _ in range(2):
+        net.zero_grad()
+        net(x).sum().backward()
+        outs.append(torch.cat([p.grad.flatten() for p in net.parameters()]))
+    assert torch.equal(outs[0], outs[1])

@@ -1,0 +1,119 @@
+"""Pre-allocated ring buffer of transitions (mirror of velora/buffer/base.py:30-279).
+
+Storage layout in HBM: six row-major float32 arrays [capacity, d] (d = S, A, 1, S, 1, H) - 76 B per transition for
+the (4, 1, 8) shapes of BASELINE configs 1/2/5 - exactly the reference's state_dict, so checkpoints interchange.
+"""
+from __future__ import annotations
+
+import json
+from abc import abstractmethod
+from pathlib import Path
+from typing import Any, Dict, Literal
+
+import torch
+
+from velora_b200.buffer.experience import BatchExperience
+
+MetaDataKeys = Literal["capacity", "state_dim", "action_dim", "hidden_dim", "position", "size", "device"]
+BufferKeys = Literal["states", "actions", "rewards", "next_states", "dones", "hiddens"]
+FIELDS = ("states", "actions", "rewards", "next_states", "dones", "hiddens")
+
+
+class BufferBase:
+    def __init__(self, capacity: int, state_dim: int, action_dim: int, hidden_dim: int, *, device: torch.device | None = None) -> None:
+        self.capacity = capacity
+        self.state_dim = state_dim
+        self.action_dim = action_dim
+        self.hidden_dim = hidden_dim
+        self.device = device
+
+        self.position = 0   # next row to write
+        self.size = 0       # rows holding data
+
+        widths = dict(states=state_dim, actions=action_dim, rewards=1, next_states=state_dim, dones=1, hiddens=hidden_dim)
+        for name in FIELDS:
+            setattr(self, name, torch.zeros((capacity, widths[name]), device=device))
+
+    # ------------------------------------------------------------------ writes
+    def add(self, state: torch.Tensor, action: torch.Tensor, reward: float, next_state: torch.Tensor, done: bool, hidden: torch.Tensor) -> None:
+        """Appends one transition (overwriting the oldest once full)."""
+        i = self.position
+        self.states[i] = state.to(torch.float32)
+        self.actions[i] = action
+        self.rewards[i] = reward
+        self.next_states[i] = next_state.to(torch.float32)
+        self.dones[i] = done
+        self.hiddens[i] = hidden
+        self.position = (i + 1) % self.capacity
+        self.size = min(self.size + 1, self.capacity)
+
+    def add_multi(self, states: torch.Tensor, actions: torch.Tensor, rewards: torch.Tensor, next_states: torch.Tensor,
+                  dones: torch.Tensor, hiddens: torch.Tensor) -> None:
+        """Appends a batch of transitions with wrap-around."""
+        n = states.shape[0]
+        end = self.position + n
+        rows = torch.arange(self.position, end) % self.capacity
+
+        def col(t: torch.Tensor) -> torch.Tensor:
+            return t.unsqueeze(-1) if t.dim() == 1 else t
+
+        f32 = torch.float32
+        self.states[rows] = states.to(f32)
+        self.actions[rows] = col(actions).to(f32)
+        self.rewards[rows] = col(rewards).to(f32)
+        self.next_states[rows] = next_states.to(f32)
+        self.dones[rows] = col(dones).to(f32)
+        self.hiddens[rows] = hiddens
+        self.position = end % self.capacity
+        self.size = min(self.size + n, self.capacity)
+
+    @abstractmethod
+    def sample(self) -> BatchExperience:
+        pass  # pragma: no cover
+
+    def __len__(self) -> int:
+        return self.size
+
+    # ------------------------------------------------------------------ persistence
+    def metadata(self) -> Dict[MetaDataKeys, Any]:
+        return {
+            "capacity": self.capacity,
+            "state_dim": self.state_dim,
+            "action_dim": self.action_dim,
+            "hidden_dim": self.hidden_dim,
+            "position": self.position,
+            "size": self.size,
+            "device": str(self.device) if self.device else None,
+        }
+
+    def state_dict(self) -> Dict[BufferKeys, torch.Tensor]:
+        return {name: getattr(self, name) for name in FIELDS}
+
+    def save(self, dirpath: str | Path, prefix: str = "buffer_") -> None:
+        """Writes `<prefix>metadata.json` and `<prefix>state.safetensors` (the reference's on-disk format)."""
+        from safetensors.torch import save_file
+
+        root = Path(dirpath)
+        root.mkdir(parents=True, exist_ok=True)
+        save_file(self.state_dict(), Path(root, f"{prefix}state").with_suffix(".safetensors"))
+        with Path(root, f"{prefix}metadata").with_suffix(".json").open("w") as f:
+            f.write(json.dumps(self.metadata(), indent=2))
+
+    @classmethod
+    def load(cls, state_path: str | Path, metadata: Dict[MetaDataKeys, Any]):
+        from safetensors.torch import load_file
+
+        device = metadata["device"] or "cpu"
+        buffer = cls(
+            capacity=metadata["capacity"],
+            state_dim=metadata["state_dim"],
+            action_dim=metadata["action_dim"],
+            hidden_dim=metadata["hidden_dim"],
+            device=torch.device(device) if device else None,
+        )
+        buffer.position = metadata["position"]
+        buffer.size = metadata["size"]
+        data = load_file(Path(state_path).with_suffix(".safetensors"), device)
+        for name in FIELDS:
+            setattr(buffer, name, data[name])
+        return buffer

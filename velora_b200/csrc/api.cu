@@ -1,0 +1,150 @@
+// C-ABI entry points that dispatch between the specialised and the generic kernels, plus error/query plumbing.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace vb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+static int g_sms[64];
+static int g_smem[64];
+static bool g_props[64];
+
+static void load_props(int dev) {
+    if (g_props[dev & 63]) return;
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess) g_sms[dev & 63] = v;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) == cudaSuccess) g_smem[dev & 63] = v;
+    g_props[dev & 63] = true;
+}
+int device_sms() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+    load_props(dev);
+    return g_sms[dev & 63];
+}
+int device_max_smem_optin() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+    load_props(dev);
+    return g_smem[dev & 63];
+}
+
+namespace small {
+bool has_fast_path(int I, int Ni, int Nc, int O);
+int fwd(const float*, const float*, const float*, float*, float*, int64_t, int, int, int, int, int, cudaStream_t);
+int bwd(const float*, const float*, const float*, const float*, const float*, const float*, const float*, float*, float*, float*,
+        int64_t, int, int, int, int, int, void*, int64_t, cudaStream_t);
+int64_t bwd_workspace_bytes(int, int, int, int, int64_t);
+}  // namespace small
+namespace generic {
+int liquid_fwd(const float*, const float*, const float*, float*, float*, int64_t, int, int, int, int, int, cudaStream_t);
+int64_t liquid_bwd_workspace_bytes(int, int, int, int);
+int liquid_bwd(const float*, const float*, const float*, const float*, const float*, const float*, const float*, float*, float*, float*,
+               int64_t, int, int, int, int, int, void*, int64_t, cudaStream_t);
+int ncp_fwd(const float*, const float*, float*, int64_t, int, int, int, int, cudaStream_t);
+int64_t ncp_bwd_workspace_bytes(int, int, int, int);
+int ncp_bwd(const float*, const float*, const float*, float*, float*, int64_t, int, int, int, int, void*, int64_t, cudaStream_t);
+}  // namespace generic
+
+}  // namespace vb
+
+using namespace vb;
+
+extern "C" const char* vb_last_error(void) { return g_err; }
+
+extern "C" int vb_query(int what) {
+    switch (what) {
+        case VB_Q_ABI_VERSION: return VB_ABI_VERSION;
+        case VB_Q_BUILT_SM: return 100;
+        case VB_Q_DEVICE_SMS: return device_sms();
+        case VB_Q_DEVICE_CC: {
+            int dev = 0, mj = 0, mn = 0;
+            if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+            cudaDeviceGetAttribute(&mj, cudaDevAttrComputeCapabilityMajor, dev);
+            cudaDeviceGetAttribute(&mn, cudaDevAttrComputeCapabilityMinor, dev);
+            return mj * 10 + mn;
+        }
+        case VB_Q_MAX_SMEM_OPTIN: return device_max_smem_optin();
+        default: set_error("vb_query: unknown key %d", what); return VB_ERR_BAD_DIMS;
+    }
+}
+
+extern "C" int vb_liquid_has_fast_path(int I, int Ni, int Nc, int O) { return small::has_fast_path(I, Ni, Nc, O) ? 1 : 0; }
+
+static inline int64_t max64(int64_t a, int64_t b) { return a > b ? a : b; }
+
+extern "C" int64_t vb_liquid_fwd_workspace_bytes(int I, int Ni, int Nc, int O, int64_t B, int T) {
+    (void)B; (void)T;
+    if (!dims_ok(I, Ni, Nc, O)) return VB_ERR_BAD_DIMS;
+    return 16;
+}
+extern "C" int64_t vb_liquid_bwd_workspace_bytes(int I, int Ni, int Nc, int O, int64_t B, int T) {
+    (void)T;
+    if (!dims_ok(I, Ni, Nc, O)) return VB_ERR_BAD_DIMS;
+    int64_t g = generic::liquid_bwd_workspace_bytes(I, Ni, Nc, O);
+    int64_t s = small::has_fast_path(I, Ni, Nc, O) ? small::bwd_workspace_bytes(I, Ni, Nc, O, B) : 0;
+    return max64(g, s);
+}
+extern "C" int64_t vb_ncp_bwd_workspace_bytes(int I, int Ni, int Nc, int O, int64_t B) {
+    (void)B;
+    if (!dims_ok(I, Ni, Nc, O)) return VB_ERR_BAD_DIMS;
+    return generic::ncp_bwd_workspace_bytes(I, Ni, Nc, O);
+}
+
+extern "C" int vb_liquid_fwd(const float* packed, const float* x, const float* h0, float* y, float* h_traj,
+                             int64_t B, int T, int I, int Ni, int Nc, int O,
+                             void* workspace, int64_t workspace_bytes, int flags, void* stream) {
+    (void)workspace; (void)workspace_bytes;
+    VB_CHECK_ARG(dims_ok(I, Ni, Nc, O) && B >= 0 && T >= 1, VB_ERR_BAD_DIMS, "vb_liquid_fwd: bad dims B=%lld T=%d (%d,%d,%d,%d)", (long long)B, T, I, Ni, Nc, O);
+    VB_CHECK_ARG(packed && x && y && h_traj, VB_ERR_NULL_POINTER, "vb_liquid_fwd: null pointer");
+    if (B == 0) return 0;
+    if (!(flags & VB_FLAG_FORCE_GENERIC) && small::has_fast_path(I, Ni, Nc, O))
+        return small::fwd(packed, x, h0, y, h_traj, B, T, I, Ni, Nc, O, (cudaStream_t)stream);
+    return generic::liquid_fwd(packed, x, h0, y, h_traj, B, T, I, Ni, Nc, O, (cudaStream_t)stream);
+}
+
+extern "C" int vb_liquid_bwd(const float* packed, const float* x, const float* h0, const float* h_traj,
+                             const float* dy, const float* dh_traj, const float* dh_last,
+                             float* dx, float* dh0, float* dpacked,
+                             int64_t B, int T, int I, int Ni, int Nc, int O,
+                             void* workspace, int64_t workspace_bytes, int flags, void* stream) {
+    VB_CHECK_ARG(dims_ok(I, Ni, Nc, O) && B >= 0 && T >= 1, VB_ERR_BAD_DIMS, "vb_liquid_bwd: bad dims");
+    VB_CHECK_ARG(packed && x && h_traj && dy && dpacked, VB_ERR_NULL_POINTER, "vb_liquid_bwd: null pointer");
+    if (B == 0) {
+        VB_CUDA(cudaMemsetAsync(dpacked, 0, (size_t)LiquidLayout(I, Ni, Nc, O).f_total * 4, (cudaStream_t)stream));
+        return 0;
+    }
+    if (!(flags & VB_FLAG_FORCE_GENERIC) && small::has_fast_path(I, Ni, Nc, O))
+        return small::bwd(packed, x, h0, h_traj, dy, dh_traj, dh_last, dx, dh0, dpacked, B, T, I, Ni, Nc, O, workspace, workspace_bytes, (cudaStream_t)stream);
+    return generic::liquid_bwd(packed, x, h0, h_traj, dy, dh_traj, dh_last, dx, dh0, dpacked, B, T, I, Ni, Nc, O, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int vb_ncp_fwd(const float* packed, const float* x, float* y, int64_t B, int I, int Ni, int Nc, int O, int flags, void* stream) {
+    (void)flags;
+    VB_CHECK_ARG(dims_ok(I, Ni, Nc, O) && B >= 0, VB_ERR_BAD_DIMS, "vb_ncp_fwd: bad dims");
+    VB_CHECK_ARG(packed && x && y, VB_ERR_NULL_POINTER, "vb_ncp_fwd: null pointer");
+    if (B == 0) return 0;
+    return generic::ncp_fwd(packed, x, y, B, I, Ni, Nc, O, (cudaStream_t)stream);
+}
+
+extern "C" int vb_ncp_bwd(const float* packed, const float* x, const float* dy, float* dx, float* dpacked,
+                          int64_t B, int I, int Ni, int Nc, int O, void* workspace, int64_t workspace_bytes, int flags, void* stream) {
+    (void)flags;
+    VB_CHECK_ARG(dims_ok(I, Ni, Nc, O) && B >= 0, VB_ERR_BAD_DIMS, "vb_ncp_bwd: bad dims");
+    VB_CHECK_ARG(packed && x && dy && dpacked, VB_ERR_NULL_POINTER, "vb_ncp_bwd: null pointer");
+    if (B == 0) {
+        VB_CUDA(cudaMemsetAsync(dpacked, 0, (size_t)NcpLayout(I, Ni, Nc, O).f_total * 4, (cudaStream_t)stream));
+        return 0;
+    }
+    return generic::ncp_bwd(packed, x, dy, dx, dpacked, B, I, Ni, Nc, O, workspace, workspace_bytes, (cudaStream_t)stream);
+}

@@ -1,0 +1,20 @@
+#!/bin/bash
+# Builds libvelora_b200.so in-tree for sm_100a (cross-compiles without a GPU).  Used by __graft_entry__.build().
+set -e
+cd "$(dirname "$0")"
+OUT=../lib
+mkdir -p "$OUT"
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr -Xptxas -v"
+SRCS="api.cu pack.cu liquid_small.cu generic.cu gather.cu"
+OBJS=""
+for s in $SRCS; do
+  o="$OUT/${s%.cu}.o"
+  if [ ! -f "$o" ] || [ "$s" -nt "$o" ] || [ common.cuh -nt "$o" ] || [ tile.cuh -nt "$o" ] || [ ../../include/velora_b200.h -nt "$o" ]; then
+    echo "nvcc $s"
+    $NVCC $FLAGS -c "$s" -o "$o" 2> "$OUT/${s%.cu}.ptxas.log" || { cat "$OUT/${s%.cu}.ptxas.log"; exit 1; }
+  fi
+  OBJS="$OBJS $o"
+done
+$NVCC -shared -o "$OUT/libvelora_b200.so" $OBJS -lcudart
+echo "built $OUT/libvelora_b200.so"

@@ -1,0 +1,149 @@
+// Shared device/host helpers for libvelora_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/velora_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "velora_b200 kernels are written for sm_100a (B200) only"
+#endif
+
+namespace vb {
+
+// ------------------------------------------------------------------------------------------------ errors
+void set_error(const char* fmt, ...);
+
+#define VB_CHECK_ARG(cond, code, ...)          \
+    do {                                       \
+        if (!(cond)) {                         \
+            vb::set_error(__VA_ARGS__);        \
+            return (code);                     \
+        }                                      \
+    } while (0)
+
+#define VB_CUDA(expr)                                                                             \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            vb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return (int)_e;                                                                       \
+        }                                                                                         \
+    } while (0)
+
+#define VB_LAUNCH_CHECK()                                                                         \
+    do {                                                                                          \
+        cudaError_t _e = cudaGetLastError();                                                      \
+        if (_e != cudaSuccess) {                                                                  \
+            vb::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return (int)_e;                                                                       \
+        }                                                                                         \
+    } while (0)
+
+int device_sms();
+int device_max_smem_optin();
+
+__host__ __device__ constexpr int ceil4(int v) { return (v + 3) & ~3; }
+
+// ------------------------------------------------------------------------------------------------ packed layouts
+// Offsets (in floats) of the packed liquid parameter block; see include/velora_b200.h.
+struct LiquidLayout {
+    int I, Ni, Nc, O;
+    int NIp, NCp, Op, Ip, K, Kp, H4;   // H4 = 4*NCp = width of one wh_t row
+    // F section
+    int win_t, b_in, wh_t, b_h, wout, b_out, f_total;
+    // D section
+    int win, wh, wout_t, total;
+    __host__ __device__ constexpr LiquidLayout(int I_, int Ni_, int Nc_, int O_)
+        : I(I_), Ni(Ni_), Nc(Nc_), O(O_),
+          NIp(ceil4(Ni_)), NCp(ceil4(Nc_)), Op(ceil4(O_)), Ip(ceil4(I_)), K(Ni_ + Nc_), Kp(ceil4(Ni_ + Nc_)),
+          H4(4 * ceil4(Nc_)),
+          win_t(0),
+          b_in(win_t + I_ * ceil4(Ni_)),
+          wh_t(b_in + ceil4(Ni_)),
+          b_h(wh_t + (Ni_ + Nc_) * 4 * ceil4(Nc_)),
+          wout(b_h + 4 * ceil4(Nc_)),
+          b_out(wout + O_ * ceil4(Nc_)),
+          f_total(b_out + ceil4(O_)),
+          win(f_total),
+          wh(win + Ni_ * ceil4(I_)),
+          wout_t(wh + 4 * ceil4(Nc_) * ceil4(Ni_ + Nc_)),
+          total(wout_t + Nc_ * ceil4(O_)) {}
+};
+
+// Three-layer NCPNetwork block.
+struct NcpLayout {
+    int I, Ni, Nc, O;
+    int NIp, NCp, Op, Ip;
+    int w1_t, b1, w2_t, b2, w3, b3, f_total;
+    int w1, w2, w3_t, total;
+    __host__ __device__ constexpr NcpLayout(int I_, int Ni_, int Nc_, int O_)
+        : I(I_), Ni(Ni_), Nc(Nc_), O(O_),
+          NIp(ceil4(Ni_)), NCp(ceil4(Nc_)), Op(ceil4(O_)), Ip(ceil4(I_)),
+          w1_t(0),
+          b1(w1_t + I_ * ceil4(Ni_)),
+          w2_t(b1 + ceil4(Ni_)),
+          b2(w2_t + Ni_ * ceil4(Nc_)),
+          w3(b2 + ceil4(Nc_)),
+          b3(w3 + O_ * ceil4(Nc_)),
+          f_total(b3 + ceil4(O_)),
+          w1(f_total),
+          w2(w1 + Ni_ * ceil4(I_)),
+          w3_t(w2 + Nc_ * ceil4(Ni_)),
+          total(w3_t + Nc_ * ceil4(O_)) {}
+};
+
+inline bool dims_ok(int I, int Ni, int Nc, int O) { return I > 0 && Ni > 0 && Nc > 0 && O > 0; }
+
+// ------------------------------------------------------------------------------------------------ device math
+#ifdef __CUDACC__
+constexpr float kLog2e = 1.4426950408889634f;
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// tanh(x) = 1 - 2 / (e^{2x} + 1).  One ex2 + one rcp; |abs err| ~ 1e-7 (the measure that matters: outputs are
+// compared in relative L2 norm).  tanh.approx (2^-11) is far too coarse for the 1e-5 contract.
+__device__ __forceinline__ float tanh_f(float x) {
+    float e = ex2_approx(fminf(x, 15.0f) * (2.0f * kLog2e));
+    return 1.0f - 2.0f * rcp_approx(e + 1.0f);
+}
+__device__ __forceinline__ float sigmoid_f(float x) {
+    float e = ex2_approx(fminf(-x, 80.0f) * kLog2e);
+    return rcp_approx(1.0f + e);
+}
+// Mish(x) = x * tanh(softplus(x)) = x * w / (w + 2), w = e^x (e^x + 2).
+__device__ __forceinline__ float mish_f(float x) {
+    float n = ex2_approx(fminf(x, 20.0f) * kLog2e);
+    float w = n * (n + 2.0f);
+    return x * (w * rcp_approx(w + 2.0f));
+}
+// Mish and its derivative t + x * sigmoid(x) * (1 - t^2), t = tanh(softplus x) = w/(w+2),
+// sigmoid(x) = n/(1+n), 1 - t^2 = 4 (w+1) / (w+2)^2.  The two reciprocals share one MUFU.
+__device__ __forceinline__ float mish_fwd_grad(float x, float& dmish) {
+    float n = ex2_approx(fminf(x, 20.0f) * kLog2e);
+    float w = n * (n + 2.0f);
+    float w2 = w + 2.0f;
+    float n1 = n + 1.0f;
+    float q = rcp_approx(w2 * n1);   // 1 / ((w+2)(n+1))
+    float r = q * n1;                // 1 / (w+2)
+    float sig = n * (q * w2);        // n / (n+1)
+    float t = w * r;
+    float omt2 = 4.0f * (w + 1.0f) * r * r;
+    dmish = fmaf(x * sig, omt2, t);
+    return x * t;
+}
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+#endif  // __CUDACC__
+
+}  // namespace vb

@@ -1,0 +1,214 @@
+"""torch.autograd.Function wrappers over the C ABI (the "thin C-ABI torch.autograd.Function extension").
+
+LiquidSeqFn   T-fold LiquidNCPNetwork.forward + its backward    (reference: velora/models/lnn/ncp.py:129-178)
+NcpFn         NCPNetwork.forward + its backward                 (reference: velora/models/lnn/ncp.py:299-328)
+gather_rows   ReplayBuffer.sample's six gathers                 (reference: velora/buffer/replay.py:81-88)
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from . import dataparallel as _dp
+
+HEAD_NAMES = ("g_head", "h_head", "f_head_to_g", "f_head_to_h", "proj")
+
+
+def _f32c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        t = t.to(torch.float32)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _rowmajor(m: torch.Tensor, dev: torch.device) -> torch.Tensor:
+    if m.device != dev:
+        m = m.to(dev)
+    return m if m.is_contiguous() else m.contiguous()
+
+
+class LiquidSeqFn(torch.autograd.Function):
+    """y[B,T,O], h_traj[B,T,Nc], h_last[B,Nc] = liquid(x[B,T,I], h0[B,Nc] | None; 7 masked layers)."""
+
+    @staticmethod
+    def forward(ctx, x, h0, dims, flags, masks, *params):
+        # params: w_in, b_in, (w,b) x5 heads, w_out, b_out ; masks: m_in, m_head x5, m_out (not differentiable)
+        I, Ni, Nc, O = dims
+        L = _lib.lib()
+        _lib.require_cuda(x, "LiquidNCPNetwork.forward")
+        dev = x.device
+        x = _f32c(x)
+        h0c = _f32c(h0)
+        B, T, _ = x.shape
+        params = [_f32c(p.detach()) for p in params]
+        w_in, b_in = params[0], params[1]
+        w_h = [params[2 + 2 * k] for k in range(5)]
+        b_h = [params[3 + 2 * k] for k in range(5)]
+        w_out, b_out = params[12], params[13]
+        # wiring masks are stored as transposed views (abs(mask.T) keeps the strides): the kernels want row-major
+        masks = tuple(_rowmajor(m, dev) for m in masks)
+        m_in, m_h, m_out = masks[0], list(masks[1:6]), masks[6]
+        with torch.cuda.device(dev):
+            st = _lib.stream_ptr(dev)
+            packed = torch.empty(L.vb_liquid_packed_floats(I, Ni, Nc, O), dtype=torch.float32, device=dev)
+            _lib.check(
+                L.vb_liquid_pack(
+                    _lib.ptr(w_in), _lib.ptr(b_in), _lib.ptr(m_in), _lib.mask_type(m_in),
+                    _lib.ptr_array(w_h), _lib.ptr_array(b_h), _lib.ptr_array(m_h), _lib.mask_type(m_h[0]),
+                    _lib.ptr(w_out), _lib.ptr(b_out), _lib.ptr(m_out), _lib.mask_type(m_out),
+                    I, Ni, Nc, O, _lib.ptr(packed), st,
+                ),
+                "vb_liquid_pack",
+            )
+            y = torch.empty((B, T, O), dtype=torch.float32, device=dev)
+            h_traj = torch.empty((B, T, Nc), dtype=torch.float32, device=dev)
+            _lib.check(
+                L.vb_liquid_fwd(_lib.ptr(packed), _lib.ptr(x), _lib.ptr(h0c), _lib.ptr(y), _lib.ptr(h_traj),
+                                B, T, I, Ni, Nc, O, None, 0, flags, st),
+                "vb_liquid_fwd",
+            )
+        h_last = h_traj[:, T - 1].clone()
+        ctx.dims, ctx.flags, ctx.masks = dims, flags, masks
+        ctx.has_h0 = h0 is not None
+        ctx.save_for_backward(x, h0c if h0c is not None else x.new_empty(0), h_traj, packed)
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable()
+        return y, h_traj, h_last
+
+    @staticmethod
+    def backward(ctx, dy, dh_traj, dh_last):
+        x, h0, h_traj, packed = ctx.saved_tensors
+        I, Ni, Nc, O = ctx.dims
+        masks = ctx.masks
+        L = _lib.lib()
+        dev = x.device
+        B, T, _ = x.shape
+        h0p = h0 if ctx.has_h0 else None
+        dy = _f32c(dy) if dy is not None else torch.zeros((B, T, O), dtype=torch.float32, device=dev)
+        dh_traj = _f32c(dh_traj)
+        dh_last = _f32c(dh_last)
+        need_x = ctx.needs_input_grad[0]
+        need_h0 = ctx.has_h0 and ctx.needs_input_grad[1]
+        with torch.cuda.device(dev):
+            st = _lib.stream_ptr(dev)
+            dx = torch.empty_like(x) if need_x else None
+            dh0 = torch.empty((B, Nc), dtype=torch.float32, device=dev) if need_h0 else None
+            n_grad = L.vb_liquid_grad_floats(I, Ni, Nc, O)
+            dpacked = torch.empty(n_grad, dtype=torch.float32, device=dev)
+            ws_bytes = L.vb_liquid_bwd_workspace_bytes(I, Ni, Nc, O, B, T)
+            ws = torch.empty(max(int(ws_bytes), 16), dtype=torch.uint8, device=dev)
+            _lib.check(
+                L.vb_liquid_bwd(_lib.ptr(packed), _lib.ptr(x), _lib.ptr(h0p), _lib.ptr(h_traj), _lib.ptr(dy),
+                                _lib.ptr(dh_traj), _lib.ptr(dh_last), _lib.ptr(dx), _lib.ptr(dh0), _lib.ptr(dpacked),
+                                B, T, I, Ni, Nc, O, _lib.ptr(ws), ws.numel(), ctx.flags, st),
+                "vb_liquid_bwd",
+            )
+            # data-parallel: ONE collective over the flat pre-masked gradient block
+            _dp.maybe_allreduce(dpacked)
+            need = ctx.needs_input_grad[5:]
+            shapes = [(Ni, I), (Ni,)] + [(Nc, Ni + Nc), (Nc,)] * 5 + [(O, Nc), (O,)]
+            grads: List[Optional[torch.Tensor]] = [
+                torch.empty(s, dtype=torch.float32, device=dev) if need[k] else None for k, s in enumerate(shapes)
+            ]
+            m_in, m_h, m_out = masks[0], list(masks[1:6]), masks[6]
+            _lib.check(
+                L.vb_liquid_unpack_grads(
+                    _lib.ptr(dpacked), _lib.ptr(m_in), _lib.mask_type(m_in), _lib.ptr_array(m_h), _lib.mask_type(m_h[0]),
+                    _lib.ptr(m_out), _lib.mask_type(m_out),
+                    _lib.ptr(grads[0]), _lib.ptr(grads[1]),
+                    _lib.ptr_array([grads[2 + 2 * k] for k in range(5)]), _lib.ptr_array([grads[3 + 2 * k] for k in range(5)]),
+                    _lib.ptr(grads[12]), _lib.ptr(grads[13]), I, Ni, Nc, O, 0, st,
+                ),
+                "vb_liquid_unpack_grads",
+            )
+        return (dx, dh0, None, None, None, *grads)
+
+
+class NcpFn(torch.autograd.Function):
+    """y[B,O] = ncp(x[B,I]; three masked layers)."""
+
+    @staticmethod
+    def forward(ctx, x, dims, flags, masks, *params):
+        I, Ni, Nc, O = dims
+        L = _lib.lib()
+        _lib.require_cuda(x, "NCPNetwork.forward")
+        dev = x.device
+        x = _f32c(x)
+        B = x.shape[0]
+        params = [_f32c(p.detach()) for p in params]
+        w = [params[0], params[2], params[4]]
+        b = [params[1], params[3], params[5]]
+        masks = tuple(_rowmajor(m, dev) for m in masks)
+        with torch.cuda.device(dev):
+            st = _lib.stream_ptr(dev)
+            packed = torch.empty(L.vb_ncp_packed_floats(I, Ni, Nc, O), dtype=torch.float32, device=dev)
+            _lib.check(
+                L.vb_ncp_pack(_lib.ptr_array(w), _lib.ptr_array(b), _lib.ptr_array(list(masks)), _lib.mask_type(masks[0]),
+                              I, Ni, Nc, O, _lib.ptr(packed), st),
+                "vb_ncp_pack",
+            )
+            y = torch.empty((B, O), dtype=torch.float32, device=dev)
+            _lib.check(L.vb_ncp_fwd(_lib.ptr(packed), _lib.ptr(x), _lib.ptr(y), B, I, Ni, Nc, O, flags, st), "vb_ncp_fwd")
+        ctx.dims, ctx.flags, ctx.masks = dims, flags, masks
+        ctx.save_for_backward(x, packed)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, packed = ctx.saved_tensors
+        I, Ni, Nc, O = ctx.dims
+        masks = ctx.masks
+        L = _lib.lib()
+        dev = x.device
+        B = x.shape[0]
+        dy = _f32c(dy)
+        with torch.cuda.device(dev):
+            st = _lib.stream_ptr(dev)
+            dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+            dpacked = torch.empty(L.vb_ncp_grad_floats(I, Ni, Nc, O), dtype=torch.float32, device=dev)
+            ws_bytes = L.vb_ncp_bwd_workspace_bytes(I, Ni, Nc, O, B)
+            ws = torch.empty(max(int(ws_bytes), 16), dtype=torch.uint8, device=dev)
+            _lib.check(
+                L.vb_ncp_bwd(_lib.ptr(packed), _lib.ptr(x), _lib.ptr(dy), _lib.ptr(dx), _lib.ptr(dpacked),
+                             B, I, Ni, Nc, O, _lib.ptr(ws), ws.numel(), ctx.flags, st),
+                "vb_ncp_bwd",
+            )
+            _dp.maybe_allreduce(dpacked)
+            need = ctx.needs_input_grad[4:]
+            shapes = [(Ni, I), (Ni,), (Nc, Ni), (Nc,), (O, Nc), (O,)]
+            grads = [torch.empty(s, dtype=torch.float32, device=dev) if need[k] else None for k, s in enumerate(shapes)]
+            _lib.check(
+                L.vb_ncp_unpack_grads(_lib.ptr(dpacked), _lib.ptr_array(list(masks)), _lib.mask_type(masks[0]),
+                                      _lib.ptr_array([grads[0], grads[2], grads[4]]), _lib.ptr_array([grads[1], grads[3], grads[5]]),
+                                      I, Ni, Nc, O, 0, st),
+                "vb_ncp_unpack_grads",
+            )
+        return (dx, None, None, None, *grads)
+
+
+def gather_rows(arrays: Sequence[torch.Tensor], indices: torch.Tensor, n_rows: int) -> Tuple[torch.Tensor, ...]:
+    """out[k] = arrays[k][indices] for 2-D float32 CUDA arrays sharing dim 0, in one launch."""
+    L = _lib.lib()
+    dev = arrays[0].device
+    _lib.require_cuda(arrays[0], "ReplayBuffer.sample")
+    if indices.dtype != torch.int64 or indices.device != dev or not indices.is_contiguous():
+        indices = indices.to(device=dev, dtype=torch.int64).contiguous()
+    B = indices.numel()
+    outs, widths = [], []
+    for a in arrays:
+        if a.dtype != torch.float32 or not a.is_contiguous() or a.dim() != 2 or a.device != dev:
+            raise ValueError("gather_rows: arrays must be contiguous 2-D float32 tensors on one CUDA device")
+        outs.append(torch.empty((B, a.shape[1]), dtype=torch.float32, device=dev))
+        widths.append(a.shape[1])
+    with torch.cuda.device(dev):
+        rf = (C.c_int * len(widths))(*widths)
+        _lib.check(
+            L.vb_gather_rows(_lib.ptr_array(list(arrays)), _lib.ptr_array(outs), rf, len(widths), _lib.ptr(indices), B,
+                             int(n_rows), _lib.stream_ptr(dev)),
+            "vb_gather_rows",
+        )
+    return tuple(outs)
