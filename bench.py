@@ -1,0 +1,360 @@
+"""Benchmark of the liquid-cell hot path (BASELINE.json metric: liquid-cell fwd+bwd sample-steps/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE config 3): set_seed(64); LiquidNCPNetwork(4, 20, 2); x ~ N(0,1) [65536, 32, 4]
+fp32 per GPU, h0 = None; one step = forward_seq + backward of  sum(y * r_y) + sum(h_T * r_h)  (r ~ N(0,1)),
+including the parameter-gradient reduction (and, for N > 1, the one NCCL all-reduce of the flat gradient block).
+Weak scaling: every rank owns 65536 batch rows.
+
+One JSON line on stdout (rank 0).  `value` is measured with inputs resident in HBM; `e2e` goes through the same
+public API with pinned HOST inputs, H2D/D2H copies inside the timed region; `roofline` is the dominant (backward)
+kernel against the measured HBM peak; `cpu_baseline` is the oracle's torch-CPU port of the reference timed on this
+box's host cores.  `--impl reference` times that port alone (the reference is Python and cannot travel here).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "liquid_cell_fwd_bwd_sample_steps_per_s"
+UNIT = "sample-steps/s"
+SHAPE = dict(I=4, N=20, O=2, Ni=12, Nc=8)
+ALGO_BYTES_FWD = 4 * (SHAPE["I"] + SHAPE["O"] + SHAPE["Nc"])            # read x_t, write y_t, write h_t
+ALGO_BYTES_BWD = 4 * (2 * SHAPE["I"] + SHAPE["O"] + SHAPE["Nc"])        # read x_t, h_{t-1}, dy_t; write dx_t
+
+
+def algo_bytes_step(T: int) -> float:
+    return ALGO_BYTES_FWD + ALGO_BYTES_BWD + 12.0 * SHAPE["Nc"] / T      # + h0/dh_T/dh0 once per sequence (131 B @ T=32)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed regions run."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        self.active = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self.stop_flag:
+            if self.active:
+                try:
+                    self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                    try:
+                        mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    except Exception:
+                        mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    for bit, name in names.items():
+                        if mask & bit:
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+            time.sleep(0.004)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {
+            "sm_mhz": s[len(s) // 2] if s else None,
+            "sm_max_mhz": self.max_mhz,
+            "reasons": sorted(self.reasons),
+            "samples": len(s),
+        }
+
+
+def cpu_port_step_fn(B: int, T: int, threads: int):
+    """The oracle's torch-CPU port of the reference (op for op the reference's ATen sequence), fwd + bwd."""
+    import torch
+
+    import velora_b200 as vb
+    from oracle import liquid_oracle as lo
+    from velora_b200.models.lnn import LiquidNCPNetwork
+
+    torch.set_num_threads(threads)
+    vb.set_seed(64)
+    net = LiquidNCPNetwork(SHAPE["I"], SHAPE["N"], SHAPE["O"])      # CPU parameter container only
+    params = lo.torch_params({k: v.detach() for k, v in net.state_dict().items()}, requires_grad=True)
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(B, T, SHAPE["I"], generator=g)
+    ry = torch.randn(B, T, SHAPE["O"], generator=g)
+    rh = torch.randn(B, SHAPE["Nc"], generator=g)
+    leaves = [t for t in params.values() if t.requires_grad]
+
+    def step():
+        for t in leaves:
+            t.grad = None
+        y, ht = lo.liquid_seq_forward_torch(params, x, None)
+        ((y * ry).sum() + (ht[:, -1] * rh).sum()).backward()
+
+    return step
+
+
+def time_cpu_port(B: int, T: int, steps: int, warmup: int):
+    import torch
+
+    threads = os.cpu_count() or 1
+    step = cpu_port_step_fn(B, T, threads)
+    for _ in range(warmup):
+        step()
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+    return times, threads, torch.get_num_threads()
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B, T = args.batch, args.seq
+    # bounded sample: full batch is ~0.5-1 s per step on 16 cores; shrink it when the requested run would take minutes
+    sample_B = B
+    if (args.steps + args.warmup) > 60:
+        sample_B = max(4096, B // 4)
+    times, threads, used = time_cpu_port(sample_B, T, args.steps, max(args.warmup, 1))
+    total = sum(times)
+    value = sample_B * T * len(times) / total
+    line = {
+        "impl": "reference",
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"LiquidNCPNetwork(4,20,2) fwd+bwd, batch {B} x seq {T}, fp32 (BASELINE config 3)",
+                   "batch_per_gpu": B, "seq_len": T},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"oracle torch-CPU port of the reference ops, batch {sample_B} x seq {T}, {len(times)} steps, {used} threads"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    import velora_b200 as vb
+    from velora_b200 import functional as VF
+    from velora_b200.models.lnn import LiquidNCPNetwork
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (velora_b200 has no CPU fallback)")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        vb.dataparallel.configure(True, reduce="sum")
+    B, T = args.batch, args.seq
+    K, W = args.steps, max(args.warmup, 3)
+
+    vb.set_seed(64)                                    # same seed on every rank => identical masks and parameters
+    net = LiquidNCPNetwork(SHAPE["I"], SHAPE["N"], SHAPE["O"], device=dev)
+    params = list(net.parameters())
+    # R rotating input sets (> L2: 4 x 52 MB of inputs, ~170 MB touched per step)
+    R = 4
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    xs = [torch.randn(B, T, SHAPE["I"], device=dev, generator=g) for _ in range(R)]
+    rys = [torch.randn(B, T, SHAPE["O"], device=dev, generator=g) for _ in range(R)]
+    rhs = [torch.randn(B, SHAPE["Nc"], device=dev, generator=g) for _ in range(R)]
+
+    def step(i: int) -> None:
+        for p in params:
+            p.grad = None
+        y, _, h_last = net.forward_seq(xs[i % R], None, return_last=True)
+        torch.autograd.backward([y, h_last], [rys[i % R], rhs[i % R]])   # d/dy, d/dh_T of sum(y r_y) + sum(h_T r_h)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    for i in range(W):
+        step(i)
+    # ------------------------------------------------------------------ device-resident timing
+    VF.PROFILE = {}
+    launches0 = VF.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    sampler.active = True
+    e0.record()
+    for i in range(K):
+        step(W + i)
+    e1.record()
+    barrier()
+    sampler.active = False
+    gpu_launches = VF.LAUNCHES - launches0
+    prof, VF.PROFILE = VF.PROFILE, None
+    ms_total = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    value = world * B * T * K / (ms_total * 1e-3)
+
+    def avg_ms(name):
+        ev = prof.get(name, [])
+        return sum(a.elapsed_time(b) for a, b in ev) / max(len(ev), 1)
+
+    bwd_ms, fwd_ms = avg_ms("liquid_bwd"), avg_ms("liquid_fwd")
+    peaks, peak_kind = measured_peaks()
+    hbm_peak = float(peaks["hbm_gbs"])
+    bwd_gbs = ALGO_BYTES_BWD * B * T / (bwd_ms * 1e-3) / 1e9 if bwd_ms > 0 else 0.0
+    fwd_gbs = ALGO_BYTES_FWD * B * T / (fwd_ms * 1e-3) / 1e9 if fwd_ms > 0 else 0.0
+    step_gbs = algo_bytes_step(T) * B * T / (ms_total / K * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")      # dram bytes per launch from the committed ncu capture
+    if os.path.isfile(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("liquid_bwd_small_kernel_bytes_per_launch")
+
+    # ------------------------------------------------------------------ end to end: pinned host inputs, H2D + D2H inside
+    hx = [torch.randn(B, T, SHAPE["I"]).pin_memory() for _ in range(2)]
+    hry = [torch.randn(B, T, SHAPE["O"]).pin_memory() for _ in range(2)]
+    hrh = [torch.randn(B, SHAPE["Nc"]).pin_memory() for _ in range(2)]
+    n_grad = sum(p.numel() for p in params)
+    hout = torch.empty(n_grad + 1).pin_memory()
+    copy_stream = torch.cuda.Stream(device=dev)
+    main_stream = torch.cuda.current_stream(dev)
+    dbuf = [[torch.empty_like(xs[0]), torch.empty_like(rys[0]), torch.empty_like(rhs[0])] for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    freed = [torch.cuda.Event() for _ in range(2)]
+
+    def upload(i: int) -> None:
+        s = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(freed[s])
+            dbuf[s][0].copy_(hx[s], non_blocking=True)
+            dbuf[s][1].copy_(hry[s], non_blocking=True)
+            dbuf[s][2].copy_(hrh[s], non_blocking=True)
+            ready[s].record(copy_stream)
+
+    def e2e_step(i: int) -> None:
+        s = i % 2
+        upload(i + 1)                                   # next step's inputs travel while this step computes
+        main_stream.wait_event(ready[s])
+        for p in params:
+            p.grad = None
+        y, _, h_last = net.forward_seq(dbuf[s][0], None, return_last=True)
+        loss = (y * dbuf[s][1]).sum() + (h_last * dbuf[s][2]).sum()
+        loss.backward()
+        freed[s].record(main_stream)
+        flat = torch.cat([loss.detach().reshape(1)] + [p.grad.reshape(-1) for p in params])
+        hout.copy_(flat, non_blocking=True)             # D2H of the step's result (loss + all parameter gradients)
+
+    for s in range(2):
+        freed[s].record(main_stream)
+    upload(0)
+    for i in range(3):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    upload(3)
+    barrier()
+    sampler.active = True
+    e0.record()
+    for i in range(3, 3 + K):
+        e2e_step(i)
+    e1.record()
+    barrier()
+    sampler.active = False
+    e2e_ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = world * B * T * K / (e2e_ms * 1e-3)
+    h2d = 4 * (B * T * (SHAPE["I"] + SHAPE["O"]) + B * SHAPE["Nc"])
+    d2h = 4 * (n_grad + 1)
+    sampler.stop_flag = True
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        times, threads, used = time_cpu_port(B, T, 3, 1)
+        best = min(times)
+        cpu = {"value": B * T / best, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"oracle torch-CPU port of the reference ops, full batch {B} x seq {T}, best of 3 steps, {used} threads"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"LiquidNCPNetwork(4,20,2) fwd+bwd, batch {B} x seq {T} per GPU, fp32 (BASELINE config 3)",
+                       "batch_per_gpu": B, "global_batch": B * world, "seq_len": T,
+                       "parallelism": f"dp{world}" if world > 1 else "single",
+                       "l2": f"{R} rotating input sets ({R * h2d // 2**20} MiB) + ~170 MB touched per step > 126 MB L2"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / K},
+            "gpu_launches": gpu_launches,
+            "roofline": {"bound": "hbm", "kernel": "liquid_bwd_small_kernel", "achieved": bwd_gbs, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": bwd_gbs / hbm_peak, "traffic": traffic, "peak_kind": peak_kind,
+                         "algorithmic_bytes_per_sample_step": ALGO_BYTES_BWD, "kernel_ms": bwd_ms,
+                         "fwd_kernel_ms": fwd_ms, "fwd_achieved": fwd_gbs,
+                         "step_achieved": step_gbs, "step_frac": step_gbs / hbm_peak,
+                         "step_algorithmic_bytes_per_sample_step": algo_bytes_step(T)},
+            "cpu_baseline": cpu,
+            "clocks": sampler.summary(),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=65536, help="batch rows per GPU")
+    ap.add_argument("--seq", type=int, default=32)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -21,8 +21,8 @@
 namespace vb {
 namespace small {
 
-constexpr int kConstFloats = 1024;   // 4 KB: the flat part of the constant-cache curve (profiles/microbench)
-__constant__ float c_p[kConstFloats];
+constexpr int kConstFloats = 2048;   // F section + transposed copies for the data-gradient (<= 8 KB)
+__constant__ __align__(16) float c_p[kConstFloats];
 
 template <int I_, int NI_, int NC_, int O_>
 struct Cfg {
@@ -35,7 +35,13 @@ struct Cfg {
     static constexpr int WOUT = B_H + H4;
     static constexpr int B_OUT = WOUT + O * NCp;
     static constexpr int F_TOTAL = B_OUT + Op;
-    static_assert(F_TOTAL <= kConstFloats, "parameter block exceeds the constant-bank budget");
+    // transposed copies (D section of the packed block, contiguous after F): used by the backward so that one
+    // LDCU.128 feeds four INDEPENDENT accumulators (dz[i..i+3] / dx[i..i+3]) exactly like the forward does
+    static constexpr int Ip = ceil4(I), Kp = ceil4(K);
+    static constexpr int WIN = F_TOTAL;                 // [NI][Ip]
+    static constexpr int WH = WIN + NI * Ip;            // [H4][Kp]
+    static constexpr int C_TOTAL = WH + H4 * Kp;
+    static_assert(C_TOTAL <= kConstFloats, "parameter block exceeds the constant-bank budget");
     static_assert(H4 <= 32, "weight-gradient block mapping needs 4*NCp <= 32");
     // weight-gradient register blocking: lane = (jb, ib), 4 ds rows x CB z columns
     static constexpr int CB = (K + 3) / 4;
@@ -111,28 +117,40 @@ __device__ __forceinline__ void store_row(float* p, const float (&src)[N], bool 
 
 // ------------------------------------------------------------------------------------------------ cell math
 // u -> a = mish(u) (and mish'(u) when KEEP); the five heads with the two f heads pre-summed.
+// opaque(): hides a compile-time index from the front end's value numbering (empty asm), ptxas still sees the constant
+__device__ __forceinline__ int opaque(int v) {
+    asm volatile("" : "+r"(v));
+    return v;
+}
+#define CQ(idx) c_p[opaque(idx)]
+// `zo` is a runtime zero (kernel argument).  The backward reads every weight twice per step (recompute and
+// data-gradient); with plain compile-time indices the compiler merges the two reads and keeps ~750 weights in
+// vector registers behind per-thread LDC loads (measured: 1186 LDC per warp-step, FFMAs stalled on the short
+// scoreboard).  Distinct opaque offsets per section keep each read a uniform LDCU.128 feeding FFMA's UR operand.
 template <class C>
-__device__ __forceinline__ void inter_layer(const float (&x)[C::I], float (&u)[C::NI]) {
+__device__ __forceinline__ void inter_layer(const float (&x)[C::I], float (&u)[C::NI], int zo = 0) {
+    const float* __restrict__ cp = c_p; (void)zo;
 #pragma unroll
-    for (int j = 0; j < C::NI; ++j) u[j] = c_p[C::B_IN + j];
+    for (int j = 0; j < C::NI; ++j) u[j] = cp[C::B_IN + j];
 #pragma unroll
     for (int i = 0; i < C::I; ++i)
 #pragma unroll
-        for (int j = 0; j < C::NI; ++j) u[j] = fmaf(x[i], c_p[C::WIN_T + i * C::NIp + j], u[j]);
+        for (int j = 0; j < C::NI; ++j) u[j] = fmaf(x[i], cp[C::WIN_T + i * C::NIp + j], u[j]);
 }
 
 template <class C>
-__device__ __forceinline__ void head_layer(const float (&z)[C::K], float (&s)[4][C::NC]) {
+__device__ __forceinline__ void head_layer(const float (&z)[C::K], float (&s)[4][C::NC], int zo = 0) {
+    const float* __restrict__ cp = c_p; (void)zo;
 #pragma unroll
     for (int hs = 0; hs < 4; ++hs)
 #pragma unroll
-        for (int j = 0; j < C::NC; ++j) s[hs][j] = c_p[C::B_H + hs * C::NCp + j];
+        for (int j = 0; j < C::NC; ++j) s[hs][j] = cp[C::B_H + hs * C::NCp + j];
 #pragma unroll
     for (int i = 0; i < C::K; ++i)
 #pragma unroll
         for (int hs = 0; hs < 4; ++hs)
 #pragma unroll
-            for (int j = 0; j < C::NC; ++j) s[hs][j] = fmaf(z[i], c_p[C::WH_T + i * C::H4 + hs * C::NCp + j], s[hs][j]);
+            for (int j = 0; j < C::NC; ++j) s[hs][j] = fmaf(z[i], cp[C::WH_T + i * C::H4 + hs * C::NCp + j], s[hs][j]);
 }
 
 // ------------------------------------------------------------------------------------------------ forward
@@ -242,7 +260,8 @@ template <class C>
 __global__ void __launch_bounds__(kBwdThreads) liquid_bwd_small_kernel(
     const float* __restrict__ x, const float* __restrict__ h0, const float* __restrict__ h_traj,
     const float* __restrict__ dy, const float* __restrict__ dh_traj, const float* __restrict__ dh_last,
-    float* __restrict__ dx, float* __restrict__ dh0, float* __restrict__ partials, int64_t B, int T, int vec_flags) {
+    float* __restrict__ dx, float* __restrict__ dh0, float* __restrict__ partials, int64_t B, int T, int vec_flags,
+    int zo1, int zo2) {
     using S = BwdSmem<C>;
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -299,7 +318,7 @@ __global__ void __launch_bounds__(kBwdThreads) liquid_bwd_small_kernel(
                 float dmu[C::NI];
                 {
                     float u[C::NI];
-                    inter_layer<C>(xr, u);
+                    inter_layer<C>(xr, u, zo1);
 #pragma unroll
                     for (int j = 0; j < C::NI; ++j) z[j] = mish_fwd_grad(u[j], dmu[j]);
                 }
@@ -315,7 +334,7 @@ __global__ void __launch_bounds__(kBwdThreads) liquid_bwd_small_kernel(
                     for (int j = 0; j < C::NC; ++j) z[C::NI + j] = hp[j];
                 }
                 float s[4][C::NC];
-                head_layer<C>(z, s);
+                head_layer<C>(z, s, zo1);
                 // ---------------- output side: dy -> dm -> dc ; gating derivatives (s is overwritten by ds)
                 float dyr[C::O];
                 load_row<C::O>(dyr, dys + lane * S::SY + tt * C::O, (C::O & 3) == 0);
@@ -345,30 +364,31 @@ __global__ void __launch_bounds__(kBwdThreads) liquid_bwd_small_kernel(
                 }
                 // ---------------- dz = sum_k ds_k W_k ; split into da (-> du) and the carry into h_{t-1}
                 float du[C::NI];
+                {
+                    float dz[C::K];
 #pragma unroll
-                for (int i = 0; i < C::K; ++i) {
-                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                    for (int i = 0; i < C::K; ++i) dz[i] = 0.f;
 #pragma unroll
-                    for (int j = 0; j < C::NC; ++j) {
-                        a0 = fmaf(s[0][j], c_p[C::WH_T + i * C::H4 + 0 * C::NCp + j], a0);
-                        a1 = fmaf(s[1][j], c_p[C::WH_T + i * C::H4 + 1 * C::NCp + j], a1);
-                        a2 = fmaf(s[2][j], c_p[C::WH_T + i * C::H4 + 2 * C::NCp + j], a2);
-                        a3 = fmaf(s[3][j], c_p[C::WH_T + i * C::H4 + 3 * C::NCp + j], a3);
-                    }
-                    float dzi = (a0 + a1) + (a2 + a3);
-                    if (i < C::NI) du[i] = dzi * dmu[i];
-                    else dhc[i - C::NI] = dzi;
+                    for (int hs = 0; hs < 4; ++hs)
+#pragma unroll
+                        for (int j = 0; j < C::NC; ++j)
+#pragma unroll
+                            for (int i = 0; i < C::K; ++i)
+                                dz[i] = fmaf(s[hs][j], c_p[C::WH + (hs * C::NCp + j) * C::Kp + i], dz[i]);
+#pragma unroll
+                    for (int i = 0; i < C::NI; ++i) du[i] = dz[i] * dmu[i];
+#pragma unroll
+                    for (int j = 0; j < C::NC; ++j) dhc[j] = dz[C::NI + j];
                 }
                 // ---------------- dx = du W_in
                 {
                     float dxr[C::I];
 #pragma unroll
-                    for (int i = 0; i < C::I; ++i) {
-                        float a = 0.f;
+                    for (int i = 0; i < C::I; ++i) dxr[i] = 0.f;
 #pragma unroll
-                        for (int j = 0; j < C::NI; ++j) a = fmaf(du[j], c_p[C::WIN_T + i * C::NIp + j], a);
-                        dxr[i] = a;
-                    }
+                    for (int j = 0; j < C::NI; ++j)
+#pragma unroll
+                        for (int i = 0; i < C::I; ++i) dxr[i] = fmaf(du[j], c_p[C::WIN + j * C::Ip + i], dxr[i]);
                     store_row<C::I>(dxs + lane * S::SX + tt * C::I, dxr, true);
                 }
                 // ---------------- weight gradients: transpose through the per-warp tile, then register blocks
@@ -572,13 +592,13 @@ static int launch_bwd(const float* packed, const float* x, const float* h0, cons
                  "vb_liquid_bwd: workspace too small (%lld bytes, need %lld)", (long long)ws_bytes,
                  (long long)((int64_t)grid * C::F_TOTAL * sizeof(float)));
     bool capturing;
-    rc = upload_constants(packed, C::F_TOTAL, stream, &dev, &capturing);
+    rc = upload_constants(packed, C::C_TOTAL, stream, &dev, &capturing);
     if (rc) return rc;
     int vf = vec_flags_for(x, dy, h0, h_traj, dh_traj, dh_last, T, C::I, C::O, C::NC, kBwdTT);
     if (dx && (reinterpret_cast<uintptr_t>(dx) & 15)) vf &= ~1;
     if (dh0 && (reinterpret_cast<uintptr_t>(dh0) & 15)) vf &= ~4;
     float* partials = reinterpret_cast<float*>(ws);
-    liquid_bwd_small_kernel<C><<<grid, kBwdThreads, BwdSmem<C>::BYTES, stream>>>(x, h0, h_traj, dy, dh_traj, dh_last, dx, dh0, partials, B, T, vf);
+    liquid_bwd_small_kernel<C><<<grid, kBwdThreads, BwdSmem<C>::BYTES, stream>>>(x, h0, h_traj, dy, dh_traj, dh_last, dx, dh0, partials, B, T, vf, 0, 0);
     VB_LAUNCH_CHECK();
     if (!capturing) VB_CUDA(cudaEventRecord(g_ev[dev & 63], stream));
     reduce_partials_kernel<<<(C::F_TOTAL + 127) / 128, 128, 0, stream>>>(partials, grid, C::F_TOTAL, dpacked);

@@ -16,6 +16,37 @@ from . import dataparallel as _dp
 
 HEAD_NAMES = ("g_head", "h_head", "f_head_to_g", "f_head_to_h", "proj")
 
+# Optional instrumentation used by bench.py: when PROFILE is a dict, every C-ABI compute call is bracketed by CUDA
+# events on the launching stream (PROFILE[name] -> list of (start, end)); LAUNCHES counts the kernels this library
+# launches (pack 1, fwd 1, bwd 2 = kernel + partial-sum reduction, unpack 1, gather 1).
+PROFILE = None
+LAUNCHES = 0
+
+
+def _count(n: int) -> None:
+    global LAUNCHES
+    LAUNCHES += n
+
+
+class _timed:
+    def __init__(self, name: str, launches: int):
+        self.name, self.launches = name, launches
+
+    def __enter__(self):
+        global LAUNCHES
+        LAUNCHES += self.launches
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            self.e1.record()
+            PROFILE.setdefault(self.name, []).append((self.e0, self.e1))
+        return False
+
 
 def _f32c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
     if t is None:
@@ -55,6 +86,7 @@ class LiquidSeqFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             st = _lib.stream_ptr(dev)
             packed = torch.empty(L.vb_liquid_packed_floats(I, Ni, Nc, O), dtype=torch.float32, device=dev)
+            _count(1)
             _lib.check(
                 L.vb_liquid_pack(
                     _lib.ptr(w_in), _lib.ptr(b_in), _lib.ptr(m_in), _lib.mask_type(m_in),
@@ -66,11 +98,12 @@ class LiquidSeqFn(torch.autograd.Function):
             )
             y = torch.empty((B, T, O), dtype=torch.float32, device=dev)
             h_traj = torch.empty((B, T, Nc), dtype=torch.float32, device=dev)
-            _lib.check(
-                L.vb_liquid_fwd(_lib.ptr(packed), _lib.ptr(x), _lib.ptr(h0c), _lib.ptr(y), _lib.ptr(h_traj),
-                                B, T, I, Ni, Nc, O, None, 0, flags, st),
-                "vb_liquid_fwd",
-            )
+            with _timed("liquid_fwd", 1):
+                _lib.check(
+                    L.vb_liquid_fwd(_lib.ptr(packed), _lib.ptr(x), _lib.ptr(h0c), _lib.ptr(y), _lib.ptr(h_traj),
+                                    B, T, I, Ni, Nc, O, None, 0, flags, st),
+                    "vb_liquid_fwd",
+                )
         h_last = h_traj[:, T - 1].clone()
         ctx.dims, ctx.flags, ctx.masks = dims, flags, masks
         ctx.has_h0 = h0 is not None
@@ -101,12 +134,13 @@ class LiquidSeqFn(torch.autograd.Function):
             dpacked = torch.empty(n_grad, dtype=torch.float32, device=dev)
             ws_bytes = L.vb_liquid_bwd_workspace_bytes(I, Ni, Nc, O, B, T)
             ws = torch.empty(max(int(ws_bytes), 16), dtype=torch.uint8, device=dev)
-            _lib.check(
-                L.vb_liquid_bwd(_lib.ptr(packed), _lib.ptr(x), _lib.ptr(h0p), _lib.ptr(h_traj), _lib.ptr(dy),
-                                _lib.ptr(dh_traj), _lib.ptr(dh_last), _lib.ptr(dx), _lib.ptr(dh0), _lib.ptr(dpacked),
-                                B, T, I, Ni, Nc, O, _lib.ptr(ws), ws.numel(), ctx.flags, st),
-                "vb_liquid_bwd",
-            )
+            with _timed("liquid_bwd", 2):
+                _lib.check(
+                    L.vb_liquid_bwd(_lib.ptr(packed), _lib.ptr(x), _lib.ptr(h0p), _lib.ptr(h_traj), _lib.ptr(dy),
+                                    _lib.ptr(dh_traj), _lib.ptr(dh_last), _lib.ptr(dx), _lib.ptr(dh0), _lib.ptr(dpacked),
+                                    B, T, I, Ni, Nc, O, _lib.ptr(ws), ws.numel(), ctx.flags, st),
+                    "vb_liquid_bwd",
+                )
             # data-parallel: ONE collective over the flat pre-masked gradient block
             _dp.maybe_allreduce(dpacked)
             need = ctx.needs_input_grad[5:]
@@ -115,6 +149,7 @@ class LiquidSeqFn(torch.autograd.Function):
                 torch.empty(s, dtype=torch.float32, device=dev) if need[k] else None for k, s in enumerate(shapes)
             ]
             m_in, m_h, m_out = masks[0], list(masks[1:6]), masks[6]
+            _count(1)
             _lib.check(
                 L.vb_liquid_unpack_grads(
                     _lib.ptr(dpacked), _lib.ptr(m_in), _lib.mask_type(m_in), _lib.ptr_array(m_h), _lib.mask_type(m_h[0]),
@@ -146,13 +181,15 @@ class NcpFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             st = _lib.stream_ptr(dev)
             packed = torch.empty(L.vb_ncp_packed_floats(I, Ni, Nc, O), dtype=torch.float32, device=dev)
+            _count(1)
             _lib.check(
                 L.vb_ncp_pack(_lib.ptr_array(w), _lib.ptr_array(b), _lib.ptr_array(list(masks)), _lib.mask_type(masks[0]),
                               I, Ni, Nc, O, _lib.ptr(packed), st),
                 "vb_ncp_pack",
             )
             y = torch.empty((B, O), dtype=torch.float32, device=dev)
-            _lib.check(L.vb_ncp_fwd(_lib.ptr(packed), _lib.ptr(x), _lib.ptr(y), B, I, Ni, Nc, O, flags, st), "vb_ncp_fwd")
+            with _timed("ncp_fwd", 1):
+                _lib.check(L.vb_ncp_fwd(_lib.ptr(packed), _lib.ptr(x), _lib.ptr(y), B, I, Ni, Nc, O, flags, st), "vb_ncp_fwd")
         ctx.dims, ctx.flags, ctx.masks = dims, flags, masks
         ctx.save_for_backward(x, packed)
         return y
@@ -172,15 +209,17 @@ class NcpFn(torch.autograd.Function):
             dpacked = torch.empty(L.vb_ncp_grad_floats(I, Ni, Nc, O), dtype=torch.float32, device=dev)
             ws_bytes = L.vb_ncp_bwd_workspace_bytes(I, Ni, Nc, O, B)
             ws = torch.empty(max(int(ws_bytes), 16), dtype=torch.uint8, device=dev)
-            _lib.check(
-                L.vb_ncp_bwd(_lib.ptr(packed), _lib.ptr(x), _lib.ptr(dy), _lib.ptr(dx), _lib.ptr(dpacked),
-                             B, I, Ni, Nc, O, _lib.ptr(ws), ws.numel(), ctx.flags, st),
-                "vb_ncp_bwd",
-            )
+            with _timed("ncp_bwd", 2):
+                _lib.check(
+                    L.vb_ncp_bwd(_lib.ptr(packed), _lib.ptr(x), _lib.ptr(dy), _lib.ptr(dx), _lib.ptr(dpacked),
+                                 B, I, Ni, Nc, O, _lib.ptr(ws), ws.numel(), ctx.flags, st),
+                    "vb_ncp_bwd",
+                )
             _dp.maybe_allreduce(dpacked)
             need = ctx.needs_input_grad[4:]
             shapes = [(Ni, I), (Ni,), (Nc, Ni), (Nc,), (O, Nc), (O,)]
             grads = [torch.empty(s, dtype=torch.float32, device=dev) if need[k] else None for k, s in enumerate(shapes)]
+            _count(1)
             _lib.check(
                 L.vb_ncp_unpack_grads(_lib.ptr(dpacked), _lib.ptr_array(list(masks)), _lib.mask_type(masks[0]),
                                       _lib.ptr_array([grads[0], grads[2], grads[4]]), _lib.ptr_array([grads[1], grads[3], grads[5]]),
@@ -206,6 +245,7 @@ def gather_rows(arrays: Sequence[torch.Tensor], indices: torch.Tensor, n_rows: i
         widths.append(a.shape[1])
     with torch.cuda.device(dev):
         rf = (C.c_int * len(widths))(*widths)
+        _count(1)
         _lib.check(
             L.vb_gather_rows(_lib.ptr_array(list(arrays)), _lib.ptr_array(outs), rf, len(widths), _lib.ptr(indices), B,
                              int(n_rows), _lib.stream_ptr(dev)),
