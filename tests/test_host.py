@@ -1,0 +1,218 @@
+"""Host-side logic of the product on CPU (no GPU needed): wiring/initialisation parity with the reference goldens,
+the reference's structural tests restated against the mirror classes, error behaviour, the C-ABI library."""
+import copy
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import velora_b200 as vb
+from velora_b200 import _lib
+from velora_b200.buffer import BatchExperience, ReplayBuffer
+from velora_b200.models.lnn import LiquidNCPNetwork, NCPLiquidCell, NCPNetwork, SparseLinear
+from velora_b200.wiring import NeuronCounts, SynapseCounts, Wiring
+from vb_testutil import liquid_case_params
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ------------------------------------------------------------------------------------------------ wiring
+def test_wiring_bit_exact_with_reference(golden):
+    d = golden("wiring")
+    for idx, (i, n, o, sp, seed) in enumerate(d["cases"]):
+        vb.set_seed(int(seed))
+        w = Wiring(int(i), int(n), int(o), sparsity_level=float(sp))
+        for k in ("inter", "command", "motor", "recurrent"):
+            m = getattr(w.masks, k)
+            assert m.dtype == torch.int32
+            assert np.array_equal(m.numpy(), d[f"c{idx}_{k}"]), (idx, k)
+        c = w.counts
+        assert [c.sensory, c.inter, c.command, c.motor] == list(d[f"c{idx}_counts"])
+        s = w.n_connections
+        assert [s.sensory, s.inter, s.command, s.motor] == list(d[f"c{idx}_synapses"])
+        assert np.random.randint(0, 2**31 - 1) == int(d[f"c{idx}_next_np"][0])      # RNG streams left in the same state
+        assert int(torch.randint(0, 2**31 - 1, (1,))) == int(d[f"c{idx}_next_torch"][0])
+
+
+def test_wiring_structure_like_reference_tests():
+    # reference tests/models/test_wiring.py:52-54, 56-67, 81-117
+    w = Wiring(4, 10, 2, sparsity_level=0.5)
+    assert w.n_connections == SynapseCounts(3, 2, 4, 2)
+    assert w.counts == NeuronCounts(4, 6, 4, 2)
+    for bad in (0.05, 0.95):
+        with pytest.raises(ValueError):
+            Wiring(4, 10, 2, sparsity_level=bad)
+    for sp in (0.1, 0.5, 0.9):
+        w = Wiring(8, 30, 3, sparsity_level=sp)
+        for k in ("inter", "command", "motor"):
+            m = getattr(w.masks, k)
+            assert set(m.unique().tolist()) <= {-1, 0, 1}
+            assert bool((m != 0).any(dim=0).all()), "every column is connected"
+            assert bool((m != 0).any(dim=1).all()), "every row is connected"
+    p = Wiring.polarity((5, 3))
+    assert p.dtype == torch.int32 and set(p.unique().tolist()) <= {-1, 1}
+    masks, counts = w.data()
+    assert masks is w.masks and counts is w.counts
+
+
+# ------------------------------------------------------------------------------------------------ networks (host side)
+@pytest.mark.parametrize("name", ["fixture", "actor_t1", "odd", "mid", "wide"])
+def test_liquid_init_parity_and_layout(golden, name):
+    d = golden("liquid")
+    i, n, o, sp, seed = d[f"{name}_meta"][:5]
+    vb.set_seed(int(seed))
+    net = LiquidNCPNetwork(int(i), int(n), int(o), sparsity_level=float(sp))
+    ref = liquid_case_params(d, name)
+    sd = net.state_dict()
+    assert list(sd.keys()) == list(ref.keys())                      # names and ORDER of the checkpoint format
+    for k, v in sd.items():
+        assert v.dtype == torch.from_numpy(ref[k]).dtype, k          # inter/motor masks int32, cell masks float32
+        assert np.array_equal(v.numpy(), ref[k]), k
+    assert [k for k, _ in net.named_parameters()] == [k for k in ref if k.endswith(("weight", "bias"))]
+
+
+def test_liquid_known_answers_and_attributes():
+    vb.set_seed(64)
+    net = LiquidNCPNetwork(10, 20, 5)
+    assert (net.total_params, net.active_params) == (1017, 657)      # reference tests/models/test_lnn.py:280-309
+    assert net.hidden_size == 8 and net.n_units == 25
+    assert [n for n, _ in net.named_children()] == ["inter", "command", "motor", "act"]
+    assert [n for n, _ in net.command.named_children()] == ["tanh", "sigmoid", "g_head", "h_head", "f_head_to_g", "f_head_to_h", "proj"]
+    assert isinstance(net.act, torch.nn.Mish)
+    with pytest.raises(ValueError):
+        LiquidNCPNetwork(4, 20, 2, sparsity_level=0.95)
+
+
+def test_ncp_init_parity(golden):
+    d = golden("ncp")
+    for name in d["names"]:
+        i, n, o, sp, seed, _ = d[f"{name}_meta"]
+        vb.set_seed(int(seed))
+        net = NCPNetwork(int(i), int(n), int(o), sparsity_level=float(sp))
+        ref = liquid_case_params(d, str(name))
+        assert list(net.state_dict().keys()) == list(ref.keys())
+        for k, v in net.state_dict().items():
+            assert np.array_equal(v.numpy(), ref[k]), (name, k)
+        assert isinstance(net.ncp, torch.nn.Sequential) and len(net.ncp) == 5
+
+
+def test_no_cpu_fallback_and_errors():
+    vb.set_seed(1)
+    net = LiquidNCPNetwork(4, 20, 2)
+    with pytest.raises(ValueError):
+        net(torch.zeros(2, 3, 4))                                    # ncp.py:153-156
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        net(torch.zeros(2, 4))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        net.forward_seq(torch.zeros(2, 3, 4))
+    critic = NCPNetwork(5, 128, 1)
+    with pytest.raises(ValueError):
+        critic(torch.zeros(5))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        critic(torch.zeros(2, 5))
+    buf = ReplayBuffer(10, 4, 1, 8)
+    buf.add_multi(torch.zeros(4, 4), torch.zeros(4, 1), torch.zeros(4), torch.zeros(4, 4), torch.zeros(4), torch.zeros(4, 8))
+    with pytest.raises(ValueError):
+        buf.sample(5)                                                # replay.py:74-77
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        buf.sample(2)
+
+
+def test_deepcopy_and_script_survive():
+    """velora/models/nf/modules.py:370-392: networks are deep-copied then torch.jit.script-ed."""
+    vb.set_seed(3)
+    for net in (LiquidNCPNetwork(4, 20, 2), NCPNetwork(5, 128, 1)):
+        twin = torch.jit.script(copy.deepcopy(net))
+        assert isinstance(twin, torch.jit.RecursiveScriptModule)
+        assert list(twin.state_dict().keys()) == list(net.state_dict().keys())
+        assert [tuple(p.shape) for p in twin.parameters()] == [tuple(p.shape) for p in net.parameters()]
+
+
+def test_layer_modules_formulas(golden):
+    """SparseLinear / NCPLiquidCell on their own follow the reference formulas (cell.npz from the reference)."""
+    d = golden("cell")
+    cell = NCPLiquidCell(8, 6, torch.tensor(d["mask"]))
+    assert cell.head_size == 14
+    assert np.array_equal(cell.sparsity_mask.numpy(), d["sd_sparsity_mask"])       # _prep_mask, cell.py:91-111
+    cell.load_state_dict({k[3:]: torch.tensor(d[k]) for k in d.files if k.startswith("sd_")})
+    x = torch.tensor(d["x"], requires_grad=True)
+    h = torch.tensor(d["h"], requires_grad=True)
+    y, hn = cell(x, h)
+    assert np.array_equal(y.detach().numpy(), d["y"]) and np.array_equal(hn.detach().numpy(), d["hn"])
+    (y.sum() + 2.0 * hn.sum()).backward()
+    assert np.allclose(x.grad.numpy(), d["dx"], atol=1e-6) and np.allclose(h.grad.numpy(), d["dh"], atol=1e-6)
+    for k, p in cell.named_parameters():
+        assert np.allclose(p.grad.numpy(), d[f"grad_{k}"], atol=1e-6), k
+        if k.endswith("weight"):
+            assert torch.all(p.grad[cell.sparsity_mask == 0] == 0)                  # tests/models/test_lnn.py:570-576
+    # SparseLinear: masked weights are zero after init and the mask is applied in forward (test_lnn.py:429-480)
+    mask = torch.tensor([[1, 0, 1], [0, 1, 0]])
+    lin = SparseLinear(3, 2, mask)
+    assert torch.all(lin.weight[mask == 0] == 0)
+    with torch.no_grad():
+        lin.weight.fill_(1.0)
+        lin.bias.zero_()
+    assert torch.equal(lin(torch.ones(1, 3)), torch.tensor([[2.0, 1.0]]))
+    lin.update_mask(torch.ones(2, 3, dtype=torch.int64))
+    assert torch.equal(lin(torch.ones(1, 3)), torch.tensor([[3.0, 3.0]]))
+
+
+# ------------------------------------------------------------------------------------------------ buffer (host side)
+def test_buffer_ring_semantics_vs_reference(golden):
+    d = golden("buffer")
+    cap, S, A, H = (int(v) for v in d["dims"])
+    buf = ReplayBuffer(cap, S, A, H)
+    fi = 0
+    while f"feed{fi}_kind" in d.files:
+        c = [torch.tensor(d[f"feed{fi}_{ti}"]) for ti in range(6)]
+        if str(d[f"feed{fi}_kind"][0]) == "multi":
+            buf.add_multi(*c)
+        else:
+            for r in range(c[0].shape[0]):
+                buf.add(c[0][r], c[1][r], float(c[2][r]), c[3][r], bool(c[4][r]), c[5][r])
+        fi += 1
+    assert [buf.position, buf.size] == list(d["position_size"]) and len(buf) == buf.size
+    for k, v in buf.state_dict().items():
+        assert np.array_equal(v.numpy(), d[f"state_{k}"]), k
+    assert buf.metadata()["capacity"] == cap and buf.config().type == "ReplayBuffer"
+    assert BatchExperience.__dataclass_fields__.keys() == {"states", "actions", "rewards", "next_states", "dones", "hiddens"}
+
+
+def test_buffer_save_load_roundtrip(tmp_path):
+    buf = ReplayBuffer(20, 3, 2, 4)
+    g = torch.Generator().manual_seed(0)
+    buf.add_multi(torch.randn(25, 3, generator=g), torch.randn(25, 2, generator=g), torch.randn(25, generator=g),
+                  torch.randn(25, 3, generator=g), torch.zeros(25), torch.randn(25, 4, generator=g))
+    buf.save(tmp_path)
+    import json
+
+    meta = json.loads((tmp_path / "buffer_metadata.json").read_text())
+    again = ReplayBuffer.load(tmp_path / "buffer_state", meta)
+    assert (again.position, again.size) == (buf.position, buf.size) == (5, 20)
+    for k, v in buf.state_dict().items():
+        assert torch.equal(v, again.state_dict()[k])
+
+
+# ------------------------------------------------------------------------------------------------ C ABI
+def test_library_loads_and_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "velora_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(vb_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert os.path.isfile(_lib.LIB_PATH), "run __graft_entry__.build() first"
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(raw, name), name
+    lib = _lib.lib()
+    assert lib.vb_query(0) == 1 and lib.vb_query(1) == 100          # ABI version, built for sm_100a
+    # pure host-side queries work without a device
+    assert lib.vb_liquid_packed_floats(4, 12, 8, 2) == 752 + 48 + 640 + 32
+    assert lib.vb_liquid_grad_floats(4, 12, 8, 2) == 752
+    assert lib.vb_liquid_has_fast_path(4, 12, 8, 2) == 1 and lib.vb_liquid_has_fast_path(5, 77, 51, 1) == 0
+    assert lib.vb_liquid_packed_floats(0, 1, 1, 1) < 0
+    # argument errors are reported, not crashed on
+    assert lib.vb_liquid_fwd(None, None, None, None, None, 1, 1, 4, 12, 8, 2, None, 0, 0, None) == -1
+    assert b"null pointer" in lib.vb_last_error()
