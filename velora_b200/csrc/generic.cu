@@ -324,12 +324,22 @@ __global__ void __launch_bounds__(kTileThreads) ncp_bwd_kernel(const float* __re
     }
 }
 
-__global__ void reduce_rows_kernel(const float* __restrict__ partials, int n_rows, int n, float* __restrict__ out) {
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n) return;
+// fixed-order (deterministic) column sums of the per-CTA partial gradient rows; see liquid_small.cu
+__global__ void __launch_bounds__(1024) reduce_rows_kernel(const float* __restrict__ partials, int n_rows, int n, float* __restrict__ out) {
+    __shared__ float sm[32][33];
+    const int cx = threadIdx.x & 31, rg = threadIdx.x >> 5;
+    const int col = blockIdx.x * 32 + cx;
     float a = 0.f;
-    for (int r = 0; r < n_rows; ++r) a += partials[(int64_t)r * n + idx];
-    out[idx] = a;
+    if (col < n)
+        for (int r = rg; r < n_rows; r += 32) a += partials[(int64_t)r * n + col];
+    sm[rg][cx] = a;
+    __syncthreads();
+    if (rg == 0 && col < n) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) t += sm[k][cx];
+        out[col] = t;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ host launchers
@@ -392,7 +402,7 @@ int liquid_bwd(const float* packed, const float* x, const float* h0, const float
         if (p.BM == 32) { LAUNCH(32) } else if (p.BM == 16) { LAUNCH(16) } else { LAUNCH(8) }
 #undef LAUNCH
         VB_LAUNCH_CHECK();
-        reduce_rows_kernel<<<(L.f_total + 127) / 128, 128, 0, stream>>>(reinterpret_cast<float*>(ws), grid, L.f_total, dpacked);
+        reduce_rows_kernel<<<(L.f_total + 31) / 32, 1024, 0, stream>>>(reinterpret_cast<float*>(ws), grid, L.f_total, dpacked);
         VB_LAUNCH_CHECK();
     } else {
         VB_CUDA(cudaMemsetAsync(dpacked, 0, (size_t)L.f_total * 4, stream));
@@ -446,7 +456,7 @@ int ncp_bwd(const float* packed, const float* x, const float* dy, float* dx, flo
         if (p.BM == 32) { LAUNCH(32) } else if (p.BM == 16) { LAUNCH(16) } else { LAUNCH(8) }
 #undef LAUNCH
         VB_LAUNCH_CHECK();
-        reduce_rows_kernel<<<(L.f_total + 127) / 128, 128, 0, stream>>>(reinterpret_cast<float*>(ws), grid, L.f_total, dpacked);
+        reduce_rows_kernel<<<(L.f_total + 31) / 32, 1024, 0, stream>>>(reinterpret_cast<float*>(ws), grid, L.f_total, dpacked);
         VB_LAUNCH_CHECK();
     } else {
         VB_CUDA(cudaMemsetAsync(dpacked, 0, (size_t)L.f_total * 4, stream));

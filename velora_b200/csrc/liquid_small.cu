@@ -495,13 +495,23 @@ __global__ void __launch_bounds__(kBwdThreads) liquid_bwd_small_kernel(
     for (int idx = threadIdx.x; idx < C::F_TOTAL; idx += kBwdThreads) partials[(int64_t)blockIdx.x * C::F_TOTAL + idx] = cta_acc[idx];
 }
 
-// sums the per-CTA partial gradient rows in a fixed order
-__global__ void reduce_partials_kernel(const float* __restrict__ partials, int n_rows, int n, float* __restrict__ out) {
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n) return;
+// sums the per-CTA partial gradient rows in a fixed order (deterministic): a 32x32 thread block owns 32 columns;
+// thread (cx, rg) adds rows rg, rg+32, ... of column cx, then the 32 row-group sums are added in index order.
+__global__ void __launch_bounds__(1024) reduce_partials_kernel(const float* __restrict__ partials, int n_rows, int n, float* __restrict__ out) {
+    __shared__ float sm[32][33];
+    const int cx = threadIdx.x & 31, rg = threadIdx.x >> 5;
+    const int col = blockIdx.x * 32 + cx;
     float a = 0.f;
-    for (int r = 0; r < n_rows; ++r) a += partials[(int64_t)r * n + idx];
-    out[idx] = a;
+    if (col < n)
+        for (int r = rg; r < n_rows; r += 32) a += partials[(int64_t)r * n + col];
+    sm[rg][cx] = a;
+    __syncthreads();
+    if (rg == 0 && col < n) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) t += sm[k][cx];
+        out[col] = t;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -601,7 +611,7 @@ static int launch_bwd(const float* packed, const float* x, const float* h0, cons
     liquid_bwd_small_kernel<C><<<grid, kBwdThreads, BwdSmem<C>::BYTES, stream>>>(x, h0, h_traj, dy, dh_traj, dh_last, dx, dh0, partials, B, T, vf, 0, 0);
     VB_LAUNCH_CHECK();
     if (!capturing) VB_CUDA(cudaEventRecord(g_ev[dev & 63], stream));
-    reduce_partials_kernel<<<(C::F_TOTAL + 127) / 128, 128, 0, stream>>>(partials, grid, C::F_TOTAL, dpacked);
+    reduce_partials_kernel<<<(C::F_TOTAL + 31) / 32, 1024, 0, stream>>>(partials, grid, C::F_TOTAL, dpacked);
     VB_LAUNCH_CHECK();
     return 0;
 }
