@@ -62,7 +62,8 @@ extern "C" {
 #define VB_MASK_F32 1
 
 /* flags */
-#define VB_FLAG_FORCE_GENERIC 1   /* skip the specialised 20-neuron-class kernels (used by the parity tests) */
+#define VB_FLAG_FORCE_GENERIC 1   /* use the generic tile kernels even where a specialised kernel exists (parity tests) */
+#define VB_FLAG_FORCE_FFMA 2      /* skip the tensor-core (tcgen05) kernels, use the specialised FFMA kernels */
 
 /* vb_query() keys */
 #define VB_Q_ABI_VERSION 0
@@ -77,7 +78,7 @@ const char* vb_last_error(void);
 /* ------------------------------------------------------------------------------------------------ liquid network */
 int64_t vb_liquid_packed_floats(int I, int Ni, int Nc, int O);   /* F + D sections */
 int64_t vb_liquid_grad_floats(int I, int Ni, int Nc, int O);     /* F section only */
-/* 1 if (I,Ni,Nc,O) is served by a specialised constant-bank kernel, else 0 */
+/* 2 = tensor-core (tcgen05) kernels, 1 = specialised FFMA kernels, 0 = generic tile kernels only */
 int vb_liquid_has_fast_path(int I, int Ni, int Nc, int O);
 
 /* Replaces the per-forward `weight * mask` of sparse.py:81 for all seven layers of ncp.py:79-102.

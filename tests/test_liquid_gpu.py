@@ -28,7 +28,7 @@ def _build(d, name, flags=0):
     return net
 
 
-@pytest.mark.parametrize("flags", [0, 1], ids=["specialised", "generic"])
+@pytest.mark.parametrize("flags", [0, 2, 1], ids=["default", "ffma", "generic"])
 @pytest.mark.parametrize("name", CASES)
 def test_forward_backward_vs_reference(golden, name, flags):
     d = golden("liquid")
@@ -133,7 +133,7 @@ def test_ragged_batches_vs_oracle(golden, B, T):
     dh = np.zeros_like(hto)
     dh[:, -1] = rh.numpy()
     dxo, dh0o, go = lo.liquid_seq_backward(p, caches, ry.numpy(), dh, np.float64)
-    for flags in (0, 1):
+    for flags in (0, 2, 1):
         net.kernel_flags = flags
         net.zero_grad()
         xc = x.cuda().requires_grad_(True)
@@ -149,8 +149,8 @@ def test_ragged_batches_vs_oracle(golden, B, T):
 
 
 def test_full_size_properties():
-    """BASELINE config 3 at full size (B=65536, T=32): two independent kernels agree, gradients are linear in the
-    upstream gradient, and the run is bit-reproducible (no atomics on the specialised path)."""
+    """BASELINE config 3 at full size (B=65536, T=32): three independent kernel families agree (tensor-core, FFMA,
+    generic), gradients are linear in the upstream gradient, and the run is bit-reproducible (no atomics)."""
     import velora_b200 as vb
     from velora_b200.models.lnn import LiquidNCPNetwork
 
@@ -169,10 +169,11 @@ def test_full_size_properties():
         return y.detach(), ht.detach(), torch.cat([p.grad.flatten() for p in net.parameters()])
 
     y0, h0, g0 = run(0, 1.0)
-    y1, h1, g1 = run(1, 1.0)
-    assert rel_err(y0.cpu().numpy(), y1.cpu().numpy()) < 2e-6
-    assert rel_err(h0.cpu().numpy(), h1.cpu().numpy()) < 2e-6
-    assert rel_err(g0.cpu().numpy(), g1.cpu().numpy()) < FP32_RTOL
+    for other in (1, 2):          # generic tile kernels, specialised FFMA kernels
+        y1, h1, g1 = run(other, 1.0)
+        assert rel_err(y0.cpu().numpy(), y1.cpu().numpy()) < 2e-6
+        assert rel_err(h0.cpu().numpy(), h1.cpu().numpy()) < 2e-6
+        assert rel_err(g0.cpu().numpy(), g1.cpu().numpy()) < FP32_RTOL
     _, _, g2 = run(0, 2.0)
     assert rel_err(g2.cpu().numpy(), 2.0 * g0.cpu().numpy()) < 1e-6
     y3, h3, g3 = run(0, 1.0)

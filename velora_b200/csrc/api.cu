@@ -46,6 +46,13 @@ int bwd(const float*, const float*, const float*, const float*, const float*, co
         int64_t, int, int, int, int, int, void*, int64_t, cudaStream_t);
 int64_t bwd_workspace_bytes(int, int, int, int, int64_t);
 }  // namespace small
+namespace tc {
+bool has_tc_path(int I, int Ni, int Nc, int O);
+int fwd(const float*, const float*, const float*, float*, float*, int64_t, int, int, int, int, int, cudaStream_t);
+int bwd(const float*, const float*, const float*, const float*, const float*, const float*, const float*, float*, float*, float*,
+        int64_t, int, int, int, int, int, void*, int64_t, cudaStream_t);
+int64_t bwd_workspace_bytes(int, int, int, int);
+}  // namespace tc
 namespace generic {
 int liquid_fwd(const float*, const float*, const float*, float*, float*, int64_t, int, int, int, int, int, cudaStream_t);
 int64_t liquid_bwd_workspace_bytes(int, int, int, int);
@@ -79,7 +86,11 @@ extern "C" int vb_query(int what) {
     }
 }
 
-extern "C" int vb_liquid_has_fast_path(int I, int Ni, int Nc, int O) { return small::has_fast_path(I, Ni, Nc, O) ? 1 : 0; }
+// 0 = generic tile kernels only, 1 = specialised FFMA kernels, 2 = tensor-core (tcgen05) kernels
+extern "C" int vb_liquid_has_fast_path(int I, int Ni, int Nc, int O) {
+    if (tc::has_tc_path(I, Ni, Nc, O)) return 2;
+    return small::has_fast_path(I, Ni, Nc, O) ? 1 : 0;
+}
 
 static inline int64_t max64(int64_t a, int64_t b) { return a > b ? a : b; }
 
@@ -93,7 +104,8 @@ extern "C" int64_t vb_liquid_bwd_workspace_bytes(int I, int Ni, int Nc, int O, i
     if (!dims_ok(I, Ni, Nc, O)) return VB_ERR_BAD_DIMS;
     int64_t g = generic::liquid_bwd_workspace_bytes(I, Ni, Nc, O);
     int64_t s = small::has_fast_path(I, Ni, Nc, O) ? small::bwd_workspace_bytes(I, Ni, Nc, O, B) : 0;
-    return max64(g, s);
+    int64_t t = tc::has_tc_path(I, Ni, Nc, O) ? tc::bwd_workspace_bytes(I, Ni, Nc, O) : 0;
+    return max64(max64(g, s), t);
 }
 extern "C" int64_t vb_ncp_bwd_workspace_bytes(int I, int Ni, int Nc, int O, int64_t B) {
     (void)B;
@@ -108,6 +120,8 @@ extern "C" int vb_liquid_fwd(const float* packed, const float* x, const float* h
     VB_CHECK_ARG(dims_ok(I, Ni, Nc, O) && B >= 0 && T >= 1, VB_ERR_BAD_DIMS, "vb_liquid_fwd: bad dims B=%lld T=%d (%d,%d,%d,%d)", (long long)B, T, I, Ni, Nc, O);
     VB_CHECK_ARG(packed && x && y && h_traj, VB_ERR_NULL_POINTER, "vb_liquid_fwd: null pointer");
     if (B == 0) return 0;
+    if (!(flags & (VB_FLAG_FORCE_GENERIC | VB_FLAG_FORCE_FFMA)) && tc::has_tc_path(I, Ni, Nc, O))
+        return tc::fwd(packed, x, h0, y, h_traj, B, T, I, Ni, Nc, O, (cudaStream_t)stream);
     if (!(flags & VB_FLAG_FORCE_GENERIC) && small::has_fast_path(I, Ni, Nc, O))
         return small::fwd(packed, x, h0, y, h_traj, B, T, I, Ni, Nc, O, (cudaStream_t)stream);
     return generic::liquid_fwd(packed, x, h0, y, h_traj, B, T, I, Ni, Nc, O, (cudaStream_t)stream);
@@ -124,6 +138,8 @@ extern "C" int vb_liquid_bwd(const float* packed, const float* x, const float* h
         VB_CUDA(cudaMemsetAsync(dpacked, 0, (size_t)LiquidLayout(I, Ni, Nc, O).f_total * 4, (cudaStream_t)stream));
         return 0;
     }
+    if (!(flags & (VB_FLAG_FORCE_GENERIC | VB_FLAG_FORCE_FFMA)) && tc::has_tc_path(I, Ni, Nc, O))
+        return tc::bwd(packed, x, h0, h_traj, dy, dh_traj, dh_last, dx, dh0, dpacked, B, T, I, Ni, Nc, O, workspace, workspace_bytes, (cudaStream_t)stream);
     if (!(flags & VB_FLAG_FORCE_GENERIC) && small::has_fast_path(I, Ni, Nc, O))
         return small::bwd(packed, x, h0, h_traj, dy, dh_traj, dh_last, dx, dh0, dpacked, B, T, I, Ni, Nc, O, workspace, workspace_bytes, (cudaStream_t)stream);
     return generic::liquid_bwd(packed, x, h0, h_traj, dy, dh_traj, dh_last, dx, dh0, dpacked, B, T, I, Ni, Nc, O, workspace, workspace_bytes, (cudaStream_t)stream);

@@ -6,7 +6,7 @@ OUT=../lib
 mkdir -p "$OUT"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr -Xptxas -v"
-SRCS="api.cu pack.cu liquid_small.cu generic.cu gather.cu"
+SRCS="api.cu pack.cu liquid_small.cu liquid_tc.cu generic.cu gather.cu"
 OBJS=""
 for s in $SRCS; do
   o="$OUT/${s%.cu}.o"
