@@ -21,6 +21,7 @@
 //
 // Replaces the same reference lines as liquid_small.cu (cell.py:147-169, ncp.py:168-171, sparse.py:81 and autograd).
 #include <mutex>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -693,14 +694,29 @@ static int vec_flags_for(const void* x, const void* y, const void* h_a, const vo
     return f;
 }
 
+// CTAs per SM.  cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for every kernel that allocates tensor memory
+// (measured: 30 KB smem, 53 registers -> "1"), so the limits are evaluated here: shared memory (+1 KB reserved per
+// CTA), registers, TMEM columns (512 per SM) and the 32-CTA / 2048-thread caps.
 template <class K>
-static int grid_cap(K kernel, int smem, int* per_sm) {
+static int grid_cap(K kernel, int smem, int tmem_cols, int* per_sm) {
     static std::mutex mu;
     std::lock_guard<std::mutex> lock(mu);
     VB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    int occ = 1;
-    VB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, TM, smem));
-    *per_sm = occ < 1 ? 1 : occ;
+    cudaFuncAttributes fa;
+    VB_CUDA(cudaFuncGetAttributes(&fa, kernel));
+    int dev = 0, smem_sm = 0, regs_sm = 0;
+    VB_CUDA(cudaGetDevice(&dev));
+    VB_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
+    VB_CUDA(cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev));
+    const int regs_cta = ((fa.numRegs + 7) & ~7) * TM;
+    int n = smem_sm / (smem + (int)fa.sharedSizeBytes + 1024);
+    if (regs_cta > 0 && regs_sm / regs_cta < n) n = regs_sm / regs_cta;
+    if (512 / tmem_cols < n) n = 512 / tmem_cols;
+    if (n > 2048 / TM) n = 2048 / TM;
+    if (n > 32) n = 32;
+    if (getenv("VB_DEBUG"))
+        fprintf(stderr, "[vb] tc kernel: smem=%d regs=%d tmem=%d -> %d CTAs/SM\n", smem, fa.numRegs, tmem_cols, n);
+    *per_sm = n < 1 ? 1 : n;
     return 0;
 }
 
@@ -712,9 +728,8 @@ static int launch_fwd(const float* packed, const float* x, const float* h0, floa
     int rc = upload_constants(packed, C::C_TOTAL, stream, &dev, &capturing);
     if (rc) return rc;
     int per_sm = 1;
-    rc = grid_cap(liquid_fwd_tc_kernel<C>, FwdSmem<C>::BYTES, &per_sm);
+    rc = grid_cap(liquid_fwd_tc_kernel<C>, FwdSmem<C>::BYTES, 32, &per_sm);
     if (rc) return rc;
-    if (per_sm > 512 / 32) per_sm = 512 / 32;            // TMEM: 32 columns per CTA
     int64_t n_tiles = (B + TM - 1) / TM;
     int64_t cap = (int64_t)device_sms() * per_sm;
     int grid = (int)(n_tiles < cap ? n_tiles : cap);
@@ -729,9 +744,8 @@ static int launch_fwd(const float* packed, const float* x, const float* h0, floa
 template <class C>
 static int bwd_grid(int64_t B, int* grid_out) {
     int per_sm = 1;
-    int rc = grid_cap(liquid_bwd_tc_kernel<C>, BwdSmem<C>::BYTES, &per_sm);
+    int rc = grid_cap(liquid_bwd_tc_kernel<C>, BwdSmem<C>::BYTES, 128, &per_sm);
     if (rc) return rc;
-    if (per_sm > 512 / 128) per_sm = 512 / 128;          // TMEM: 128 columns per CTA
     int64_t n_tiles = (B + TM - 1) / TM;
     int64_t cap = (int64_t)device_sms() * per_sm;
     int grid = (int)(n_tiles < cap ? n_tiles : cap);
