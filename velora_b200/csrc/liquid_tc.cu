@@ -1,5 +1,12 @@
 // Tensor-core (tcgen05 / TMEM) kernels for the 20-neuron class of LiquidNCPNetwork.
 //
+// Measured notes (profiles/r01): one tcgen05.mma costs the issuing CTA ~60-95 cycles of serial latency whatever its shape
+// (N = 16..96, M = 64/128, SS or TS operands) and ~47-50 cycles of SM time when two CTAs interleave, so the design
+// minimises the NUMBER of MMAs per step (12 heads + 12 dz + 8 dW) rather than their size; building the two 64-bit
+// descriptors at issue time is free (it hides inside that latency; a precomputed table was slower).
+// cudaOccupancyMaxActiveBlocksPerMultiprocessor reports 1 CTA/SM for any kernel that allocates TMEM; the real limits
+// (shared memory, registers, 512 TMEM columns) allow 4 (backward) and 8 (forward) here.
+//
 // Why: the FFMA kernels (liquid_small.cu) spend ~2200 of their 4240 warp-instructions per step on three small
 // contractions (head pre-activations, dz = ds W, dW = ds^T z) plus ~850 uniform constant loads feeding them
 // (profiles/r01).  Here those contractions run on the 5th-generation tensor cores and the CUDA cores keep only
@@ -53,7 +60,6 @@ static int upload_constants(const float* packed, int n_floats, cudaStream_t stre
 
 constexpr int TM = 128;                  // samples per CTA = threads per CTA
 constexpr int PLANE = TM * 16;           // bytes per plane
-constexpr int KP = 32;                   // padded feature count of the z / ds operand vectors (4 planes per part)
 constexpr int kFlush = 8;                // steps between flushes of the truncating dW accumulator
 
 template <int I_, int NI_, int NC_, int O_>
@@ -63,12 +69,16 @@ struct Cfg {
     static constexpr int Ip = ceil4(I), Kp = ceil4(K);
     static constexpr int WIN_T = 0, B_IN = WIN_T + I * NIp, WH_T = B_IN + NIp, B_H = WH_T + K * H4, WOUT = B_H + H4,
                          B_OUT = WOUT + O * NCp, F_TOTAL = B_OUT + Op, WIN = F_TOTAL, WH = WIN + NI * Ip, C_TOTAL = WH + H4 * Kp;
-    static constexpr int ONE = K;        // index of the constant-one feature (bias row)
+    // z~ = [a (NI) | h (NC) | 1 at ONE | 0..] : 24 features = three 8-feature planes per bf16 part
+    static constexpr int ONE = K;
     static_assert(H4 == 32, "tensor-core path: 4 * Nc must be 32 (Nc = 8)");
     static_assert(K + 1 <= 24, "tensor-core path: Ni + Nc + 1 must fit three 8-feature planes");
-    static constexpr int N_SMALL = I * NI + O * NC + NI + O;   // register-accumulated small gradients
-    static_assert(N_SMALL <= 96, "tensor-core backward keeps the small layers' gradients in registers: I*Ni + O*Nc + Ni + O <= 96");
     static_assert(C_TOTAL <= kConstFloats, "constant-bank budget");
+    // small-layer gradients reduced on the CUDA cores: dW_in, dW_out, db_in, db_out
+    static constexpr int N_SMALL = I * NI + O * NC + NI + O;
+    static constexpr int SROWS = NI + I + O + NC;      // fp32 rows du | x | dy | m of the transposition buffer
+    static_assert(SROWS * 132 * 4 <= 12 * PLANE, "transposition buffer must fit the ds planes");
+    static_assert((16 * PLANE + NC * 128 * 4) / 4 < 0xfffe, "row offsets are packed in 16 bits");
 };
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
@@ -120,6 +130,24 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // x0, x1 -> three packed bf16x2 words (low half = x0): x = p1 + p2 + p3 to 24 bits
 __device__ __forceinline__ void split3(float x0, float x1, uint32_t& p1, uint32_t& p2, uint32_t& p3) {
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p1) : "f"(x1), "f"(x0));
@@ -130,6 +158,8 @@ __device__ __forceinline__ void split3(float x0, float x1, uint32_t& p1, uint32_
 }
 
 // eight consecutive features of this thread's sample -> one 16-byte chunk in each of the three part planes
+// (CPP = chunks per part: 3 for the z~ planes, 4 for the ds planes)
+template <int CPP>
 __device__ __forceinline__ void store_chunk3(unsigned char* planes, int chunk, int row, const float (&f)[8]) {
     uint4 a, b, c;
     split3(f[0], f[1], a.x, b.x, c.x);
@@ -137,25 +167,27 @@ __device__ __forceinline__ void store_chunk3(unsigned char* planes, int chunk, i
     split3(f[4], f[5], a.z, b.z, c.z);
     split3(f[6], f[7], a.w, b.w, c.w);
     uint4* p = reinterpret_cast<uint4*>(planes);
-    p[(0 * 4 + chunk) * TM + row] = a;
-    p[(1 * 4 + chunk) * TM + row] = b;
-    p[(2 * 4 + chunk) * TM + row] = c;
+    p[(0 * CPP + chunk) * TM + row] = a;
+    p[(1 * CPP + chunk) * TM + row] = b;
+    p[(2 * CPP + chunk) * TM + row] = c;
 }
 
 // product order for one per-step contraction: small terms first, b1*b1 last (the accumulator truncates)
-// D[128 x 32] = A(parts, K-major planes, K = 32) * B(parts)^T : 12 MMAs, issued by one thread
-__device__ __forceinline__ void issue_contraction(uint32_t d_tmem, uint32_t a_planes, uint32_t b_planes) {
+// heads: D[128 x 32] = z~ W^T.  z~ planes: 3 chunks per part (24 features) followed by ONE shared all-zero plane (index 9)
+// that stands in for features 24..31 of every part: the second K-step's descriptor reaches it through its own LBO.
+// 6 part-products x 2 K-steps = 12 MMAs, issued by one thread.
+__device__ __forceinline__ void issue_heads(uint32_t d_tmem, uint32_t z_planes, uint32_t w_planes) {
     constexpr uint32_t idesc = make_idesc(128, 32, 0, 0);
 #pragma unroll
     for (int p = 0; p < 6; ++p) {
         const int pa = (p == 0) ? 1 : (p == 1) ? 0 : (p == 2) ? 2 : (p == 3) ? 0 : (p == 4) ? 1 : 0;
         const int pb = (p == 0) ? 1 : (p == 1) ? 2 : (p == 2) ? 0 : (p == 3) ? 1 : (p == 4) ? 0 : 0;
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-            uint64_t ad = make_desc(a_planes + (pa * 4 + 2 * ks) * PLANE, PLANE, 128);
-            uint64_t bd = make_desc(b_planes + (pb * 4 + 2 * ks) * (32 * 16), 32 * 16, 128);
-            mma_bf16(d_tmem, ad, bd, idesc, (p | ks) != 0);
-        }
+        uint64_t a0 = make_desc(z_planes + (pa * 3 + 0) * PLANE, PLANE, 128);                   // chunks 0, 1
+        uint64_t a1 = make_desc(z_planes + (pa * 3 + 2) * PLANE, (9 - (pa * 3 + 2)) * PLANE, 128);   // chunk 2, zero plane
+        uint64_t b0 = make_desc(w_planes + (pb * 4 + 0) * (32 * 16), 32 * 16, 128);
+        uint64_t b1 = make_desc(w_planes + (pb * 4 + 2) * (32 * 16), 32 * 16, 128);
+        mma_bf16(d_tmem, a0, b0, idesc, p != 0);
+        mma_bf16(d_tmem, a1, b1, idesc, 1);
     }
 }
 
@@ -222,7 +254,7 @@ __device__ __forceinline__ void inter_layer(const float (&x)[C::I], float (&u)[C
         for (int j = 0; j < C::NI; ++j) u[j] = fmaf(x[i], c_p[C::WIN_T + i * C::NIp + j], u[j]);
 }
 
-// z~ = [a (NI), h (NC), 1, 0...] -> chunks 0..2 of the three part planes
+// z~ = [a (NI), h (NC), 1, 0..] -> chunks 0..2 of the three part planes
 template <class C>
 __device__ __forceinline__ void store_z(unsigned char* zP, int row, const float (&a)[C::NI], const float (&h)[C::NC]) {
     float zt[24];
@@ -238,15 +270,15 @@ __device__ __forceinline__ void store_z(unsigned char* zP, int row, const float 
         float f[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) f[e] = zt[8 * c + e];
-        store_chunk3(zP, c, row, f);
+        store_chunk3<3>(zP, c, row, f);
     }
 }
 
 // ================================================================================================ forward
 template <class C>
 struct FwdSmem {
-    static constexpr int Z = 0;                                  // 12 planes
-    static constexpr int WB = Z + 12 * PLANE;                    // 3 parts x 4 chunks x 32 rows x 16 B
+    static constexpr int Z = 0;                                  // 9 z~ planes + the shared zero plane
+    static constexpr int WB = Z + 10 * PLANE;                    // 3 parts x 4 chunks x 32 rows x 16 B
     static constexpr int BAR = WB + 3 * 4 * 32 * 16;
     static constexpr int BYTES = BAR + 64;
 };
@@ -265,15 +297,12 @@ __global__ void __launch_bounds__(TM) liquid_fwd_tc_kernel(const float* __restri
     const bool vx = vec_flags & 1, vy = vec_flags & 2, vh = vec_flags & 4;
 
     // heads operand: B[n][k] = W_heads[k][n] for k < K, bias for k == ONE
+    // rows in NEURON-MAJOR head order n' = 4 j + hs, so that one 8-column TMEM load holds two complete neurons
     build_weight_planes(wB, [&](int n, int k) {
-        return k < C::K ? __ldg(packed + C::WH_T + k * C::H4 + n) : (k == C::ONE ? __ldg(packed + C::B_H + n) : 0.f);
+        const int col = (n & 3) * C::NCp + (n >> 2);
+        return k < C::K ? __ldg(packed + C::WH_T + k * C::H4 + col) : (k == C::ONE ? __ldg(packed + C::B_H + col) : 0.f);
     });
-    {   // zero the never-written fourth chunk of the z planes
-        uint4* p = reinterpret_cast<uint4*>(zP);
-        const uint4 z4 = make_uint4(0, 0, 0, 0);
-#pragma unroll
-        for (int part = 0; part < 3; ++part) p[(part * 4 + 3) * TM + tid] = z4;
-    }
+    reinterpret_cast<uint4*>(zP)[9 * TM + tid] = make_uint4(0, 0, 0, 0);   // the shared zero plane
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 32;" ::"r"(smem_u32(tmem_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -321,21 +350,25 @@ __global__ void __launch_bounds__(TM) liquid_fwd_tc_kernel(const float* __restri
             __syncthreads();
             if (tid == 0) {
                 tc_fence_after();
-                issue_contraction(tmem, z_addr, w_addr);
+                issue_heads(tmem, z_addr, w_addr);
                 mma_commit(bar1);
             }
             mbar_wait(bar1, ph1);
             ph1 ^= 1;
             tc_fence_after();
-            float s[32];
-            tmem_ld32(taddr, s);
             float m[C::NC];
 #pragma unroll
-            for (int j = 0; j < C::NC; ++j) {
-                float tg = tanh_f(s[0 * C::NCp + j]), th = tanh_f(s[1 * C::NCp + j]), gate = sigmoid_f(s[2 * C::NCp + j]);
-                float hn = fmaf(gate, th - tg, tg);
-                h[j] = hn;
-                m[j] = mish_f(s[3 * C::NCp + j] + hn);
+            for (int c = 0; c < C::NC / 2; ++c) {
+                float s8[8];
+                tmem_ld8(taddr + 8 * c, s8);
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj) {
+                    const int j = 2 * c + jj;
+                    float tg = tanh_f(s8[4 * jj + 0]), th = tanh_f(s8[4 * jj + 1]), gate = sigmoid_f(s8[4 * jj + 2]);
+                    float hn = fmaf(gate, th - tg, tg);
+                    h[j] = hn;
+                    m[j] = mish_f(s8[4 * jj + 3] + hn);
+                }
             }
             float yo[C::O];
 #pragma unroll
@@ -359,50 +392,56 @@ __global__ void __launch_bounds__(TM) liquid_fwd_tc_kernel(const float* __restri
 // ================================================================================================ backward
 template <class C>
 struct BwdSmem {
-    static constexpr int Z = 0;                                  // z~ parts: 12 planes
-    static constexpr int DS = Z + 12 * PLANE;                    // ds parts: 12 planes (MN-major M = 128 reads 4 planes past: WB/WT)
-    static constexpr int WB = DS + 12 * PLANE;                   // heads operand  (6 KB)
-    static constexpr int WT = WB + 3 * 4 * 32 * 16;              // dz operand     (6 KB): B[i][r] = W_heads[i][r]
-    static constexpr int BAR = WT + 3 * 4 * 32 * 16;
-    static constexpr int BYTES = BAR + 64;
-    static_assert(WT + 3 * 4 * 32 * 16 - DS >= 16 * PLANE, "M = 128 stack must stay inside the CTA's shared memory");
+    static constexpr int Z = 0;                                  // 9 z~ planes + shared zero plane
+    static constexpr int DS = Z + 10 * PLANE;                    // ds parts: 12 planes; the MN-major M = 128 stack reads 4 planes past the end
+    static constexpr int WB = DS + 12 * PLANE;                   // heads operand (6 KB), also read MN-major for dz = ds W
+    static constexpr int BAR = WB + 3 * 4 * 32 * 16;
+    static constexpr int TAIL = BAR + 64;
+    static constexpr int MSTRIP = DS + 16 * PLANE > TAIL ? DS + 16 * PLANE : TAIL;  // keep the over-read inside the CTA's window
+    static constexpr int BYTES = MSTRIP + C::NC * TM * 4;                           // m[Nc][128] fp32, parked between gating and the small-gradient pass
 };
 
-constexpr int D3_FLOATS = TM * 64;   // per-CTA flush buffer: two 128 x 32 accumulators
+constexpr int D3_COLS = 96;                 // flush buffer columns per thread (80 used)
+constexpr int D3_FLOATS = TM * D3_COLS;     // per-CTA flush buffer
+constexpr int SBUF_STRIDE = 132;            // fp32 transposition buffer row stride (floats): 128 samples + 4 pad
 
 template <class C>
-__global__ void __launch_bounds__(TM, 3) liquid_bwd_tc_kernel(
+__global__ void __launch_bounds__(TM, 4) liquid_bwd_tc_kernel(
     const float* __restrict__ packed, const float* __restrict__ x, const float* __restrict__ h0, const float* __restrict__ h_traj,
     const float* __restrict__ dy, const float* __restrict__ dh_traj, const float* __restrict__ dh_last,
     float* __restrict__ dx, float* __restrict__ dh0, float* __restrict__ partials, float* __restrict__ d3buf,
-    int64_t B, int T, int vec_flags) {
+    int64_t B, int T, int vec_flags, long long* __restrict__ trace) {
     using S = BwdSmem<C>;
+#define VB_TRACE(slot) do { if (trace && blockIdx.x == 0 && tid == 0 && t >= T - 4) trace[(T - 1 - t) * 16 + (slot)] = clock64(); } while (0)
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* zP = smem + S::Z;
     unsigned char* dsP = smem + S::DS;
     unsigned char* wB = smem + S::WB;
-    unsigned char* wT = smem + S::WT;
-    uint64_t* bar1 = reinterpret_cast<uint64_t*>(smem + S::BAR);
-    uint64_t* bar2 = bar1 + 1;
-    uint64_t* bar3 = bar1 + 2;
+    float* sbuf = reinterpret_cast<float*>(dsP);                   // fp32 [SROWS][SBUF_STRIDE], aliases the ds planes between MMAs
+    float* mstrip = reinterpret_cast<float*>(smem + S::MSTRIP);
+    uint64_t* bar1 = reinterpret_cast<uint64_t*>(smem + S::BAR);   // heads ready
+    uint64_t* bar2 = bar1 + 1;                                     // dz ready
+    uint64_t* bar3 = bar1 + 2;                                     // dW batch done (z~ and ds planes may be overwritten)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::BAR + 32);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool vx = vec_flags & 1, vy = vec_flags & 2, vh = vec_flags & 4;
 
+    // heads operand B[n][k]: W_heads[k][n] for k < K, bias for k == ONE, zero elsewhere
+    // rows in NEURON-MAJOR head order n' = 4 j + hs, so that one 8-column TMEM load holds two complete neurons
     build_weight_planes(wB, [&](int n, int k) {
-        return k < C::K ? __ldg(packed + C::WH_T + k * C::H4 + n) : (k == C::ONE ? __ldg(packed + C::B_H + n) : 0.f);
+        const int col = (n & 3) * C::NCp + (n >> 2);
+        return k < C::K ? __ldg(packed + C::WH_T + k * C::H4 + col) : (k == C::ONE ? __ldg(packed + C::B_H + col) : 0.f);
     });
-    // dz operand: B[i][r] = W_heads[i][r] (weight of input i to (head, neuron) r); rows i >= K are zero
-    build_weight_planes(wT, [&](int i, int r) { return i < C::K ? __ldg(packed + C::WH_T + i * C::H4 + r) : 0.f; });
-    {
-        uint4* p = reinterpret_cast<uint4*>(zP);
+    {   // zero plane, the ds area and the over-read tail (so the first M = 128 stack read is finite)
         const uint4 z4 = make_uint4(0, 0, 0, 0);
-#pragma unroll
-        for (int part = 0; part < 3; ++part) p[(part * 4 + 3) * TM + tid] = z4;
+        reinterpret_cast<uint4*>(zP)[9 * TM + tid] = z4;
+        uint4* q = reinterpret_cast<uint4*>(dsP);
+        for (int i = tid; i < (S::BYTES - S::DS) / 16; i += TM)
+            if (i < 12 * TM || i >= (S::TAIL - S::DS + 15) / 16) q[i] = z4;
     }
-    float* d3row = d3buf + (int64_t)blockIdx.x * D3_FLOATS + tid * 64;   // this thread's rows of the two dW accumulators
+    float* d3row = d3buf + (int64_t)blockIdx.x * D3_FLOATS + tid * D3_COLS;   // this thread's (stack) row of the dW accumulator
 #pragma unroll
-    for (int q = 0; q < 16; ++q) reinterpret_cast<float4*>(d3row)[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = 0; q < D3_COLS / 4; ++q) reinterpret_cast<float4*>(d3row)[q] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(tmem_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -410,7 +449,7 @@ __global__ void __launch_bounds__(TM, 3) liquid_bwd_tc_kernel(
     if (tid == 0) {
         mbar_init(bar1, 1);
         mbar_init(bar2, 1);
-        mbar_init(bar3, 2);
+        mbar_init(bar3, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     fence_async_smem();
@@ -419,42 +458,48 @@ __global__ void __launch_bounds__(TM, 3) liquid_bwd_tc_kernel(
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
-    const uint32_t z_addr = smem_u32(zP), ds_addr = smem_u32(dsP), wb_addr = smem_u32(wB), wt_addr = smem_u32(wT);
-    uint32_t ph1 = 0, ph2 = 0, ph3 = 0;
-    bool wgrad_pending = false;   // a dW batch whose completion has not been waited for yet
+    const uint32_t z_addr = smem_u32(zP), ds_addr = smem_u32(dsP), wb_addr = smem_u32(wB);
+    // TMEM columns: [0,32) heads, then dz (reused);  [32,112) dW = stack(ds)^T x [z~_b1 | z~_b2 | z~_b3 | 0]
+    uint32_t ph = 0;              // all three barriers complete exactly once per step: one shared phase bit
     int since_flush = 0;          // dW batches accumulated in TMEM since the last flush (0 => next batch overwrites)
 
-    // gradients of the small layers: per-sample register accumulators, reduced across the CTA once at the end
-    float g_win[C::I][C::NI], g_wout[C::O][C::NC], g_bin[C::NI], g_bout[C::O];
+    // small-layer gradients: unit u = (entry e, sample quarter q); thread owns units tid, tid+128, tid+256
+    //   entries: [0, I*NI) dW_in[i][j] = sum x_i du_j ; then O*NC: dW_out[o][j] = sum dy_o m_j ; then NI: db_in ; then O: db_out
+    constexpr int R_DU = 0, R_X = C::NI, R_DY = C::NI + C::I, R_M = C::NI + C::I + C::O;
+    constexpr int N_UNITS = 4 * C::N_SMALL;
+    constexpr int UPT = (N_UNITS + TM - 1) / TM;   // units per thread
+    float g_small[UPT];
+    uint32_t rows[UPT];           // rowA | rowB << 16 (float offsets into sbuf); rowB = 0xffff: bias entry (plain sum of rowA); 0xfffe: no unit
 #pragma unroll
-    for (int i = 0; i < C::I; ++i)
-#pragma unroll
-        for (int j = 0; j < C::NI; ++j) g_win[i][j] = 0.f;
-#pragma unroll
-    for (int o = 0; o < C::O; ++o) {
-        g_bout[o] = 0.f;
-#pragma unroll
-        for (int j = 0; j < C::NC; ++j) g_wout[o][j] = 0.f;
+    for (int k = 0; k < UPT; ++k) {
+        g_small[k] = 0.f;
+        const int u = tid + k * TM;
+        const int e = u % C::N_SMALL, q = (u / C::N_SMALL) & 3;
+        int ra, rb;
+        bool m_row = false;
+        if (e < C::I * C::NI) { ra = R_X + e / C::NI; rb = R_DU + e % C::NI; }
+        else if (e < C::I * C::NI + C::O * C::NC) { const int f = e - C::I * C::NI; ra = R_DY + f / C::NC; rb = f % C::NC; m_row = true; }
+        else if (e < C::I * C::NI + C::O * C::NC + C::NI) { ra = R_DU + (e - C::I * C::NI - C::O * C::NC); rb = -1; }
+        else { ra = R_DY + (e - C::I * C::NI - C::O * C::NC - C::NI); rb = -1; }
+        const uint32_t oa = ra * SBUF_STRIDE + q * 32;
+        // m rows live in the strip ([Nc][128] floats right after the plane window): offset relative to sbuf
+        const uint32_t ob = rb < 0 ? 0xffffu
+                                   : (m_row ? (uint32_t)((S::MSTRIP - S::DS) / 4 + rb * TM + q * 32) : (uint32_t)(rb * SBUF_STRIDE + q * 32));
+        rows[k] = (u >= N_UNITS) ? 0xfffe0000u : (oa | (ob << 16));
     }
-#pragma unroll
-    for (int j = 0; j < C::NI; ++j) g_bin[j] = 0.f;
 
-    auto flush_dw = [&]() {   // all threads; requires the last dW batch to be complete
+    auto flush_dw = [&]() {   // all threads; requires the dW batch to be complete
         tc_fence_after();
-        float v[32];
-        tmem_ld32(taddr + 64, v);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            float4 a = reinterpret_cast<float4*>(d3row)[q];
-            a.x += v[4 * q]; a.y += v[4 * q + 1]; a.z += v[4 * q + 2]; a.w += v[4 * q + 3];
-            reinterpret_cast<float4*>(d3row)[q] = a;
-        }
-        tmem_ld32(taddr + 96, v);
+        for (int g = 0; g < 3; ++g) {
+            float v[32];
+            tmem_ld32(taddr + 32 + 32 * g, v);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            float4 a = reinterpret_cast<float4*>(d3row)[8 + q];
-            a.x += v[4 * q]; a.y += v[4 * q + 1]; a.z += v[4 * q + 2]; a.w += v[4 * q + 3];
-            reinterpret_cast<float4*>(d3row)[8 + q] = a;
+            for (int q = 0; q < 8; ++q) {
+                float4 a4 = reinterpret_cast<float4*>(d3row)[8 * g + q];
+                a4.x += v[4 * q]; a4.y += v[4 * q + 1]; a4.z += v[4 * q + 2]; a4.w += v[4 * q + 3];
+                reinterpret_cast<float4*>(d3row)[8 * g + q] = a4;
+            }
         }
         since_flush = 0;
     };
@@ -467,139 +512,186 @@ __global__ void __launch_bounds__(TM, 3) liquid_bwd_tc_kernel(
 #pragma unroll
         for (int j = 0; j < C::NC; ++j) dhc[j] = 0.f;
         if (valid && dh_last) ldg_row<C::NC>(dhc, dh_last + b * C::NC, vh);
+        // x_t is prefetched one step ahead (it is needed first thing); h_{t-1} and dy_t are requested at the top of the
+        // step and consumed after the inter layer / Mish, which covers their latency without extra live registers
+        float xn[C::I], dyn[C::O];
+#pragma unroll
+        for (int i = 0; i < C::I; ++i) xn[i] = 0.f;
+#pragma unroll
+        for (int o = 0; o < C::O; ++o) dyn[o] = 0.f;
+        if (valid) {
+            ldg_row<C::I>(xn, x + (b * T + T - 1) * C::I, vx);
+            ldg_row<C::O>(dyn, dy + (b * T + T - 1) * C::O, vy);
+        }
         for (int t = T - 1; t >= 0; --t) {
-            // ---------------- loads of this step (one to two full sectors per thread)
-            float xr[C::I], dyr[C::O], hp[C::NC], dhe[C::NC];
+            float xr[C::I], dyr[C::O], hp[C::NC];
 #pragma unroll
-            for (int i = 0; i < C::I; ++i) xr[i] = 0.f;
+            for (int i = 0; i < C::I; ++i) xr[i] = xn[i];
 #pragma unroll
-            for (int o = 0; o < C::O; ++o) dyr[o] = 0.f;
+            for (int o = 0; o < C::O; ++o) dyr[o] = dyn[o];
 #pragma unroll
-            for (int j = 0; j < C::NC; ++j) { hp[j] = 0.f; dhe[j] = 0.f; }
+            for (int j = 0; j < C::NC; ++j) hp[j] = 0.f;
             if (valid) {
-                ldg_row<C::I>(xr, x + (b * T + t) * C::I, vx);
-                ldg_row<C::O>(dyr, dy + (b * T + t) * C::O, vy);
                 if (t > 0) ldg_row<C::NC>(hp, h_traj + (b * T + t - 1) * C::NC, vh);
                 else if (h0) ldg_row<C::NC>(hp, h0 + b * C::NC, vh);
-                if (dh_traj) ldg_row<C::NC>(dhe, dh_traj + (b * T + t) * C::NC, vh);
+                if (t > 0) {
+                    ldg_row<C::I>(xn, x + (b * T + t - 1) * C::I, vx);
+                    ldg_row<C::O>(dyn, dy + (b * T + t - 1) * C::O, vy);
+                }
             }
+            VB_TRACE(0);
             // ---------------- recompute: inter layer on CUDA cores, heads on the tensor cores
-            float a[C::NI], dmu[C::NI];
+            float dmu[C::NI];
             {
-                float u[C::NI];
+                float a[C::NI], u[C::NI];
                 inter_layer<C>(xr, u);
 #pragma unroll
                 for (int j = 0; j < C::NI; ++j) a[j] = mish_fwd_grad(u[j], dmu[j]);
+                store_z<C>(zP, tid, a, hp);     // the previous dW batch was waited for at the end of the previous step
             }
-            if (wgrad_pending) {   // the previous step's dW MMAs still read the z / ds planes
-                mbar_wait(bar3, ph3);
-                ph3 ^= 1;
-                wgrad_pending = false;
-                if (since_flush >= kFlush) flush_dw();
-            }
-            store_z<C>(zP, tid, a, hp);
+            VB_TRACE(1);
             fence_async_smem();
             tc_fence_before();
-            __syncthreads();
+            __syncthreads();                    // also: everybody is done reading the fp32 buffer of the previous step
+            VB_TRACE(2);
             if (tid == 0) {
                 tc_fence_after();
-                issue_contraction(tmem + 0, z_addr, wb_addr);
+                issue_heads(tmem + 0, z_addr, wb_addr);
                 mma_commit(bar1);
             }
-            mbar_wait(bar1, ph1);
-            ph1 ^= 1;
+            VB_TRACE(3);
+            mbar_wait(bar1, ph);
             tc_fence_after();
-            float s[32];
-            tmem_ld32(taddr + 0, s);
-            // ---------------- gating derivatives; ds -> planes
-            float m[C::NC];
+            VB_TRACE(4);
+            // ---------------- gating derivatives, two neurons (= one 8-feature chunk of ds) at a time
+            {
+                const float* dhe_p = (valid && dh_traj) ? dh_traj + (b * T + t) * C::NC : nullptr;
 #pragma unroll
-            for (int j = 0; j < C::NC; ++j) {
-                float tg = tanh_f(s[0 * C::NCp + j]), th = tanh_f(s[1 * C::NCp + j]), gate = sigmoid_f(s[2 * C::NCp + j]);
-                float hn = fmaf(gate, th - tg, tg);
-                float dmc;
-                m[j] = mish_fwd_grad(s[3 * C::NCp + j] + hn, dmc);
-                float dm = 0.f;
+                for (int c = 0; c < C::NC / 2; ++c) {
+                    float s8[8];
+                    tmem_ld8(taddr + 8 * c, s8);
 #pragma unroll
-                for (int o = 0; o < C::O; ++o) dm = fmaf(dyr[o], c_p[C::WOUT + o * C::NCp + j], dm);
-                float dc = dm * dmc;
-                float dhn = dc + dhc[j] + dhe[j];
-                float omg = 1.0f - gate;
-                s[0 * C::NCp + j] = dhn * omg * (1.0f - tg * tg);
-                s[1 * C::NCp + j] = dhn * gate * (1.0f - th * th);
-                s[2 * C::NCp + j] = dhn * (th - tg) * gate * omg;
-                s[3 * C::NCp + j] = dc;
+                    for (int jj = 0; jj < 2; ++jj) {
+                        const int j = 2 * c + jj;
+                        float tg = tanh_f(s8[4 * jj + 0]), th = tanh_f(s8[4 * jj + 1]), gate = sigmoid_f(s8[4 * jj + 2]);
+                        float hn = fmaf(gate, th - tg, tg);
+                        float dmc;
+                        mstrip[j * TM + tid] = mish_fwd_grad(s8[4 * jj + 3] + hn, dmc);
+                        float dm = 0.f;
+#pragma unroll
+                        for (int o = 0; o < C::O; ++o) dm = fmaf(dyr[o], c_p[C::WOUT + o * C::NCp + j], dm);
+                        float dc = dm * dmc;
+                        float dhn = dc + dhc[j] + (dhe_p ? __ldg(dhe_p + j) : 0.f);
+                        float omg = 1.0f - gate;
+                        s8[4 * jj + 0] = dhn * omg * (1.0f - tg * tg);       // ds_g
+                        s8[4 * jj + 1] = dhn * gate * (1.0f - th * th);      // ds_h
+                        s8[4 * jj + 2] = dhn * (th - tg) * gate * omg;       // ds_f (both f heads)
+                        s8[4 * jj + 3] = dc;                                 // ds_proj
+                    }
+                    store_chunk3<4>(dsP, c, tid, s8);
+                }
             }
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                float f[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] = s[8 * c + e];
-                store_chunk3(dsP, c, tid, f);
-            }
+            VB_TRACE(5);
             fence_async_smem();
-            tc_fence_before();
+            tc_fence_before();     // also orders this thread's TMEM read of the heads before dz overwrites those columns
             __syncthreads();
+            VB_TRACE(6);
             if (lane == 0) {
-                tc_fence_after();
-                if (warp == 1) {            // dz = ds W : K-major ds planes x dz operand
-                    issue_contraction(tmem + 32, ds_addr, wt_addr);
+                if (warp == 1) {            // dz = ds W
+                    tc_fence_after();
+                    constexpr uint32_t idesc2 = make_idesc(128, 32, 0, 1);
+#pragma unroll
+                    for (int p = 0; p < 6; ++p) {
+                        const int pa = (p == 0) ? 1 : (p == 1) ? 0 : (p == 2) ? 2 : (p == 3) ? 0 : (p == 4) ? 1 : 0;
+                        const int pb = (p == 0) ? 1 : (p == 1) ? 2 : (p == 2) ? 0 : (p == 3) ? 1 : (p == 4) ? 0 : 0;
+#pragma unroll
+                        for (int ks = 0; ks < 2; ++ks)
+                            mma_bf16(tmem + 0, make_desc(ds_addr + (pa * 4 + 2 * ks) * PLANE, PLANE, 128),
+                                     make_desc(wb_addr + pb * (4 * 32 * 16) + ks * 256, 128, 32 * 16), idesc2, (p | ks) != 0);
+                    }
                     mma_commit(bar2);
-                } else if (warp >= 2) {     // dW += ds^T z~ : MN-major reads of the same planes, K = 16 samples per MMA
-                    constexpr uint32_t idesc3 = make_idesc(128, 32, 1, 1);
-                    const uint32_t dcol = tmem + (warp == 2 ? 64 : 96);
-                    const int ks0 = (warp == 2) ? 0 : 4;
+                } else if (warp == 2) {     // dW (+ bias column) += stack(ds)^T x [z~_b1 | z~_b2 | z~_b3 | 0] : all nine part-products at once
+                    tc_fence_after();
+                    constexpr uint32_t idesc3 = make_idesc(128, 80, 1, 1);
 #pragma unroll
-                    for (int zp = 2; zp >= 0; --zp)          // small parts first
-#pragma unroll
-                        for (int k4 = 0; k4 < 4; ++k4) {
-                            const int ks = ks0 + k4;
-                            uint64_t ad = make_desc(ds_addr + ks * 256, 128, PLANE);                    // M = [b1|b2|b3|x] stack
-                            uint64_t bd = make_desc(z_addr + zp * 4 * PLANE + ks * 256, 128, PLANE);    // N = 32 features of part zp
-                            mma_bf16(dcol, ad, bd, idesc3, (since_flush != 0) || zp != 2 || k4 != 0);
-                        }
+                    for (int ks = 0; ks < 8; ++ks)
+                        mma_bf16(tmem + 32, make_desc(ds_addr + ks * 256, 128, PLANE), make_desc(z_addr + ks * 256, 128, PLANE), idesc3,
+                                 !(since_flush == 0 && ks == 0));
                     mma_commit(bar3);
                 }
             }
-            wgrad_pending = true;
             since_flush += 1;
-            // small-layer gradients that do not need dz (overlap with the tensor cores)
-#pragma unroll
-            for (int o = 0; o < C::O; ++o) {
-                g_bout[o] += dyr[o];
-#pragma unroll
-                for (int j = 0; j < C::NC; ++j) g_wout[o][j] = fmaf(dyr[o], m[j], g_wout[o][j]);
-            }
-            mbar_wait(bar2, ph2);
-            ph2 ^= 1;
+            VB_TRACE(7);
+            mbar_wait(bar2, ph);
             tc_fence_after();
-            float dz[32];
-            tmem_ld32(taddr + 32, dz);
+            VB_TRACE(8);
             float du[C::NI];
+            {
+                float dz[16];
+                tmem_ld16(taddr + 0, dz);
 #pragma unroll
-            for (int j = 0; j < C::NI; ++j) {
-                du[j] = dz[j] * dmu[j];
-                g_bin[j] += du[j];
-            }
-#pragma unroll
-            for (int j = 0; j < C::NC; ++j) dhc[j] = dz[C::NI + j];
-            float dxr[C::I];
-#pragma unroll
-            for (int i = 0; i < C::I; ++i) dxr[i] = 0.f;
-#pragma unroll
-            for (int j = 0; j < C::NI; ++j)
-#pragma unroll
-                for (int i = 0; i < C::I; ++i) {
-                    dxr[i] = fmaf(du[j], c_p[C::WIN + j * C::Ip + i], dxr[i]);
-                    g_win[i][j] = fmaf(xr[i], du[j], g_win[i][j]);
+                for (int i = 0; i < 16; ++i) {
+                    if (i < C::NI) du[i < C::NI ? i : 0] = dz[i] * dmu[i < C::NI ? i : 0];
+                    else if (i < C::K) dhc[(i - C::NI) >= 0 ? (i - C::NI) : 0] = dz[i];
                 }
-            if (valid && dx) stg_row<C::I>(dx + (b * T + t) * C::I, dxr, vx);
+                float dz2[8];
+                tmem_ld8(taddr + 16, dz2);
+#pragma unroll
+                for (int i = 16; i < 24; ++i) {
+                    if (i < C::NI) du[i < C::NI ? i : 0] = dz2[i - 16] * dmu[i < C::NI ? i : 0];
+                    else if (i < C::K) dhc[(i - C::NI) < C::NC ? (i - C::NI) : 0] = dz2[i - 16];
+                }
+            }
+            {
+                float dxr[C::I];
+#pragma unroll
+                for (int i = 0; i < C::I; ++i) dxr[i] = 0.f;
+#pragma unroll
+                for (int j = 0; j < C::NI; ++j)
+#pragma unroll
+                    for (int i = 0; i < C::I; ++i) dxr[i] = fmaf(du[j], c_p[C::WIN + j * C::Ip + i], dxr[i]);
+                if (valid && dx) stg_row<C::I>(dx + (b * T + t) * C::I, dxr, vx);
+            }
+            // ---------------- small-layer gradients: fp32 transposition through the (now idle) ds planes
+            VB_TRACE(9);
+            mbar_wait(bar3, ph);       // the dW batch has finished reading the z~ and ds planes
+            ph ^= 1;
+            VB_TRACE(10);
+            if (since_flush >= kFlush) flush_dw();
+#pragma unroll
+            for (int j = 0; j < C::NI; ++j) sbuf[(R_DU + j) * SBUF_STRIDE + tid] = du[j];
+#pragma unroll
+            for (int i = 0; i < C::I; ++i) sbuf[(R_X + i) * SBUF_STRIDE + tid] = xr[i];
+#pragma unroll
+            for (int o = 0; o < C::O; ++o) sbuf[(R_DY + o) * SBUF_STRIDE + tid] = dyr[o];
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < UPT; ++k) {
+                const uint32_t oa = rows[k] & 0xffffu, ob = rows[k] >> 16;
+                if (ob < 0xfffeu) {
+                    const float4* pa = reinterpret_cast<const float4*>(sbuf + oa);
+                    const float4* pb = reinterpret_cast<const float4*>(sbuf + ob);
+                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;      // independent chains: the loop is latency bound otherwise
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        float4 va = pa[q], vb = pb[q];
+                        a0 = fmaf(va.x, vb.x, a0); a1 = fmaf(va.y, vb.y, a1); a2 = fmaf(va.z, vb.z, a2); a3 = fmaf(va.w, vb.w, a3);
+                    }
+                    g_small[k] += (a0 + a1) + (a2 + a3);
+                } else if (ob == 0xffffu) {
+                    const float4* pa = reinterpret_cast<const float4*>(sbuf + oa);
+                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        float4 va = pa[q];
+                        a0 += va.x; a1 += va.y; a2 += va.z; a3 += va.w;
+                    }
+                    g_small[k] += (a0 + a1) + (a2 + a3);
+                }
+            }
+            VB_TRACE(11);
         }
         if (valid && dh0) stg_row<C::NC>(dh0 + b * C::NC, dhc, vh);
-    }
-    if (wgrad_pending) {
-        mbar_wait(bar3, ph3);
-        ph3 ^= 1;
     }
     if (since_flush > 0) flush_dw();
     tc_fence_before();
@@ -608,59 +700,37 @@ __global__ void __launch_bounds__(TM, 3) liquid_bwd_tc_kernel(
 
     // ---------------- per-CTA partial gradient row (F layout)
     float* prow = partials + (int64_t)blockIdx.x * C::F_TOTAL;
-    // heads: dW[i][r] = sum over the three stacked part rows of both accumulators; column ONE is the bias gradient
-    __threadfence_block();
+    for (int idx = tid; idx < C::F_TOTAL; idx += TM) prow[idx] = 0.f;
+    float* units = reinterpret_cast<float*>(smem);   // [N_UNITS]
+#pragma unroll
+    for (int k = 0; k < UPT; ++k)
+        if (tid + k * TM < N_UNITS) units[tid + k * TM] = g_small[k];
     __syncthreads();
     {
         const float* d3 = d3buf + (int64_t)blockIdx.x * D3_FLOATS;
-        for (int e = tid; e < 32 * 32; e += TM) {
-            const int r = e >> 5, i = e & 31;
-            float acc = 0.f;
+        // stack row (pa, r) x column (pb, i): dW_heads[i][r] (i < K), db_heads[r] (i == ONE)
+        for (int e = tid; e < 32 * 24; e += TM) {
+            const int r = e / 24, i = e % 24;           // r = 4 j + hs (neuron-major)
+            const int col = (r & 3) * C::NCp + (r >> 2);
+            if (i < C::K || i == C::ONE) {
+                float acc = 0.f;
 #pragma unroll
-            for (int part = 0; part < 3; ++part) {
-                const float* row = d3 + (part * 32 + r) * 64;
-                acc += row[i] + row[32 + i];
+                for (int pa = 0; pa < 3; ++pa)
+#pragma unroll
+                    for (int pb = 2; pb >= 0; --pb) acc += d3[(pa * 32 + r) * D3_COLS + pb * 24 + i];
+                if (i < C::K) prow[C::WH_T + i * C::H4 + col] = acc;
+                else prow[C::B_H + col] = acc;
             }
-            if (i < C::K) prow[C::WH_T + i * C::H4 + r] = acc;
-            else if (i == C::ONE) prow[C::B_H + r] = acc;
         }
-    }
-    // small layers: reduce the per-sample registers over the CTA through shared memory (planes are free now)
-    float* red = reinterpret_cast<float*>(smem);   // [N_SMALL][TM + 1]
-    {
-        int k = 0;
-#pragma unroll
-        for (int i = 0; i < C::I; ++i)
-#pragma unroll
-            for (int j = 0; j < C::NI; ++j) red[(k++) * (TM + 1) + tid] = g_win[i][j];
-#pragma unroll
-        for (int o = 0; o < C::O; ++o)
-#pragma unroll
-            for (int j = 0; j < C::NC; ++j) red[(k++) * (TM + 1) + tid] = g_wout[o][j];
-#pragma unroll
-        for (int j = 0; j < C::NI; ++j) red[(k++) * (TM + 1) + tid] = g_bin[j];
-#pragma unroll
-        for (int o = 0; o < C::O; ++o) red[(k++) * (TM + 1) + tid] = g_bout[o];
-    }
-    __syncthreads();
-    for (int k = tid; k < C::N_SMALL; k += TM) {
-        float acc = 0.f;
-        for (int s2 = 0; s2 < TM; ++s2) acc += red[k * (TM + 1) + s2];
-        int idx;
-        if (k < C::I * C::NI) idx = C::WIN_T + (k / C::NI) * C::NIp + (k % C::NI);
-        else if (k < C::I * C::NI + C::O * C::NC) { int q = k - C::I * C::NI; idx = C::WOUT + (q / C::NC) * C::NCp + (q % C::NC); }
-        else if (k < C::I * C::NI + C::O * C::NC + C::NI) idx = C::B_IN + (k - C::I * C::NI - C::O * C::NC);
-        else idx = C::B_OUT + (k - C::I * C::NI - C::O * C::NC - C::NI);
-        prow[idx] = acc;
-    }
-    // padding entries of the F layout
-    for (int idx = tid; idx < C::F_TOTAL; idx += TM) {
-        bool pad = false;
-        if (idx >= C::B_IN && idx < C::WH_T) pad = (idx - C::B_IN) >= C::NI;
-        else if (idx < C::B_IN) pad = (idx % C::NIp) >= C::NI;
-        else if (idx >= C::WOUT && idx < C::B_OUT) pad = ((idx - C::WOUT) % C::NCp) >= C::NC;
-        else if (idx >= C::B_OUT) pad = (idx - C::B_OUT) >= C::O;
-        if (pad) prow[idx] = 0.f;
+        for (int e = tid; e < C::N_SMALL; e += TM) {
+            const float acc = (units[e] + units[C::N_SMALL + e]) + (units[2 * C::N_SMALL + e] + units[3 * C::N_SMALL + e]);
+            int idx;
+            if (e < C::I * C::NI) idx = C::WIN_T + (e / C::NI) * C::NIp + (e % C::NI);
+            else if (e < C::I * C::NI + C::O * C::NC) { const int f = e - C::I * C::NI; idx = C::WOUT + (f / C::NC) * C::NCp + (f % C::NC); }
+            else if (e < C::I * C::NI + C::O * C::NC + C::NI) idx = C::B_IN + (e - C::I * C::NI - C::O * C::NC);
+            else idx = C::B_OUT + (e - C::I * C::NI - C::O * C::NC - C::NI);
+            prow[idx] = acc;
+        }
     }
 }
 
@@ -771,9 +841,24 @@ static int launch_bwd(const float* packed, const float* x, const float* h0, cons
     int vf = vec_flags_for(x, dy, h0, h_traj, dh_traj, dh_last, dx, dh0, T, C::I, C::O, C::NC);
     float* partials = reinterpret_cast<float*>(ws);
     float* d3buf = partials + (int64_t)grid * C::F_TOTAL;
+    long long* trace = nullptr;
+    if (getenv("VB_TRACE")) cudaMalloc(&trace, 64 * 16 * sizeof(long long));
     liquid_bwd_tc_kernel<C><<<grid, TM, BwdSmem<C>::BYTES, stream>>>(packed, x, h0, h_traj, dy, dh_traj, dh_last, dx, dh0, partials,
-                                                                     d3buf, B, T, vf);
+                                                                     d3buf, B, T, vf, trace);
     VB_LAUNCH_CHECK();
+    if (trace) {
+        long long h[64];
+        cudaMemcpy(h, trace, sizeof(h), cudaMemcpyDeviceToHost);
+        const char* names[12] = {"top(loads issued)", "inter+mish+store_z", "sync1", "issue heads", "wait heads", "gating+store ds", "sync2", "issue dz/dW",
+                                 "wait dz", "du,dx", "wait dW", "small grads"};
+        for (int st = 0; st < 4; ++st) {
+            fprintf(stderr, "[vb trace] step %d:", st);
+            for (int k = 1; k < 12; ++k) fprintf(stderr, " %s=%lld", names[k], h[st * 16 + k] - h[st * 16 + k - 1]);
+            if (st < 3) fprintf(stderr, " | to next top=%lld", h[(st + 1) * 16] - h[st * 16 + 11]);
+            fprintf(stderr, "\n");
+        }
+        cudaFree(trace);
+    }
     if (!capturing) VB_CUDA(cudaEventRecord(g_ev[dev & 63], stream));
     reduce_partials_tc_kernel<<<(C::F_TOTAL + 31) / 32, 1024, 0, stream>>>(partials, grid, C::F_TOTAL, dpacked);
     VB_LAUNCH_CHECK();
