@@ -246,7 +246,7 @@ def run_ours(args) -> None:
     tpath = os.path.join(ROOT, "profiles", "traffic.json")      # dram bytes per launch from the committed ncu capture
     if os.path.isfile(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get("liquid_bwd_small_kernel_bytes_per_launch")
+            traffic = json.load(f).get("liquid_bwd_tc_kernel_bytes_per_launch")
 
     # ------------------------------------------------------------------ end to end: pinned host inputs, H2D + D2H inside
     hx = [torch.randn(B, T, SHAPE["I"]).pin_memory() for _ in range(2)]
@@ -326,7 +326,7 @@ def run_ours(args) -> None:
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / K},
             "gpu_launches": gpu_launches,
-            "roofline": {"bound": "hbm", "kernel": "liquid_bwd_small_kernel", "achieved": bwd_gbs, "peak": hbm_peak,
+            "roofline": {"bound": "hbm", "kernel": "liquid_bwd_tc_kernel", "achieved": bwd_gbs, "peak": hbm_peak,
                          "unit": "GB/s", "frac": bwd_gbs / hbm_peak, "traffic": traffic, "peak_kind": peak_kind,
                          "algorithmic_bytes_per_sample_step": ALGO_BYTES_BWD, "kernel_ms": bwd_ms,
                          "fwd_kernel_ms": fwd_ms, "fwd_achieved": fwd_gbs,

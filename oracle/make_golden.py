@@ -11,6 +11,7 @@ goldens are outputs of the reference itself, run here with torch 2.11.0 CPU / nu
   cell.npz     NCPLiquidCell on a hand-written mask                      velora/models/lnn/cell.py:147-169
   ncp.npz      NCPNetwork parameters, y, gradients incl. dx              velora/models/lnn/ncp.py:299-328
   buffer.npz   ReplayBuffer ring writes and seeded sample()              velora/buffer/base.py:73-143, replay.py:61-88
+  train.npz    three NeuroFlowCT._train_step calls (noise/indices given)  velora/models/nf/agent.py:182-255
 
 fp64 arbiters are produced by deep-copying the reference module to float64 and composing its own sub-modules
 (the reference forward() casts x to float32 at ncp.py:158, so the composition is spelled out here).
@@ -290,6 +291,80 @@ def gen_buffer(ref) -> dict:
     return out
 
 
+# ----------------------------------------------------------------------------------------------- train step (cfg 1/2)
+def gen_train(ref) -> dict:
+    """Three NeuroFlowCT._train_step calls (velora/models/nf/agent.py:182-255) on a synthetic buffer, InvertedPendulum
+    shapes (S=4, A=1, scale 3, bias 0; actor 20 / critic 128 neurons), batch 32, with the policy noise and the sampled
+    indices supplied from outside so that any device can replay the same step."""
+    import torch.nn as nn
+    from torch.distributions import Normal
+    import velora.models.sac.continuous as cont
+    from velora.buffer.experience import BatchExperience
+
+    out = {}
+    EPS, IDX = [], []
+
+    def get_sample(self, mean, std):
+        eps = EPS.pop(0).to(mean)
+        x_t = mean + eps * std                     # == Normal(mean, std).rsample() with this eps
+        return x_t, Normal(mean, std).log_prob(x_t)
+
+    orig = cont.SACActor.get_sample
+    cont.SACActor.get_sample = torch.jit.ignore(get_sample)
+    try:
+        S, A, B, steps = 4, 1, 32, 3
+        ref.set_seed(64)
+        agent = object.__new__(ref.NeuroFlowCT)
+        agent.device = None
+        agent.gamma, agent.tau = 0.99, 0.005
+        agent.actor = ref.ActorModule(S, 20, A, torch.tensor([3.0]), torch.tensor([0.0]))
+        agent.critic = ref.CriticModule(S, 128, A)
+        agent.entropy = ref.EntropyModule(A)
+        agent.loss = nn.MSELoss()
+        agent.buffer = ref.ReplayBuffer(512, S, A, agent.actor.hidden_size)
+        g = torch.Generator().manual_seed(2)
+        n = 300
+        feed = (torch.randn(n, S, generator=g), torch.rand(n, A, generator=g) * 6 - 3, torch.ones(n),
+                torch.randn(n, S, generator=g), (torch.rand(n, generator=g) < 0.02), 0.3 * torch.randn(n, 8, generator=g))
+        agent.buffer.add_multi(*feed)
+        for k, v in agent.buffer.state_dict().items():
+            out[f"buf_{k}"] = t2n(v)
+        for k, v in agent.actor.network.state_dict().items():
+            out[f"init_actor_{k}"] = t2n(v)
+        for k, v in agent.critic.network1.state_dict().items():
+            out[f"init_critic1_{k}"] = t2n(v)
+        for k, v in agent.critic.network2.state_dict().items():
+            out[f"init_critic2_{k}"] = t2n(v)
+
+        def sample(batch_size):
+            idx = IDX.pop(0)
+            b = agent.buffer
+            return BatchExperience(b.states[idx], b.actions[idx], b.rewards[idx], b.next_states[idx], b.dones[idx], b.hiddens[idx])
+
+        agent.buffer.sample = sample
+        eps_all = torch.randn(steps * 2, B, A, generator=g)
+        idx_all = torch.randint(0, n, (steps, B), generator=g)
+        out["eps"], out["idx"] = t2n(eps_all), t2n(idx_all)
+        losses = []
+        for s in range(steps):
+            EPS.extend([eps_all[2 * s], eps_all[2 * s + 1]])
+            IDX.append(idx_all[s])
+            r = agent._train_step(B)
+            losses.append([float(r["critic"]), float(r["actor"]), float(r["entropy"])])
+        out["losses"] = np.array(losses, dtype=np.float64)
+        for k, v in agent.actor.network.state_dict().items():
+            out[f"final_actor_{k}"] = t2n(v)
+        for k, v in agent.critic.network1.state_dict().items():
+            out[f"final_critic1_{k}"] = t2n(v)
+        for k, v in agent.critic.target1.state_dict().items():
+            out[f"final_target1_{k}"] = t2n(v)
+        out["final_log_alpha"] = t2n(agent.entropy.log_alpha)
+        out["dims"] = np.array([S, A, B, steps, n], dtype=np.int64)
+    finally:
+        cont.SACActor.get_sample = orig
+    return out
+
+
 def main() -> None:
     # The reference writes polarities with `mask[rows, cols] = pol` where (row, col) pairs repeat
     # (np.random.choice draws with replacement, wiring.py:245-251).  With several intra-op threads torch's
@@ -299,7 +374,8 @@ def main() -> None:
     torch.set_num_threads(1)
     ref = ref_import.import_reference()
     os.makedirs(OUT, exist_ok=True)
-    for name, fn in (("wiring", gen_wiring), ("liquid", gen_liquid), ("cell", gen_cell), ("ncp", gen_ncp), ("buffer", gen_buffer)):
+    for name, fn in (("wiring", gen_wiring), ("liquid", gen_liquid), ("cell", gen_cell), ("ncp", gen_ncp), ("buffer", gen_buffer),
+                     ("train", gen_train)):
         data = fn(ref)
         path = os.path.join(OUT, f"{name}.npz")
         np.savez_compressed(path, **data)

@@ -89,7 +89,7 @@ def _stub_third_party() -> None:
         sys.modules["sqlmodel"] = sm
         sa = types.ModuleType("sqlalchemy")
         sa.Engine = type("Engine", (), {})
-        sa.ScalarResult = type("ScalarResult", (), {})
+        sa.ScalarResult = type("ScalarResult", (), {"__class_getitem__": classmethod(lambda cls, item: cls)})
         sys.modules["sqlalchemy"] = sa
 
 
@@ -112,7 +112,19 @@ def import_reference():
     from velora.wiring import Wiring
     from velora.buffer.replay import ReplayBuffer
 
+    try:   # the agent layer (only needed for the train-step goldens); heavier stubs, optional
+        _shell("velora.models.nf", os.path.join(vroot, "models", "nf"))
+        from velora.models.nf.modules import ActorModule, CriticModule, EntropyModule
+        from velora.models.nf.agent import NeuroFlowCT
+    except Exception as e:   # pragma: no cover
+        ActorModule = CriticModule = EntropyModule = NeuroFlowCT = None
+        print(f"[ref_import] agent layer not importable: {e!r}")
+
     ns = types.SimpleNamespace(
+        ActorModule=ActorModule,
+        CriticModule=CriticModule,
+        EntropyModule=EntropyModule,
+        NeuroFlowCT=NeuroFlowCT,
         NCPLiquidCell=NCPLiquidCell,
         LiquidNCPNetwork=LiquidNCPNetwork,
         NCPNetwork=NCPNetwork,

@@ -23,6 +23,20 @@ PROFILE = None
 LAUNCHES = 0
 
 
+_WORKSPACES = {}
+
+
+def _workspace(dev: torch.device, nbytes: int) -> torch.Tensor:
+    """Scratch buffer for the backward kernels, reused per (device, stream): work on one stream is ordered, so the
+    next backward on that stream may overwrite it."""
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    ws = _WORKSPACES.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=dev)
+        _WORKSPACES[key] = ws
+    return ws
+
+
 def _count(n: int) -> None:
     global LAUNCHES
     LAUNCHES += n
@@ -132,8 +146,7 @@ class LiquidSeqFn(torch.autograd.Function):
             dh0 = torch.empty((B, Nc), dtype=torch.float32, device=dev) if need_h0 else None
             n_grad = L.vb_liquid_grad_floats(I, Ni, Nc, O)
             dpacked = torch.empty(n_grad, dtype=torch.float32, device=dev)
-            ws_bytes = L.vb_liquid_bwd_workspace_bytes(I, Ni, Nc, O, B, T)
-            ws = torch.empty(max(int(ws_bytes), 16), dtype=torch.uint8, device=dev)
+            ws = _workspace(dev, L.vb_liquid_bwd_workspace_bytes(I, Ni, Nc, O, B, T))
             with _timed("liquid_bwd", 2):
                 _lib.check(
                     L.vb_liquid_bwd(_lib.ptr(packed), _lib.ptr(x), _lib.ptr(h0p), _lib.ptr(h_traj), _lib.ptr(dy),
@@ -207,8 +220,7 @@ class NcpFn(torch.autograd.Function):
             st = _lib.stream_ptr(dev)
             dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
             dpacked = torch.empty(L.vb_ncp_grad_floats(I, Ni, Nc, O), dtype=torch.float32, device=dev)
-            ws_bytes = L.vb_ncp_bwd_workspace_bytes(I, Ni, Nc, O, B)
-            ws = torch.empty(max(int(ws_bytes), 16), dtype=torch.uint8, device=dev)
+            ws = _workspace(dev, L.vb_ncp_bwd_workspace_bytes(I, Ni, Nc, O, B))
             with _timed("ncp_bwd", 2):
                 _lib.check(
                     L.vb_ncp_bwd(_lib.ptr(packed), _lib.ptr(x), _lib.ptr(dy), _lib.ptr(dx), _lib.ptr(dpacked),

@@ -1,0 +1,97 @@
+"""Agent modules of NeuroFlowCT (mirror of velora/models/nf/modules.py: ActorModule :41, CriticModule :320,
+EntropyModule :646): network + optimizer bundles.  Networks are torch.jit.script-ed after construction exactly like
+the reference (modules.py:107, 388-392) - the fused forward survives because it sits behind @torch.jit.ignore."""
+from copy import deepcopy
+from typing import Tuple, Type
+
+import torch
+import torch.nn as nn
+from torch import optim
+
+from velora_b200.models.sac.continuous import SACActor, SACCriticNCP
+from velora_b200.utils.torch import soft_update
+
+
+class ActorModule:
+    def __init__(self, state_dim: int, n_neurons: int, action_dim: int, action_scale: torch.Tensor, action_bias: torch.Tensor,
+                 *, log_std_min: float = -5, log_std_max: float = 2, optim: Type[optim.Optimizer] = optim.Adam,
+                 lr: float = 3e-4, device: torch.device | None = None):
+        self.device = device
+        self.network = SACActor(state_dim, n_neurons, action_dim, action_scale, action_bias, log_std_min=log_std_min,
+                                log_std_max=log_std_max, device=device).to(device)
+        self.hidden_size = self.network.ncp.hidden_size
+        self.optim = optim(self.network.parameters(), lr=lr)
+        self.active_params = self.network.ncp.active_params
+        self.total_params = self.network.ncp.total_params
+        self.network = torch.jit.script(self.network)
+
+    def gradient_step(self, loss: torch.Tensor) -> None:
+        self.optim.zero_grad()
+        loss.backward()
+        self.optim.step()
+
+    def predict(self, obs: torch.Tensor, hidden: torch.Tensor | None = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        return self.network.predict(obs, hidden)
+
+    def forward(self, obs: torch.Tensor, hidden: torch.Tensor | None = None):
+        return self.network(obs, hidden)
+
+
+class CriticModule:
+    def __init__(self, state_dim: int, n_neurons: int, action_dim: int, *, optim: Type[optim.Optimizer] = optim.Adam,
+                 lr: float = 3e-4, tau: float = 0.005, device: torch.device | None = None):
+        self.tau = tau
+        self.device = device
+        self.network1 = SACCriticNCP(state_dim, n_neurons, action_dim, device=device).to(device)
+        self.network2 = SACCriticNCP(state_dim, n_neurons, action_dim, device=device).to(device)
+        self.target1 = deepcopy(self.network1)
+        self.target2 = deepcopy(self.network2)
+        self.optim1 = optim(self.network1.parameters(), lr=lr)
+        self.optim2 = optim(self.network2.parameters(), lr=lr)
+        self.active_params = self.network1.ncp.active_params + self.network2.ncp.active_params
+        self.total_params = self.network1.ncp.total_params + self.network2.ncp.total_params
+        self.network1 = torch.jit.script(self.network1)
+        self.network2 = torch.jit.script(self.network2)
+        self.target1 = torch.jit.script(self.target1)
+        self.target2 = torch.jit.script(self.target2)
+
+    def update_targets(self) -> None:
+        soft_update(self.network1, self.target1, tau=self.tau)
+        soft_update(self.network2, self.target2, tau=self.tau)
+
+    def gradient_step(self, c1_loss: torch.Tensor, c2_loss: torch.Tensor) -> None:
+        self.optim1.zero_grad()
+        c1_loss.backward()
+        self.optim1.step()
+        self.optim2.zero_grad()
+        c2_loss.backward()
+        self.optim2.step()
+
+    def predict(self, obs: torch.Tensor, actions: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        return self.network1(obs, actions), self.network2(obs, actions)
+
+    def target_predict(self, obs: torch.Tensor, actions: torch.Tensor) -> torch.Tensor:
+        return torch.min(self.target1(obs, actions), self.target2(obs, actions))
+
+
+class EntropyModule:
+    """Automatic entropy tuning: one scalar log_alpha (modules.py:646-717)."""
+
+    def __init__(self, action_dim: int, *, initial_alpha: float = 1.0, optim: Type[optim.Optimizer] = optim.Adam,
+                 lr: float = 3e-4, device: torch.device | None = None):
+        self.target = -action_dim
+        self.log_alpha = nn.Parameter(torch.tensor(initial_alpha, device=device).log())
+        self.optim = optim([self.log_alpha], lr=lr)
+
+    @property
+    def alpha(self) -> torch.Tensor:
+        return self.log_alpha.exp()
+
+    def compute_loss(self, log_probs: torch.Tensor) -> torch.Tensor:
+        entropy = (log_probs + self.target).detach()
+        return -(self.log_alpha * entropy).mean()
+
+    def gradient_step(self, loss: torch.Tensor) -> None:
+        self.optim.zero_grad()
+        loss.backward()
+        self.optim.step()
