@@ -350,6 +350,7 @@ def gen_train(ref) -> dict:
             EPS.extend([eps_all[2 * s], eps_all[2 * s + 1]])
             IDX.append(idx_all[s])
             r = agent._train_step(B)
+            assert not EPS and not IDX, "the recorded noise / indices were not consumed: the patched hooks are not in use"
             losses.append([float(r["critic"]), float(r["actor"]), float(r["entropy"])])
         out["losses"] = np.array(losses, dtype=np.float64)
         for k, v in agent.actor.network.state_dict().items():
