@@ -1,0 +1,169 @@
+"""Secondary measurements for the other BASELINE.json configs (one GPU).  `bench.py` is the headline (config 3); this
+script prints one JSON line per measurement so that profiles/ can quote configs 1/2/4/5 next to it.
+
+    python bench_configs.py [--quick] [--no-cpu]
+
+  cfg1/2  NeuroFlowCT train step, actor 20 / critic 128 neurons, batch 64 (InvertedPendulum shapes, synthetic buffer)
+  cfg2b   batch-1 actor forward (the per-environment-step `predict`)
+  cfg4    LiquidNCPNetwork(8, 512, 1) forward+backward (currently the generic fp32 tile kernels; tcgen05 path: next)
+  cfg5    1M-transition replay buffer: fused gather of a 1M (and 131072) batch, and a full train step at those batches
+CPU baselines use the oracle's torch-CPU ports (the Python reference cannot travel to the GPU box).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        return json.load(open(p))
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def gpu_time_ms(fn, warmup=5, iters=20):
+    import torch
+
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def cpu_time_ms(fn, warmup=1, iters=3):
+    for _ in range(warmup):
+        fn()
+    ts = []
+    for _ in range(iters):
+        t0 = time.perf_counter()
+        fn()
+        ts.append(time.perf_counter() - t0)
+    return 1e3 * min(ts)
+
+
+def emit(**kw):
+    print(json.dumps(kw), flush=True)
+
+
+def make_agent(dev, buffer_rows, seed=64):
+    import torch
+
+    from velora_b200.models.nf import NeuroFlowCTCore
+
+    agent = NeuroFlowCTCore(4, 1, 20, 128, torch.tensor([3.0]), torch.tensor([0.0]), buffer_size=buffer_rows, seed=seed, device=dev)
+    g = torch.Generator(device=dev).manual_seed(0)
+    b = agent.buffer
+    b.states.copy_(torch.randn(b.states.shape, device=dev, generator=g))
+    b.next_states.copy_(torch.randn(b.states.shape, device=dev, generator=g))
+    b.actions.copy_(torch.rand(b.actions.shape, device=dev, generator=g) * 6 - 3)
+    b.rewards.fill_(1.0)
+    b.dones.copy_((torch.rand(b.dones.shape, device=dev, generator=g) < 0.02).float())
+    b.hiddens.copy_(0.3 * torch.randn(b.hiddens.shape, device=dev, generator=g))
+    b.size = buffer_rows
+    return agent
+
+
+def cpu_train_oracle(agent):
+    from oracle.train_oracle import TrainOracle
+
+    sd = lambda net: {k: v.detach().cpu().numpy() for k, v in net.state_dict().items()}   # noqa: E731
+    return TrainOracle(sd(agent.actor.network), sd(agent.critic.network1), sd(agent.critic.network2))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    import torch
+
+    import velora_b200 as vb
+    from velora_b200.models.lnn import LiquidNCPNetwork
+
+    dev = torch.device("cuda:0")
+    pk = peaks()
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+
+    # ------------------------------------------------------------------ cfg 1/2: train step at batch 64
+    agent = make_agent(dev, 100_000)
+    ms = gpu_time_ms(lambda: agent._train_step(64), warmup=10, iters=50)
+    cpu_ms = None
+    if not args.no_cpu:
+        o = cpu_train_oracle(agent)
+        idx = torch.randint(0, 100_000, (64,))
+        batch = {k: getattr(agent.buffer, k)[idx.to(dev)].cpu() for k in ("states", "actions", "rewards", "next_states", "dones", "hiddens")}
+        cpu_ms = cpu_time_ms(lambda: o.train_step(batch), warmup=3, iters=20)
+    emit(config="cfg1/2 NeuroFlowCT._train_step, actor 20 / critic 128, batch 64", metric="us_per_train_step", value=1e3 * ms,
+         cpu_port_us=None if cpu_ms is None else 1e3 * cpu_ms, cpu_cores=cores,
+         note="sample (fused gather) + 2 liquid fwd + 1 liquid bwd + 6 NCP fwd + 4 NCP bwd through the C ABI; SAC head math, Adam, "
+              "soft update are framework ops (next rows)")
+
+    # ------------------------------------------------------------------ cfg 2b: batch-1 actor forward
+    x1 = torch.randn(1, 4, device=dev)
+    h1 = torch.zeros(1, 8, device=dev)
+    with torch.no_grad():
+        ms1 = gpu_time_ms(lambda: agent.actor.network.ncp(x1, h1), warmup=20, iters=200)
+    emit(config="cfg2b LiquidNCPNetwork(4,20,2) forward, batch 1 (predict)", metric="us_per_call", value=1e3 * ms1)
+
+    # ------------------------------------------------------------------ cfg 5: gather + train step at large batch
+    big = make_agent(dev, 1_000_000)
+    for B in ([131072] if args.quick else [131072, 1_000_000]):
+        torch.manual_seed(1)
+        idx = torch.randint(0, big.buffer.size, (B,), device=dev)
+        gms = gpu_time_ms(lambda: big.buffer.gather(idx), warmup=5, iters=20)
+        gbs = 160.0 * B / (gms * 1e-3) / 1e9
+        ref_ms = gpu_time_ms(lambda: [getattr(big.buffer, k)[idx] for k in ("states", "actions", "rewards", "next_states", "dones", "hiddens")],
+                             warmup=3, iters=10)
+        emit(config=f"cfg5 ReplayBuffer(1M,4,1,8) gather, batch {B}", metric="transitions_per_s", value=B / (gms * 1e-3), ms=gms,
+             roofline={"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
+                       "algorithmic_bytes_per_transition": 160},
+             torch_six_index_kernels_ms=ref_ms)
+        tms = gpu_time_ms(lambda: big._train_step(B), warmup=3, iters=10)
+        emit(config=f"cfg5 sample + NeuroFlowCT update, batch {B}, 1 GPU", metric="transitions_per_s", value=B / (tms * 1e-3), ms=tms)
+    if not args.no_cpu:
+        B = 131072
+        o = cpu_train_oracle(big)
+        idxc = torch.randint(0, 1_000_000, (B,))
+        cb = {k: getattr(big.buffer, k).cpu()[idxc] for k in ("states", "actions", "rewards", "next_states", "dones", "hiddens")}
+        cms = cpu_time_ms(lambda: o.train_step(cb), warmup=1, iters=2)
+        emit(config=f"cfg5 CPU port of the NeuroFlowCT update, batch {B}", metric="transitions_per_s", value=B / (cms * 1e-3), ms=cms, cpu_cores=cores)
+    del big
+
+    # ------------------------------------------------------------------ cfg 4: 512-neuron liquid network
+    vb.set_seed(64)
+    net = LiquidNCPNetwork(8, 512, 1, device=dev)
+    B, T = (1024, 4) if args.quick else (4096, 8)
+    x = torch.randn(B, T, 8, device=dev)
+    ry = torch.randn(B, T, 1, device=dev)
+
+    def step4():
+        for p in net.parameters():
+            p.grad = None
+        y, _, hl = net.forward_seq(x, None, return_last=True)
+        torch.autograd.backward([y, hl], [ry, torch.ones_like(hl)])
+
+    ms4 = gpu_time_ms(step4, warmup=2, iters=5)
+    flops = 3.149e6 * B * T
+    emit(config=f"cfg4 LiquidNCPNetwork(8,512,1) fwd+bwd, batch {B} x seq {T}, fp32 generic tile kernels", metric="sample_steps_per_s",
+         value=B * T / (ms4 * 1e-3), ms=ms4,
+         roofline={"bound": "tensor", "achieved": flops / (ms4 * 1e-3) / 1e12, "peak": pk.get("bf16_tflops_sustained", 1400.0), "unit": "TFLOP/s",
+                   "frac": flops / (ms4 * 1e-3) / 1e12 / pk.get("bf16_tflops_sustained", 1400.0)},
+         note="not yet on tensor cores: the bf16 tcgen05 path for the 512-neuron class is the next kernel")
+
+
+if __name__ == "__main__":
+    main()

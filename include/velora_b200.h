@@ -60,6 +60,8 @@ extern "C" {
  * velora/wiring.py:132-149, velora/models/lnn/cell.py:109-111) */
 #define VB_MASK_I32 0
 #define VB_MASK_F32 1
+#define VB_MASK_TRANSPOSED 2   /* OR-ed in: the [out, in] mask is stored column-major (a transposed view of a row-major
+                                * [in, out] tensor, which is how the reference keeps `abs(mask.T)`) */
 
 /* flags */
 #define VB_FLAG_FORCE_GENERIC 1   /* use the generic tile kernels even where a specialised kernel exists (parity tests) */

@@ -162,3 +162,21 @@ def test_buffer_oracle_vs_reference(golden):
             assert np.array_equal(out[k], d[f"sample{B}_{k}"]), k
     with pytest.raises(ValueError):
         buf.gather(np.zeros(cap + 1, np.int64))
+
+
+def test_train_oracle_vs_reference(golden):
+    """The CPU restatement of the NeuroFlowCT train step reproduces three reference `_train_step` calls."""
+    from oracle.train_oracle import TrainOracle
+
+    d = golden("train")
+    pre = lambda p: {k[len(p):]: d[k] for k in d.files if k.startswith(p)}   # noqa: E731
+    torch.set_num_threads(1)
+    o = TrainOracle(pre("init_actor_"), pre("init_critic1_"), pre("init_critic2_"))
+    eps, idx = torch.tensor(d["eps"]), d["idx"]
+    for s in range(int(d["dims"][3])):
+        batch = {k: torch.tensor(d[f"buf_{k}"][idx[s]]) for k in ("states", "actions", "rewards", "next_states", "dones", "hiddens")}
+        losses = o.train_step(batch, [eps[2 * s], eps[2 * s + 1]])
+        assert np.allclose(losses, d["losses"][s], rtol=1e-5, atol=1e-6), (s, losses, d["losses"][s])
+    for k, v in pre("final_actor_ncp.").items():
+        assert np.allclose(o.actor[k].detach().numpy(), v, atol=1e-6), k
+    assert abs(float(o.log_alpha) - float(d["final_log_alpha"])) < 1e-6

@@ -92,12 +92,28 @@ def ptr_array(ts: Sequence[Optional[torch.Tensor]]):
     return arr
 
 
+VB_MASK_TRANSPOSED = 2
+
+
 def mask_type(t: torch.Tensor) -> int:
+    """Type code of a 2-D mask that is either row-major or a transposed view of a row-major tensor (see mask_arg)."""
     if t.dtype == torch.int32:
-        return VB_MASK_I32
-    if t.dtype == torch.float32:
-        return VB_MASK_F32
-    raise TypeError(f"mask dtype {t.dtype} not supported (int32 or float32)")
+        code = VB_MASK_I32
+    elif t.dtype == torch.float32:
+        code = VB_MASK_F32
+    else:
+        raise TypeError(f"mask dtype {t.dtype} not supported (int32 or float32)")
+    return code if t.is_contiguous() else code | VB_MASK_TRANSPOSED
+
+
+def mask_arg(m: torch.Tensor, dev: torch.device) -> torch.Tensor:
+    """The reference stores `abs(mask.T)`: a transposed VIEW.  Row-major and transposed-row-major masks are passed
+    as they are (the kernels index them through the type code); anything else is copied once."""
+    if m.device != dev:
+        m = m.to(dev)
+    if m.is_contiguous() or (m.dim() == 2 and m.t().is_contiguous()):
+        return m
+    return m.contiguous()
 
 
 def stream_ptr(device: torch.device) -> int:

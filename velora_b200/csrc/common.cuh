@@ -1,6 +1,7 @@
 // Shared device/host helpers for libvelora_b200.so (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <mutex>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -43,6 +44,38 @@ void set_error(const char* fmt, ...);
 
 int device_sms();
 int device_max_smem_optin();
+
+// Launch-configuration cache: raising the dynamic shared-memory limit and the occupancy query are driver calls of
+// several microseconds each; at batch 64 (BASELINE configs 1/2) they cost more than the kernels.  One entry per
+// (device, kernel, shared-memory size).
+struct LaunchCfg { int blocks_per_sm; int regs; int static_smem; };
+template <class K>
+inline int cached_launch_cfg(K kernel, int threads, int smem, LaunchCfg* out) {
+    struct Entry { int dev; const void* k; int smem; LaunchCfg cfg; };
+    static Entry entries[64];
+    static int n_entries = 0;
+    static std::mutex mu;
+    int dev = 0;
+    VB_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    const void* kp = reinterpret_cast<const void*>(kernel);
+    int max_set = -1;   // the attribute is per-kernel state: only ever raise it
+    for (int i = 0; i < n_entries; ++i) {
+        if (entries[i].dev == dev && entries[i].k == kp) {
+            if (entries[i].smem == smem) { *out = entries[i].cfg; return 0; }
+            if (entries[i].smem > max_set) max_set = entries[i].smem;
+        }
+    }
+    if (smem > max_set) VB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int occ = 1;
+    VB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem));
+    cudaFuncAttributes fa;
+    VB_CUDA(cudaFuncGetAttributes(&fa, kernel));
+    LaunchCfg cfg{occ < 1 ? 1 : occ, fa.numRegs, (int)fa.sharedSizeBytes};
+    if (n_entries < 64) entries[n_entries++] = Entry{dev, kp, smem, cfg};
+    *out = cfg;
+    return 0;
+}
 
 __host__ __device__ constexpr int ceil4(int v) { return (v + 3) & ~3; }
 

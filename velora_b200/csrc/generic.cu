@@ -350,10 +350,10 @@ static int ncp_bwd_rows(const NcpLayout& L) { return L.I + 3 * L.NIp + 3 * L.NCp
 
 template <class K>
 static int grid_for(K kernel, int smem, int64_t n_tiles, int cap_per_sm, int* grid) {
-    VB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    int occ = 1;
-    VB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kTileThreads, smem));
-    if (occ < 1) occ = 1;
+    LaunchCfg cfg;
+    int rc = cached_launch_cfg(kernel, kTileThreads, smem, &cfg);
+    if (rc) return rc;
+    int occ = cfg.blocks_per_sm;
     if (cap_per_sm > 0 && occ > cap_per_sm) occ = cap_per_sm;
     int64_t cap = (int64_t)device_sms() * occ;
     int64_t g = n_tiles < cap ? n_tiles : cap;

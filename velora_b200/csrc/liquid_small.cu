@@ -547,18 +547,15 @@ static int vec_flags_for(const void* x, const void* y, const void* h_a, const vo
 
 template <class C>
 static int launch_fwd(const float* packed, const float* x, const float* h0, float* y, float* h_traj, int64_t B, int T, cudaStream_t stream) {
-    static bool attr_done[64] = {false};
+    LaunchCfg cfg;
+    int rc = cached_launch_cfg(liquid_fwd_small_kernel<C>, kFwdThreads, FwdSmem<C>::BYTES, &cfg);
+    if (rc) return rc;
+    const int occ = cfg.blocks_per_sm;
     std::lock_guard<std::mutex> lock(g_mu);
     int dev;
     bool capturing;
-    int rc = upload_constants(packed, C::F_TOTAL, stream, &dev, &capturing);
+    rc = upload_constants(packed, C::F_TOTAL, stream, &dev, &capturing);
     if (rc) return rc;
-    if (!attr_done[dev & 63]) {
-        VB_CUDA(cudaFuncSetAttribute(liquid_fwd_small_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem<C>::BYTES));
-        attr_done[dev & 63] = true;
-    }
-    int occ = 1;
-    VB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, liquid_fwd_small_kernel<C>, kFwdThreads, FwdSmem<C>::BYTES));
     int64_t n_groups = (B + 31) / 32;
     int64_t want = (n_groups + kFwdThreads / 32 - 1) / (kFwdThreads / 32);
     int64_t cap = (int64_t)device_sms() * (occ > 0 ? occ : 1);
@@ -573,8 +570,10 @@ static int launch_fwd(const float* packed, const float* x, const float* h0, floa
 
 template <class C>
 static int bwd_grid(int64_t B, int* grid_out) {
-    int occ = 1;
-    VB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, liquid_bwd_small_kernel<C>, kBwdThreads, BwdSmem<C>::BYTES));
+    LaunchCfg cfg;
+    int rc0 = cached_launch_cfg(liquid_bwd_small_kernel<C>, kBwdThreads, BwdSmem<C>::BYTES, &cfg);
+    if (rc0) return rc0;
+    const int occ = cfg.blocks_per_sm;
     int64_t n_groups = (B + 31) / 32;
     int64_t want = (n_groups + kBwdThreads / 32 - 1) / (kBwdThreads / 32);
     int64_t cap = (int64_t)device_sms() * (occ > 0 ? occ : 1);
@@ -587,17 +586,11 @@ template <class C>
 static int launch_bwd(const float* packed, const float* x, const float* h0, const float* h_traj, const float* dy,
                       const float* dh_traj, const float* dh_last, float* dx, float* dh0, float* dpacked,
                       int64_t B, int T, void* ws, int64_t ws_bytes, cudaStream_t stream) {
-    static bool attr_done[64] = {false};
-    std::lock_guard<std::mutex> lock(g_mu);
-    int dev = 0;
-    VB_CUDA(cudaGetDevice(&dev));
-    if (!attr_done[dev & 63]) {
-        VB_CUDA(cudaFuncSetAttribute(liquid_bwd_small_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem<C>::BYTES));
-        attr_done[dev & 63] = true;
-    }
     int grid = 1;
     int rc = bwd_grid<C>(B, &grid);
     if (rc) return rc;
+    std::lock_guard<std::mutex> lock(g_mu);
+    int dev = 0;
     VB_CHECK_ARG(ws && ws_bytes >= (int64_t)grid * C::F_TOTAL * (int64_t)sizeof(float), VB_ERR_WORKSPACE,
                  "vb_liquid_bwd: workspace too small (%lld bytes, need %lld)", (long long)ws_bytes,
                  (long long)((int64_t)grid * C::F_TOTAL * sizeof(float)));

@@ -769,23 +769,22 @@ static int vec_flags_for(const void* x, const void* y, const void* h_a, const vo
 // CTA), registers, TMEM columns (512 per SM) and the 32-CTA / 2048-thread caps.
 template <class K>
 static int grid_cap(K kernel, int smem, int tmem_cols, int* per_sm) {
-    static std::mutex mu;
-    std::lock_guard<std::mutex> lock(mu);
-    VB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    cudaFuncAttributes fa;
-    VB_CUDA(cudaFuncGetAttributes(&fa, kernel));
-    int dev = 0, smem_sm = 0, regs_sm = 0;
+    LaunchCfg cfg;
+    int rc = cached_launch_cfg(kernel, TM, smem, &cfg);
+    if (rc) return rc;
+    static int smem_sm[64], regs_sm[64];
+    int dev = 0;
     VB_CUDA(cudaGetDevice(&dev));
-    VB_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
-    VB_CUDA(cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev));
-    const int regs_cta = ((fa.numRegs + 7) & ~7) * TM;
-    int n = smem_sm / (smem + (int)fa.sharedSizeBytes + 1024);
-    if (regs_cta > 0 && regs_sm / regs_cta < n) n = regs_sm / regs_cta;
+    if (!regs_sm[dev & 63]) {
+        VB_CUDA(cudaDeviceGetAttribute(&smem_sm[dev & 63], cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
+        VB_CUDA(cudaDeviceGetAttribute(&regs_sm[dev & 63], cudaDevAttrMaxRegistersPerMultiprocessor, dev));
+    }
+    const int regs_cta = ((cfg.regs + 7) & ~7) * TM;
+    int n = smem_sm[dev & 63] / (smem + cfg.static_smem + 1024);
+    if (regs_cta > 0 && regs_sm[dev & 63] / regs_cta < n) n = regs_sm[dev & 63] / regs_cta;
     if (512 / tmem_cols < n) n = 512 / tmem_cols;
     if (n > 2048 / TM) n = 2048 / TM;
     if (n > 32) n = 32;
-    if (getenv("VB_DEBUG"))
-        fprintf(stderr, "[vb] tc kernel: smem=%d regs=%d tmem=%d -> %d CTAs/SM\n", smem, fa.numRegs, tmem_cols, n);
     *per_sm = n < 1 ? 1 : n;
     return 0;
 }

@@ -12,17 +12,20 @@ struct LiquidSrc {
     int t_in, t_h, t_out;
 };
 
-__device__ __forceinline__ float mask_at(const void* m, int type, int64_t idx) {
-    return type == VB_MASK_I32 ? (float)reinterpret_cast<const int*>(m)[idx] : reinterpret_cast<const float*>(m)[idx];
+// element (r, c) of an [R, C] mask; types >= VB_MASK_TRANSPOSED are stored column-major (the reference keeps
+// `abs(mask.T)`, a transposed view of a row-major [C, R] tensor: velora/models/lnn/ncp.py:82, cell.py:111)
+__device__ __forceinline__ float mask_rc(const void* m, int type, int r, int c, int R, int C) {
+    const int64_t idx = (type & VB_MASK_TRANSPOSED) ? (int64_t)c * R + r : (int64_t)r * C + c;
+    return (type & 1) == VB_MASK_I32 ? (float)reinterpret_cast<const int*>(m)[idx] : reinterpret_cast<const float*>(m)[idx];
 }
 
 // effective (masked) weight of head slot hs in {g,h,f,proj} at [j][i]; the f slot is the sum of both f heads
-__device__ __forceinline__ float head_w(const LiquidSrc& s, int hs, int j, int i, int K) {
+__device__ __forceinline__ float head_w(const LiquidSrc& s, int hs, int j, int i, int K, int Nc) {
     int64_t e = (int64_t)j * K + i;
-    if (hs == 0) return s.w_h[0][e] * mask_at(s.m_h[0], s.t_h, e);
-    if (hs == 1) return s.w_h[1][e] * mask_at(s.m_h[1], s.t_h, e);
-    if (hs == 2) return s.w_h[2][e] * mask_at(s.m_h[2], s.t_h, e) + s.w_h[3][e] * mask_at(s.m_h[3], s.t_h, e);
-    return s.w_h[4][e] * mask_at(s.m_h[4], s.t_h, e);
+    if (hs == 0) return s.w_h[0][e] * mask_rc(s.m_h[0], s.t_h, j, i, Nc, K);
+    if (hs == 1) return s.w_h[1][e] * mask_rc(s.m_h[1], s.t_h, j, i, Nc, K);
+    if (hs == 2) return s.w_h[2][e] * mask_rc(s.m_h[2], s.t_h, j, i, Nc, K) + s.w_h[3][e] * mask_rc(s.m_h[3], s.t_h, j, i, Nc, K);
+    return s.w_h[4][e] * mask_rc(s.m_h[4], s.t_h, j, i, Nc, K);
 }
 __device__ __forceinline__ float head_b(const LiquidSrc& s, int hs, int j) {
     if (hs == 0) return s.b_h[0][j];
@@ -36,7 +39,7 @@ __global__ void liquid_pack_kernel(LiquidSrc s, LiquidLayout L, float* __restric
         float v = 0.f;
         if (idx < L.b_in) {                       // win_t [I][NIp]
             int i = idx / L.NIp, j = idx % L.NIp;
-            if (j < L.Ni) v = s.w_in[j * L.I + i] * mask_at(s.m_in, s.t_in, j * L.I + i);
+            if (j < L.Ni) v = s.w_in[j * L.I + i] * mask_rc(s.m_in, s.t_in, j, i, L.Ni, L.I);
         } else if (idx < L.wh_t) {                // b_in
             int j = idx - L.b_in;
             if (j < L.Ni) v = s.b_in[j];
@@ -44,7 +47,7 @@ __global__ void liquid_pack_kernel(LiquidSrc s, LiquidLayout L, float* __restric
             int e = idx - L.wh_t;
             int i = e / L.H4, r = e % L.H4;
             int hs = r / L.NCp, j = r % L.NCp;
-            if (j < L.Nc) v = head_w(s, hs, j, i, L.K);
+            if (j < L.Nc) v = head_w(s, hs, j, i, L.K, L.Nc);
         } else if (idx < L.wout) {                // b_h [4][NCp]
             int r = idx - L.b_h;
             int hs = r / L.NCp, j = r % L.NCp;
@@ -52,23 +55,23 @@ __global__ void liquid_pack_kernel(LiquidSrc s, LiquidLayout L, float* __restric
         } else if (idx < L.b_out) {               // wout [O][NCp]
             int e = idx - L.wout;
             int o = e / L.NCp, j = e % L.NCp;
-            if (j < L.Nc) v = s.w_out[o * L.Nc + j] * mask_at(s.m_out, s.t_out, o * L.Nc + j);
+            if (j < L.Nc) v = s.w_out[o * L.Nc + j] * mask_rc(s.m_out, s.t_out, o, j, L.O, L.Nc);
         } else if (idx < L.f_total) {             // b_out
             int o = idx - L.b_out;
             if (o < L.O) v = s.b_out[o];
         } else if (idx < L.wh) {                  // win [Ni][Ip]
             int e = idx - L.win;
             int j = e / L.Ip, i = e % L.Ip;
-            if (i < L.I) v = s.w_in[j * L.I + i] * mask_at(s.m_in, s.t_in, j * L.I + i);
+            if (i < L.I) v = s.w_in[j * L.I + i] * mask_rc(s.m_in, s.t_in, j, i, L.Ni, L.I);
         } else if (idx < L.wout_t) {              // wh [4*NCp][Kp]
             int e = idx - L.wh;
             int r = e / L.Kp, i = e % L.Kp;
             int hs = r / L.NCp, j = r % L.NCp;
-            if (j < L.Nc && i < L.K) v = head_w(s, hs, j, i, L.K);
+            if (j < L.Nc && i < L.K) v = head_w(s, hs, j, i, L.K, L.Nc);
         } else {                                  // wout_t [Nc][Op]
             int e = idx - L.wout_t;
             int j = e / L.Op, o = e % L.Op;
-            if (o < L.O) v = s.w_out[o * L.Nc + j] * mask_at(s.m_out, s.t_out, o * L.Nc + j);
+            if (o < L.O) v = s.w_out[o * L.Nc + j] * mask_rc(s.m_out, s.t_out, o, j, L.O, L.Nc);
         }
         packed[idx] = v;
     }
@@ -93,7 +96,7 @@ __global__ void liquid_unpack_kernel(const float* __restrict__ dp, LiquidGradDst
         int e = idx;
         if (e < n_in) {
             int j = e / L.I, i = e % L.I;
-            put(d.g_w_in, e, dp[L.win_t + i * L.NIp + j] * mask_at(d.m_in, d.t_in, e), acc);
+            put(d.g_w_in, e, dp[L.win_t + i * L.NIp + j] * mask_rc(d.m_in, d.t_in, j, i, L.Ni, L.I), acc);
             continue;
         }
         e -= n_in;
@@ -105,7 +108,7 @@ __global__ void liquid_unpack_kernel(const float* __restrict__ dp, LiquidGradDst
             int hs = hd < 2 ? hd : (hd < 4 ? 2 : 3);
             if (r < n_h) {
                 int j = r / L.K, i = r % L.K;
-                put(d.g_w_h[hd], r, dp[L.wh_t + i * L.H4 + hs * L.NCp + j] * mask_at(d.m_h[hd], d.t_h, r), acc);
+                put(d.g_w_h[hd], r, dp[L.wh_t + i * L.H4 + hs * L.NCp + j] * mask_rc(d.m_h[hd], d.t_h, j, i, L.Nc, L.K), acc);
             } else {
                 int j = r - n_h;
                 put(d.g_b_h[hd], j, dp[L.b_h + hs * L.NCp + j], acc);
@@ -115,7 +118,7 @@ __global__ void liquid_unpack_kernel(const float* __restrict__ dp, LiquidGradDst
         e -= 5 * (n_h + L.Nc);
         if (e < n_out) {
             int o = e / L.Nc, j = e % L.Nc;
-            put(d.g_w_out, e, dp[L.wout + o * L.NCp + j] * mask_at(d.m_out, d.t_out, e), acc);
+            put(d.g_w_out, e, dp[L.wout + o * L.NCp + j] * mask_rc(d.m_out, d.t_out, o, j, L.O, L.Nc), acc);
             continue;
         }
         e -= n_out;
@@ -128,42 +131,43 @@ struct NcpSrc {
     const float* w[3]; const float* b[3]; const void* m[3];
     int t;
 };
+// NCP layers share one mask type code; the three masks have the same storage kind (all built by `abs(mask.T)`)
 
 __global__ void ncp_pack_kernel(NcpSrc s, NcpLayout L, float* __restrict__ packed) {
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < L.total; idx += gridDim.x * blockDim.x) {
         float v = 0.f;
         if (idx < L.b1) {                          // w1_t [I][NIp]
             int i = idx / L.NIp, j = idx % L.NIp;
-            if (j < L.Ni) v = s.w[0][j * L.I + i] * mask_at(s.m[0], s.t, j * L.I + i);
+            if (j < L.Ni) v = s.w[0][j * L.I + i] * mask_rc(s.m[0], s.t, j, i, L.Ni, L.I);
         } else if (idx < L.w2_t) {
             int j = idx - L.b1;
             if (j < L.Ni) v = s.b[0][j];
         } else if (idx < L.b2) {                   // w2_t [Ni][NCp]
             int e = idx - L.w2_t;
             int i = e / L.NCp, j = e % L.NCp;
-            if (j < L.Nc) v = s.w[1][j * L.Ni + i] * mask_at(s.m[1], s.t, j * L.Ni + i);
+            if (j < L.Nc) v = s.w[1][j * L.Ni + i] * mask_rc(s.m[1], s.t, j, i, L.Nc, L.Ni);
         } else if (idx < L.w3) {
             int j = idx - L.b2;
             if (j < L.Nc) v = s.b[1][j];
         } else if (idx < L.b3) {                   // w3 [O][NCp]
             int e = idx - L.w3;
             int o = e / L.NCp, j = e % L.NCp;
-            if (j < L.Nc) v = s.w[2][o * L.Nc + j] * mask_at(s.m[2], s.t, o * L.Nc + j);
+            if (j < L.Nc) v = s.w[2][o * L.Nc + j] * mask_rc(s.m[2], s.t, o, j, L.O, L.Nc);
         } else if (idx < L.f_total) {
             int o = idx - L.b3;
             if (o < L.O) v = s.b[2][o];
         } else if (idx < L.w2) {                   // w1 [Ni][Ip]
             int e = idx - L.w1;
             int j = e / L.Ip, i = e % L.Ip;
-            if (i < L.I) v = s.w[0][j * L.I + i] * mask_at(s.m[0], s.t, j * L.I + i);
+            if (i < L.I) v = s.w[0][j * L.I + i] * mask_rc(s.m[0], s.t, j, i, L.Ni, L.I);
         } else if (idx < L.w3_t) {                 // w2 [Nc][NIp]
             int e = idx - L.w2;
             int j = e / L.NIp, i = e % L.NIp;
-            if (i < L.Ni) v = s.w[1][j * L.Ni + i] * mask_at(s.m[1], s.t, j * L.Ni + i);
+            if (i < L.Ni) v = s.w[1][j * L.Ni + i] * mask_rc(s.m[1], s.t, j, i, L.Nc, L.Ni);
         } else {                                   // w3_t [Nc][Op]
             int e = idx - L.w3_t;
             int j = e / L.Op, o = e % L.Op;
-            if (o < L.O) v = s.w[2][o * L.Nc + j] * mask_at(s.m[2], s.t, o * L.Nc + j);
+            if (o < L.O) v = s.w[2][o * L.Nc + j] * mask_rc(s.m[2], s.t, o, j, L.O, L.Nc);
         }
         packed[idx] = v;
     }
@@ -179,15 +183,15 @@ __global__ void ncp_unpack_kernel(const float* __restrict__ dp, NcpGradDst d, Nc
     const int total = n1 + L.Ni + n2 + L.Nc + n3 + L.O;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
         int e = idx;
-        if (e < n1) { int j = e / L.I, i = e % L.I; put(d.g_w[0], e, dp[L.w1_t + i * L.NIp + j] * mask_at(d.m[0], d.t, e), acc); continue; }
+        if (e < n1) { int j = e / L.I, i = e % L.I; put(d.g_w[0], e, dp[L.w1_t + i * L.NIp + j] * mask_rc(d.m[0], d.t, j, i, L.Ni, L.I), acc); continue; }
         e -= n1;
         if (e < L.Ni) { put(d.g_b[0], e, dp[L.b1 + e], acc); continue; }
         e -= L.Ni;
-        if (e < n2) { int j = e / L.Ni, i = e % L.Ni; put(d.g_w[1], e, dp[L.w2_t + i * L.NCp + j] * mask_at(d.m[1], d.t, e), acc); continue; }
+        if (e < n2) { int j = e / L.Ni, i = e % L.Ni; put(d.g_w[1], e, dp[L.w2_t + i * L.NCp + j] * mask_rc(d.m[1], d.t, j, i, L.Nc, L.Ni), acc); continue; }
         e -= n2;
         if (e < L.Nc) { put(d.g_b[1], e, dp[L.b2 + e], acc); continue; }
         e -= L.Nc;
-        if (e < n3) { int o = e / L.Nc, j = e % L.Nc; put(d.g_w[2], e, dp[L.w3 + o * L.NCp + j] * mask_at(d.m[2], d.t, e), acc); continue; }
+        if (e < n3) { int o = e / L.Nc, j = e % L.Nc; put(d.g_w[2], e, dp[L.w3 + o * L.NCp + j] * mask_rc(d.m[2], d.t, o, j, L.O, L.Nc), acc); continue; }
         e -= n3;
         put(d.g_b[2], e, dp[L.b3 + e], acc);
     }

@@ -94,8 +94,10 @@ class LiquidSeqFn(torch.autograd.Function):
         w_h = [params[2 + 2 * k] for k in range(5)]
         b_h = [params[3 + 2 * k] for k in range(5)]
         w_out, b_out = params[12], params[13]
-        # wiring masks are stored as transposed views (abs(mask.T) keeps the strides): the kernels want row-major
-        masks = tuple(_rowmajor(m, dev) for m in masks)
+        # wiring masks are stored as transposed views (abs(mask.T) keeps the strides): passed as they are, with a type code
+        masks = tuple(_lib.mask_arg(m, dev) for m in masks)
+        if len({_lib.mask_type(m) for m in masks[1:6]}) != 1:
+            masks = (masks[0], *[m.contiguous() for m in masks[1:6]], masks[6])
         m_in, m_h, m_out = masks[0], list(masks[1:6]), masks[6]
         with torch.cuda.device(dev):
             st = _lib.stream_ptr(dev)
@@ -190,7 +192,9 @@ class NcpFn(torch.autograd.Function):
         params = [_f32c(p.detach()) for p in params]
         w = [params[0], params[2], params[4]]
         b = [params[1], params[3], params[5]]
-        masks = tuple(_rowmajor(m, dev) for m in masks)
+        masks = tuple(_lib.mask_arg(m, dev) for m in masks)
+        if len({_lib.mask_type(m) for m in masks}) != 1:
+            masks = tuple(m.contiguous() for m in masks)
         with torch.cuda.device(dev):
             st = _lib.stream_ptr(dev)
             packed = torch.empty(L.vb_ncp_packed_floats(I, Ni, Nc, O), dtype=torch.float32, device=dev)
