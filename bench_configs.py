@@ -58,12 +58,13 @@ def emit(**kw):
     print(json.dumps(kw), flush=True)
 
 
-def make_agent(dev, buffer_rows, seed=64):
+def make_agent(dev, buffer_rows, seed=64, capturable=False):
     import torch
 
     from velora_b200.models.nf import NeuroFlowCTCore
 
-    agent = NeuroFlowCTCore(4, 1, 20, 128, torch.tensor([3.0]), torch.tensor([0.0]), buffer_size=buffer_rows, seed=seed, device=dev)
+    agent = NeuroFlowCTCore(4, 1, 20, 128, torch.tensor([3.0]), torch.tensor([0.0]), buffer_size=buffer_rows, seed=seed, device=dev,
+                            capturable=capturable)
     g = torch.Generator(device=dev).manual_seed(0)
     b = agent.buffer
     b.states.copy_(torch.randn(b.states.shape, device=dev, generator=g))
@@ -107,6 +108,11 @@ def main():
         idx = torch.randint(0, 100_000, (64,))
         batch = {k: getattr(agent.buffer, k)[idx.to(dev)].cpu() for k in ("states", "actions", "rewards", "next_states", "dones", "hiddens")}
         cpu_ms = cpu_time_ms(lambda: o.train_step(batch), warmup=3, iters=20)
+    gagent = make_agent(dev, 100_000, capturable=True)
+    replay = gagent.capture_train_step(64)
+    gms = gpu_time_ms(replay, warmup=10, iters=200)
+    emit(config="cfg1/2 NeuroFlowCT._train_step captured in one CUDA graph, batch 64", metric="us_per_train_step", value=1e3 * gms,
+         cpu_port_us=None if cpu_ms is None else 1e3 * cpu_ms, cpu_cores=cores)
     emit(config="cfg1/2 NeuroFlowCT._train_step, actor 20 / critic 128, batch 64", metric="us_per_train_step", value=1e3 * ms,
          cpu_port_us=None if cpu_ms is None else 1e3 * cpu_ms, cpu_cores=cores,
          note="sample (fused gather) + 2 liquid fwd + 1 liquid bwd + 6 NCP fwd + 4 NCP bwd through the C ABI; SAC head math, Adam, "

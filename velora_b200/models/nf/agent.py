@@ -22,16 +22,18 @@ class NeuroFlowCTCore:
                  action_bias: torch.Tensor, *, optim: Type[optim.Optimizer] = optim.Adam, buffer_size: int = 1_000_000,
                  actor_lr: float = 3e-4, critic_lr: float = 3e-4, alpha_lr: float = 3e-4, initial_alpha: float = 1.0,
                  log_std: tuple = (-5, 2), tau: float = 0.005, gamma: float = 0.99, device: torch.device | None = None,
-                 seed: int | None = None) -> None:
+                 seed: int | None = None, capturable: bool = False) -> None:
         self.device = device
         self.seed = set_seed(seed)
         self.state_dim, self.action_dim = state_dim, action_dim
         self.gamma, self.tau = gamma, tau
+        # capturable=True keeps the optimizer state on the device so that a whole train step can be captured in a CUDA graph
+        okw = {"capturable": True} if capturable else None
         self.actor = ActorModule(state_dim, actor_neurons, action_dim, action_scale.to(device), action_bias.to(device),
-                                 log_std_min=log_std[0], log_std_max=log_std[1], optim=optim, lr=actor_lr, device=device)
-        self.critic = CriticModule(state_dim, critic_neurons, action_dim, optim=optim, lr=critic_lr, tau=tau, device=device)
+                                 log_std_min=log_std[0], log_std_max=log_std[1], optim=optim, lr=actor_lr, device=device, optim_kwargs=okw)
+        self.critic = CriticModule(state_dim, critic_neurons, action_dim, optim=optim, lr=critic_lr, tau=tau, device=device, optim_kwargs=okw)
         self.hidden_dim = self.actor.hidden_size
-        self.entropy = EntropyModule(action_dim, initial_alpha=initial_alpha, optim=optim, lr=alpha_lr, device=device)
+        self.entropy = EntropyModule(action_dim, initial_alpha=initial_alpha, optim=optim, lr=alpha_lr, device=device, optim_kwargs=okw)
         self.loss = nn.MSELoss()
         self.buffer = ReplayBuffer(buffer_size, state_dim, action_dim, self.actor.hidden_size, device=device)
 
@@ -64,3 +66,32 @@ class NeuroFlowCTCore:
         self.entropy.gradient_step(entropy_loss)
         self.critic.update_targets()
         return {"critic": critic_loss.detach(), "actor": actor_loss.detach(), "entropy": entropy_loss.detach()}
+
+    def capture_train_step(self, batch_size: int, warmup: int = 3):
+        """Captures one `_train_step(batch_size)` - index draw, fused gather, every network forward/backward, the SAC head
+        math, the four optimizer steps and the target update - into ONE CUDA graph and returns a callable that replays it.
+
+        At batch 64 a train step is ~250 tiny launches, i.e. pure launch/dispatch latency (the reference spends 5.9 ms per
+        step on the CPU for the same reason); replaying a graph removes the per-launch host cost.
+        Requires `capturable=True` at construction.  The returned losses are the graph's static output tensors.
+        """
+        if self.device is None or torch.device(self.device).type != "cuda":
+            raise RuntimeError("capture_train_step needs a CUDA device")
+        cur = torch.cuda.current_stream(self.device)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._train_step(batch_size)
+        cur.wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = self._train_step(batch_size)
+
+        def replay():
+            graph.replay()
+            return out
+
+        replay.graph = graph
+        return replay

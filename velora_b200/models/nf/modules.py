@@ -15,12 +15,12 @@ from velora_b200.utils.torch import soft_update
 class ActorModule:
     def __init__(self, state_dim: int, n_neurons: int, action_dim: int, action_scale: torch.Tensor, action_bias: torch.Tensor,
                  *, log_std_min: float = -5, log_std_max: float = 2, optim: Type[optim.Optimizer] = optim.Adam,
-                 lr: float = 3e-4, device: torch.device | None = None):
+                 lr: float = 3e-4, device: torch.device | None = None, optim_kwargs: dict | None = None):
         self.device = device
         self.network = SACActor(state_dim, n_neurons, action_dim, action_scale, action_bias, log_std_min=log_std_min,
                                 log_std_max=log_std_max, device=device).to(device)
         self.hidden_size = self.network.ncp.hidden_size
-        self.optim = optim(self.network.parameters(), lr=lr)
+        self.optim = optim(self.network.parameters(), lr=lr, **(optim_kwargs or {}))
         self.active_params = self.network.ncp.active_params
         self.total_params = self.network.ncp.total_params
         self.network = torch.jit.script(self.network)
@@ -39,15 +39,15 @@ class ActorModule:
 
 class CriticModule:
     def __init__(self, state_dim: int, n_neurons: int, action_dim: int, *, optim: Type[optim.Optimizer] = optim.Adam,
-                 lr: float = 3e-4, tau: float = 0.005, device: torch.device | None = None):
+                 lr: float = 3e-4, tau: float = 0.005, device: torch.device | None = None, optim_kwargs: dict | None = None):
         self.tau = tau
         self.device = device
         self.network1 = SACCriticNCP(state_dim, n_neurons, action_dim, device=device).to(device)
         self.network2 = SACCriticNCP(state_dim, n_neurons, action_dim, device=device).to(device)
         self.target1 = deepcopy(self.network1)
         self.target2 = deepcopy(self.network2)
-        self.optim1 = optim(self.network1.parameters(), lr=lr)
-        self.optim2 = optim(self.network2.parameters(), lr=lr)
+        self.optim1 = optim(self.network1.parameters(), lr=lr, **(optim_kwargs or {}))
+        self.optim2 = optim(self.network2.parameters(), lr=lr, **(optim_kwargs or {}))
         self.active_params = self.network1.ncp.active_params + self.network2.ncp.active_params
         self.total_params = self.network1.ncp.total_params + self.network2.ncp.total_params
         self.network1 = torch.jit.script(self.network1)
@@ -78,10 +78,10 @@ class EntropyModule:
     """Automatic entropy tuning: one scalar log_alpha (modules.py:646-717)."""
 
     def __init__(self, action_dim: int, *, initial_alpha: float = 1.0, optim: Type[optim.Optimizer] = optim.Adam,
-                 lr: float = 3e-4, device: torch.device | None = None):
+                 lr: float = 3e-4, device: torch.device | None = None, optim_kwargs: dict | None = None):
         self.target = -action_dim
         self.log_alpha = nn.Parameter(torch.tensor(initial_alpha, device=device).log())
-        self.optim = optim([self.log_alpha], lr=lr)
+        self.optim = optim([self.log_alpha], lr=lr, **(optim_kwargs or {}))
 
     @property
     def alpha(self) -> torch.Tensor:

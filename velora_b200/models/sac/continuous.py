@@ -33,7 +33,9 @@ class SACActor(nn.Module):
     @torch.jit.ignore
     def get_sample(self, mean: torch.Tensor, std: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         """Reparameterised sample and its log-density (continuous.py:57-77)."""
-        dist = Normal(mean, std)
+        # argument validation reads a device flag back to the host, which is illegal while a CUDA graph is being captured
+        validate = not (mean.is_cuda and torch.cuda.is_current_stream_capturing())
+        dist = Normal(mean, std, validate_args=validate)
         x_t = dist.rsample()
         return x_t, dist.log_prob(x_t)
 
