@@ -178,3 +178,47 @@ def test_full_size_properties():
     assert rel_err(g2.cpu().numpy(), 2.0 * g0.cpu().numpy()) < 1e-6
     y3, h3, g3 = run(0, 1.0)
     assert torch.equal(y0, y3) and torch.equal(h0, h3) and torch.equal(g0, g3)
+
+
+@pytest.mark.parametrize("name", ["actor_seq", "actor_seq_allh", "fixture_seq"])
+def test_time_major_storage_matches_reference(golden, name):
+    """x and the upstream gradients stored time-major ([T,B,F], the stack of per-step batches) are read in place:
+    same results as the reference, dx comes back in x's storage order, y / h_traj are [B,T,F] views."""
+    d = golden("liquid")
+    net = _build(d, name)
+    dev = torch.device("cuda")
+
+    def tm(a):   # [B,T,F] values in time-major storage
+        return torch.tensor(a, device=dev).permute(1, 0, 2).contiguous().permute(1, 0, 2)
+
+    x = tm(d[f"{name}_x"]).requires_grad_(True)
+    assert not x.is_contiguous()
+    h0 = torch.tensor(d[f"{name}_h0"], device=dev, requires_grad=True)
+    ry, rh = tm(d[f"{name}_ry"]), tm(d[f"{name}_rh"])
+    y, ht = net.forward_seq(x, h0)
+    assert y.shape == tuple(d[f"{name}_f32_y"].shape) and ht.shape == tuple(d[f"{name}_f32_htraj"].shape)
+    assert_close_to_reference(y.detach().cpu().numpy(), d[f"{name}_f32_y"], d[f"{name}_f64_y"], "y")
+    assert_close_to_reference(ht.detach().cpu().numpy(), d[f"{name}_f32_htraj"], d[f"{name}_f64_htraj"], "h_traj")
+    torch.autograd.backward([y, ht], [ry, rh])
+    assert x.grad.stride() == x.stride()
+    assert_close_to_reference(x.grad.cpu().numpy(), d[f"{name}_f32_dx"], d[f"{name}_f64_dx"], "dx")
+    assert_close_to_reference(h0.grad.cpu().numpy(), d[f"{name}_f32_dh0"], d[f"{name}_f64_dh0"], "dh0")
+    for k, p in net.named_parameters():
+        assert_close_to_reference(p.grad.cpu().numpy(), d[f"{name}_f32_grad_{k}"], d[f"{name}_f64_grad_{k}"], f"grad {k}")
+
+
+def test_time_major_flag_rejected_off_the_tensor_core_path():
+    """The layout flags are a contract of the tcgen05 kernels; the C ABI refuses them elsewhere instead of misreading rows."""
+    from velora_b200 import _lib
+
+    L = _lib.lib()
+    assert L.vb_liquid_time_major_ok(4, 12, 8, 2, 0) == 1
+    assert L.vb_liquid_time_major_ok(4, 12, 8, 2, 2) == 0      # FORCE_FFMA
+    assert L.vb_liquid_time_major_ok(8, 300, 212, 1, 0) == 0   # no tensor-core kernel for this shape
+    n = L.vb_liquid_packed_floats(4, 12, 8, 2)
+    packed = torch.zeros(n, device="cuda")
+    x = torch.zeros(8, 3, 4, device="cuda")
+    y = torch.zeros(8, 3, 2, device="cuda")
+    h = torch.zeros(8, 3, 8, device="cuda")
+    rc = L.vb_liquid_fwd(_lib.ptr(packed), _lib.ptr(x), None, _lib.ptr(y), _lib.ptr(h), 8, 3, 4, 12, 8, 2, None, 0, 2 | 16, None)
+    assert rc == -6 and b"time-major" in L.vb_last_error()

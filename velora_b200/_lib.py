@@ -29,6 +29,7 @@ SIGNATURES = {
     "vb_liquid_packed_floats": (_i64, [_i, _i, _i, _i]),
     "vb_liquid_grad_floats": (_i64, [_i, _i, _i, _i]),
     "vb_liquid_has_fast_path": (_i, [_i, _i, _i, _i]),
+    "vb_liquid_time_major_ok": (_i, [_i, _i, _i, _i, _i]),
     "vb_liquid_pack": (_i, [_p, _p, _p, _i, _pp, _pp, _pp, _i, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
     "vb_liquid_fwd_workspace_bytes": (_i64, [_i, _i, _i, _i, _i64, _i]),
     "vb_liquid_bwd_workspace_bytes": (_i64, [_i, _i, _i, _i, _i64, _i]),

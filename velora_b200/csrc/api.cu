@@ -48,9 +48,9 @@ int64_t bwd_workspace_bytes(int, int, int, int, int64_t);
 }  // namespace small
 namespace tc {
 bool has_tc_path(int I, int Ni, int Nc, int O);
-int fwd(const float*, const float*, const float*, float*, float*, int64_t, int, int, int, int, int, cudaStream_t);
+int fwd(const float*, const float*, const float*, float*, float*, int64_t, int, int, int, int, int, int, cudaStream_t);
 int bwd(const float*, const float*, const float*, const float*, const float*, const float*, const float*, float*, float*, float*,
-        int64_t, int, int, int, int, int, void*, int64_t, cudaStream_t);
+        int64_t, int, int, int, int, int, int, void*, int64_t, cudaStream_t);
 int64_t bwd_workspace_bytes(int, int, int, int);
 }  // namespace tc
 namespace generic {
@@ -99,6 +99,9 @@ extern "C" int64_t vb_liquid_fwd_workspace_bytes(int I, int Ni, int Nc, int O, i
     if (!dims_ok(I, Ni, Nc, O)) return VB_ERR_BAD_DIMS;
     return 16;
 }
+extern "C" int vb_liquid_time_major_ok(int I, int Ni, int Nc, int O, int flags) {
+    return !(flags & (VB_FLAG_FORCE_GENERIC | VB_FLAG_FORCE_FFMA)) && tc::has_tc_path(I, Ni, Nc, O);
+}
 extern "C" int64_t vb_liquid_bwd_workspace_bytes(int I, int Ni, int Nc, int O, int64_t B, int T) {
     (void)T;
     if (!dims_ok(I, Ni, Nc, O)) return VB_ERR_BAD_DIMS;
@@ -121,7 +124,9 @@ extern "C" int vb_liquid_fwd(const float* packed, const float* x, const float* h
     VB_CHECK_ARG(packed && x && y && h_traj, VB_ERR_NULL_POINTER, "vb_liquid_fwd: null pointer");
     if (B == 0) return 0;
     if (!(flags & (VB_FLAG_FORCE_GENERIC | VB_FLAG_FORCE_FFMA)) && tc::has_tc_path(I, Ni, Nc, O))
-        return tc::fwd(packed, x, h0, y, h_traj, B, T, I, Ni, Nc, O, (cudaStream_t)stream);
+        return tc::fwd(packed, x, h0, y, h_traj, B, T, I, Ni, Nc, O, flags & VB_FLAG_LAYOUT_MASK, (cudaStream_t)stream);
+    VB_CHECK_ARG(!(flags & VB_FLAG_LAYOUT_MASK) || T == 1, VB_ERR_LAYOUT,
+                 "vb_liquid_fwd: time-major tensors are only supported by the tensor-core kernels (vb_liquid_time_major_ok)");
     if (!(flags & VB_FLAG_FORCE_GENERIC) && small::has_fast_path(I, Ni, Nc, O))
         return small::fwd(packed, x, h0, y, h_traj, B, T, I, Ni, Nc, O, (cudaStream_t)stream);
     return generic::liquid_fwd(packed, x, h0, y, h_traj, B, T, I, Ni, Nc, O, (cudaStream_t)stream);
@@ -139,7 +144,10 @@ extern "C" int vb_liquid_bwd(const float* packed, const float* x, const float* h
         return 0;
     }
     if (!(flags & (VB_FLAG_FORCE_GENERIC | VB_FLAG_FORCE_FFMA)) && tc::has_tc_path(I, Ni, Nc, O))
-        return tc::bwd(packed, x, h0, h_traj, dy, dh_traj, dh_last, dx, dh0, dpacked, B, T, I, Ni, Nc, O, workspace, workspace_bytes, (cudaStream_t)stream);
+        return tc::bwd(packed, x, h0, h_traj, dy, dh_traj, dh_last, dx, dh0, dpacked, B, T, I, Ni, Nc, O, flags & VB_FLAG_LAYOUT_MASK,
+                       workspace, workspace_bytes, (cudaStream_t)stream);
+    VB_CHECK_ARG(!(flags & VB_FLAG_LAYOUT_MASK) || T == 1, VB_ERR_LAYOUT,
+                 "vb_liquid_bwd: time-major tensors are only supported by the tensor-core kernels (vb_liquid_time_major_ok)");
     if (!(flags & VB_FLAG_FORCE_GENERIC) && small::has_fast_path(I, Ni, Nc, O))
         return small::bwd(packed, x, h0, h_traj, dy, dh_traj, dh_last, dx, dh0, dpacked, B, T, I, Ni, Nc, O, workspace, workspace_bytes, (cudaStream_t)stream);
     return generic::liquid_bwd(packed, x, h0, h_traj, dy, dh_traj, dh_last, dx, dh0, dpacked, B, T, I, Ni, Nc, O, workspace, workspace_bytes, (cudaStream_t)stream);

@@ -160,19 +160,16 @@ __device__ __forceinline__ float mish_f(float x) {
     float w = n * (n + 2.0f);
     return x * (w * rcp_approx(w + 2.0f));
 }
-// Mish and its derivative t + x * sigmoid(x) * (1 - t^2), t = tanh(softplus x) = w/(w+2),
-// sigmoid(x) = n/(1+n), 1 - t^2 = 4 (w+1) / (w+2)^2.  The two reciprocals share one MUFU.
+// Mish and its derivative.  With n = e^x, w = n (n + 2), t = tanh(softplus x) = w / (w + 2):
+//   dt/dx = (1 - t^2) sigmoid(x) = [4 (w + 1) / (w + 2)^2] [n / (n + 1)] = 4 n (n + 1) / (w + 2)^2     (w + 1 = (n + 1)^2)
+// so mish'(x) = t + 4 x n (n + 1) r^2 with r = 1 / (w + 2): one ex2, one rcp, 10 FP32 ops.
 __device__ __forceinline__ float mish_fwd_grad(float x, float& dmish) {
     float n = ex2_approx(fminf(x, 20.0f) * kLog2e);
     float w = n * (n + 2.0f);
-    float w2 = w + 2.0f;
-    float n1 = n + 1.0f;
-    float q = rcp_approx(w2 * n1);   // 1 / ((w+2)(n+1))
-    float r = q * n1;                // 1 / (w+2)
-    float sig = n * (q * w2);        // n / (n+1)
+    float r = rcp_approx(w + 2.0f);
     float t = w * r;
-    float omt2 = 4.0f * (w + 1.0f) * r * r;
-    dmish = fmaf(x * sig, omt2, t);
+    float p = fmaf(n, n, n) * r;     // n (n + 1) / (w + 2)
+    dmish = fmaf(4.0f * x, p * r, t);
     return x * t;
 }
 

@@ -35,6 +35,15 @@
 namespace vb {
 namespace tc {
 
+// Row index of (sample b, step t) in a [B,T,F] tensor stored batch-major (row b*T + t) or time-major (row t*B + b).
+// One thread owns one sample, so time-major storage makes every warp access one contiguous run of 32 rows.
+struct RowMap {
+    int64_t sb, st;
+    __host__ __device__ RowMap(bool time_major, int64_t B, int T) : sb(time_major ? 1 : T), st(time_major ? B : 1) {}
+    __device__ __forceinline__ int64_t operator()(int64_t b, int t) const { return b * sb + (int64_t)t * st; }
+};
+constexpr int LAY_X = 16, LAY_Y = 32, LAY_H = 64, LAY_DX = 128, LAY_DH = 256;   // = VB_FLAG_*_TIME_MAJOR
+
 // constant-bank copy of the small layers' weights (inter / motor and their data-gradients): F section + transposed
 // copies, same layout as liquid_small.cu.  A __constant__ symbol is private to its translation unit.
 constexpr int kConstFloats = 2048;
@@ -295,6 +304,7 @@ __global__ void __launch_bounds__(TM) liquid_fwd_tc_kernel(const float* __restri
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::BAR + 16);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool vx = vec_flags & 1, vy = vec_flags & 2, vh = vec_flags & 4;
+    const RowMap rx(vec_flags & LAY_X, B, T), ry(vec_flags & LAY_Y, B, T), rh(vec_flags & LAY_H, B, T), rdx(vec_flags & LAY_DX, B, T), rdh(vec_flags & LAY_DH, B, T);
 
     // heads operand: B[n][k] = W_heads[k][n] for k < K, bias for k == ONE
     // rows in NEURON-MAJOR head order n' = 4 j + hs, so that one 8-column TMEM load holds two complete neurons
@@ -331,12 +341,12 @@ __global__ void __launch_bounds__(TM) liquid_fwd_tc_kernel(const float* __restri
         float xn[C::I];
 #pragma unroll
         for (int i = 0; i < C::I; ++i) xn[i] = 0.f;
-        if (valid) ldg_row<C::I>(xn, x + (b * T) * C::I, vx);
+        if (valid) ldg_row<C::I>(xn, x + rx(b, 0) * C::I, vx);
         for (int t = 0; t < T; ++t) {
             float xr[C::I];
 #pragma unroll
             for (int i = 0; i < C::I; ++i) xr[i] = xn[i];
-            if (valid && t + 1 < T) ldg_row<C::I>(xn, x + (b * T + t + 1) * C::I, vx);   // prefetch the next step's input
+            if (valid && t + 1 < T) ldg_row<C::I>(xn, x + rx(b, t + 1) * C::I, vx);   // prefetch the next step's input
             float a[C::NI];
             {
                 float u[C::NI];
@@ -379,8 +389,8 @@ __global__ void __launch_bounds__(TM) liquid_fwd_tc_kernel(const float* __restri
                 yo[o] = acc;
             }
             if (valid) {
-                stg_row<C::O>(y + (b * T + t) * C::O, yo, vy);
-                stg_row<C::NC>(h_traj + (b * T + t) * C::NC, h, vh);
+                stg_row<C::O>(y + ry(b, t) * C::O, yo, vy);
+                stg_row<C::NC>(h_traj + rh(b, t) * C::NC, h, vh);
             }
         }
     }
@@ -412,8 +422,17 @@ __global__ void __launch_bounds__(TM, 4) liquid_bwd_tc_kernel(
     float* __restrict__ dx, float* __restrict__ dh0, float* __restrict__ partials, float* __restrict__ d3buf,
     int64_t B, int T, int vec_flags, long long* __restrict__ trace) {
     using S = BwdSmem<C>;
-#define VB_TRACE(slot) do { if (trace && blockIdx.x == 0 && tid == 0 && t >= T - 4) trace[(T - 1 - t) * 16 + (slot)] = clock64(); } while (0)
+#define VB_TRACE(slot) do { if (trace && blockIdx.x == 0 && tid == 0 && T - 1 - t < 40) trace[(T - 1 - t) * 16 + (slot)] = clock64(); } while (0)
+#define VB_MARK(slot) do { if (trace && blockIdx.x == 0 && tid == 0) trace[40 * 16 + (slot)] = clock64(); } while (0)
     extern __shared__ __align__(1024) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    VB_MARK(0);
+    if (trace && tid == 0 && blockIdx.x < 1024) {
+        unsigned long long gt; unsigned smid;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+        asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+        trace[1024 + blockIdx.x * 4] = (long long)gt; trace[1024 + blockIdx.x * 4 + 2] = smid;
+    }
     unsigned char* zP = smem + S::Z;
     unsigned char* dsP = smem + S::DS;
     unsigned char* wB = smem + S::WB;
@@ -423,8 +442,8 @@ __global__ void __launch_bounds__(TM, 4) liquid_bwd_tc_kernel(
     uint64_t* bar2 = bar1 + 1;                                     // dz ready
     uint64_t* bar3 = bar1 + 2;                                     // dW batch done (z~ and ds planes may be overwritten)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::BAR + 32);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool vx = vec_flags & 1, vy = vec_flags & 2, vh = vec_flags & 4;
+    const RowMap rx(vec_flags & LAY_X, B, T), ry(vec_flags & LAY_Y, B, T), rh(vec_flags & LAY_H, B, T), rdx(vec_flags & LAY_DX, B, T), rdh(vec_flags & LAY_DH, B, T);
 
     // heads operand B[n][k]: W_heads[k][n] for k < K, bias for k == ONE, zero elsewhere
     // rows in NEURON-MAJOR head order n' = 4 j + hs, so that one 8-column TMEM load holds two complete neurons
@@ -463,30 +482,23 @@ __global__ void __launch_bounds__(TM, 4) liquid_bwd_tc_kernel(
     uint32_t ph = 0;              // all three barriers complete exactly once per step: one shared phase bit
     int since_flush = 0;          // dW batches accumulated in TMEM since the last flush (0 => next batch overwrites)
 
-    // small-layer gradients: unit u = (entry e, sample quarter q); thread owns units tid, tid+128, tid+256
-    //   entries: [0, I*NI) dW_in[i][j] = sum x_i du_j ; then O*NC: dW_out[o][j] = sum dy_o m_j ; then NI: db_in ; then O: db_out
-    constexpr int R_DU = 0, R_X = C::NI, R_DY = C::NI + C::I, R_M = C::NI + C::I + C::O;
-    constexpr int N_UNITS = 4 * C::N_SMALL;
-    constexpr int UPT = (N_UNITS + TM - 1) / TM;   // units per thread
-    float g_small[UPT];
-    uint32_t rows[UPT];           // rowA | rowB << 16 (float offsets into sbuf); rowB = 0xffff: bias entry (plain sum of rowA); 0xfffe: no unit
+    // small-layer gradients: register-blocked reductions over the fp32 transposition buffer (rows = features, columns = the
+    // tile's 128 samples), 5x less shared-memory traffic than one (entry, sample-quarter) unit per thread:
+    //   warps 0-1  dW_in[i][j], db_in[j] for the three inter neurons j = 3 blk + r (4 blocks) over samples {4 sg .. 4 sg + 3} and
+    //              {64 + 4 sg ..} (16 sample groups): 7 rows x 2 LDS.128 feed 120 FMA/ADD
+    //   warps 2-3  dW_out[o][j], db_out[o] for the four command neurons j = 4 blk + r (2 blocks) over samples {4 sg ..} (32 groups)
+    constexpr int R_DU = 0, R_X = C::NI, R_DY = C::NI + C::I;
+    static_assert(C::NI == 12 && C::NC == 8, "small-gradient blocking is written for 12 inter / 8 command neurons");
+    constexpr int JA = 3, JB = 4;
+    constexpr int NACC = (C::I * JA + JA > C::O * JB + C::O) ? (C::I * JA + JA) : (C::O * JB + C::O);
+    float acc[NACC];
 #pragma unroll
-    for (int k = 0; k < UPT; ++k) {
-        g_small[k] = 0.f;
-        const int u = tid + k * TM;
-        const int e = u % C::N_SMALL, q = (u / C::N_SMALL) & 3;
-        int ra, rb;
-        bool m_row = false;
-        if (e < C::I * C::NI) { ra = R_X + e / C::NI; rb = R_DU + e % C::NI; }
-        else if (e < C::I * C::NI + C::O * C::NC) { const int f = e - C::I * C::NI; ra = R_DY + f / C::NC; rb = f % C::NC; m_row = true; }
-        else if (e < C::I * C::NI + C::O * C::NC + C::NI) { ra = R_DU + (e - C::I * C::NI - C::O * C::NC); rb = -1; }
-        else { ra = R_DY + (e - C::I * C::NI - C::O * C::NC - C::NI); rb = -1; }
-        const uint32_t oa = ra * SBUF_STRIDE + q * 32;
-        // m rows live in the strip ([Nc][128] floats right after the plane window): offset relative to sbuf
-        const uint32_t ob = rb < 0 ? 0xffffu
-                                   : (m_row ? (uint32_t)((S::MSTRIP - S::DS) / 4 + rb * TM + q * 32) : (uint32_t)(rb * SBUF_STRIDE + q * 32));
-        rows[k] = (u >= N_UNITS) ? 0xfffe0000u : (oa | (ob << 16));
-    }
+    for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
+    const int sgA = tid & 15, blkA = (tid >> 4) & 3, sgB = tid & 31, blkB = (tid >> 5) & 1;
+    const float* rowsA = sbuf + 4 * sgA;                                      // + row * SBUF_STRIDE (+ 64 for the second half)
+    const float* rowsB = sbuf + 4 * sgB;
+    const float* duA = rowsA + (R_DU + JA * blkA) * SBUF_STRIDE;
+    const float* mB = mstrip + (JB * blkB) * TM + 4 * sgB;
 
     auto flush_dw = [&]() {   // all threads; requires the dW batch to be complete
         tc_fence_after();
@@ -494,16 +506,16 @@ __global__ void __launch_bounds__(TM, 4) liquid_bwd_tc_kernel(
         for (int g = 0; g < 3; ++g) {
             float v[32];
             tmem_ld32(taddr + 32 + 32 * g, v);
+            // fire-and-forget vector reductions into this thread's private row: no load, nothing to wait for
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                float4 a4 = reinterpret_cast<float4*>(d3row)[8 * g + q];
-                a4.x += v[4 * q]; a4.y += v[4 * q + 1]; a4.z += v[4 * q + 2]; a4.w += v[4 * q + 3];
-                reinterpret_cast<float4*>(d3row)[8 * g + q] = a4;
-            }
+            for (int q = 0; q < 8; ++q)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d3row + 32 * g + 4 * q), "f"(v[4 * q]), "f"(v[4 * q + 1]),
+                             "f"(v[4 * q + 2]), "f"(v[4 * q + 3]) : "memory");
         }
         since_flush = 0;
     };
 
+    VB_MARK(1);
     const int64_t n_tiles = (B + TM - 1) / TM;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t b = tile * TM + tid;
@@ -520,8 +532,8 @@ __global__ void __launch_bounds__(TM, 4) liquid_bwd_tc_kernel(
 #pragma unroll
         for (int o = 0; o < C::O; ++o) dyn[o] = 0.f;
         if (valid) {
-            ldg_row<C::I>(xn, x + (b * T + T - 1) * C::I, vx);
-            ldg_row<C::O>(dyn, dy + (b * T + T - 1) * C::O, vy);
+            ldg_row<C::I>(xn, x + rx(b, T - 1) * C::I, vx);
+            ldg_row<C::O>(dyn, dy + ry(b, T - 1) * C::O, vy);
         }
         for (int t = T - 1; t >= 0; --t) {
             float xr[C::I], dyr[C::O], hp[C::NC];
@@ -532,11 +544,11 @@ __global__ void __launch_bounds__(TM, 4) liquid_bwd_tc_kernel(
 #pragma unroll
             for (int j = 0; j < C::NC; ++j) hp[j] = 0.f;
             if (valid) {
-                if (t > 0) ldg_row<C::NC>(hp, h_traj + (b * T + t - 1) * C::NC, vh);
+                if (t > 0) ldg_row<C::NC>(hp, h_traj + rh(b, t - 1) * C::NC, vh);
                 else if (h0) ldg_row<C::NC>(hp, h0 + b * C::NC, vh);
                 if (t > 0) {
-                    ldg_row<C::I>(xn, x + (b * T + t - 1) * C::I, vx);
-                    ldg_row<C::O>(dyn, dy + (b * T + t - 1) * C::O, vy);
+                    ldg_row<C::I>(xn, x + rx(b, t - 1) * C::I, vx);
+                    ldg_row<C::O>(dyn, dy + ry(b, t - 1) * C::O, vy);
                 }
             }
             VB_TRACE(0);
@@ -565,7 +577,7 @@ __global__ void __launch_bounds__(TM, 4) liquid_bwd_tc_kernel(
             VB_TRACE(4);
             // ---------------- gating derivatives, two neurons (= one 8-feature chunk of ds) at a time
             {
-                const float* dhe_p = (valid && dh_traj) ? dh_traj + (b * T + t) * C::NC : nullptr;
+                const float* dhe_p = (valid && dh_traj) ? dh_traj + rdh(b, t) * C::NC : nullptr;
 #pragma unroll
                 for (int c = 0; c < C::NC / 2; ++c) {
                     float s8[8];
@@ -650,7 +662,7 @@ __global__ void __launch_bounds__(TM, 4) liquid_bwd_tc_kernel(
                 for (int j = 0; j < C::NI; ++j)
 #pragma unroll
                     for (int i = 0; i < C::I; ++i) dxr[i] = fmaf(du[j], c_p[C::WIN + j * C::Ip + i], dxr[i]);
-                if (valid && dx) stg_row<C::I>(dx + (b * T + t) * C::I, dxr, vx);
+                if (valid && dx) stg_row<C::I>(dx + rdx(b, t) * C::I, dxr, vx);
             }
             // ---------------- small-layer gradients: fp32 transposition through the (now idle) ds planes
             VB_TRACE(9);
@@ -665,34 +677,41 @@ __global__ void __launch_bounds__(TM, 4) liquid_bwd_tc_kernel(
 #pragma unroll
             for (int o = 0; o < C::O; ++o) sbuf[(R_DY + o) * SBUF_STRIDE + tid] = dyr[o];
             __syncthreads();
+            if (warp < 2) {
 #pragma unroll
-            for (int k = 0; k < UPT; ++k) {
-                const uint32_t oa = rows[k] & 0xffffu, ob = rows[k] >> 16;
-                if (ob < 0xfffeu) {
-                    const float4* pa = reinterpret_cast<const float4*>(sbuf + oa);
-                    const float4* pb = reinterpret_cast<const float4*>(sbuf + ob);
-                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;      // independent chains: the loop is latency bound otherwise
+                for (int half = 0; half < 2; ++half) {
+                    float4 xv[C::I], dv[JA];
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        float4 va = pa[q], vb = pb[q];
-                        a0 = fmaf(va.x, vb.x, a0); a1 = fmaf(va.y, vb.y, a1); a2 = fmaf(va.z, vb.z, a2); a3 = fmaf(va.w, vb.w, a3);
+                    for (int i = 0; i < C::I; ++i) xv[i] = *reinterpret_cast<const float4*>(rowsA + (R_X + i) * SBUF_STRIDE + 64 * half);
+#pragma unroll
+                    for (int r = 0; r < JA; ++r) dv[r] = *reinterpret_cast<const float4*>(duA + r * SBUF_STRIDE + 64 * half);
+#pragma unroll
+                    for (int r = 0; r < JA; ++r) {
+#pragma unroll
+                        for (int i = 0; i < C::I; ++i)
+                            acc[i * JA + r] = fmaf(xv[i].x, dv[r].x, fmaf(xv[i].y, dv[r].y, fmaf(xv[i].z, dv[r].z, fmaf(xv[i].w, dv[r].w, acc[i * JA + r]))));
+                        acc[C::I * JA + r] += (dv[r].x + dv[r].y) + (dv[r].z + dv[r].w);
                     }
-                    g_small[k] += (a0 + a1) + (a2 + a3);
-                } else if (ob == 0xffffu) {
-                    const float4* pa = reinterpret_cast<const float4*>(sbuf + oa);
-                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                }
+            } else {
+                float4 yv[C::O], mv[JB];
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        float4 va = pa[q];
-                        a0 += va.x; a1 += va.y; a2 += va.z; a3 += va.w;
-                    }
-                    g_small[k] += (a0 + a1) + (a2 + a3);
+                for (int o = 0; o < C::O; ++o) yv[o] = *reinterpret_cast<const float4*>(rowsB + (R_DY + o) * SBUF_STRIDE);
+#pragma unroll
+                for (int r = 0; r < JB; ++r) mv[r] = *reinterpret_cast<const float4*>(mB + r * TM);
+#pragma unroll
+                for (int o = 0; o < C::O; ++o) {
+#pragma unroll
+                    for (int r = 0; r < JB; ++r)
+                        acc[o * JB + r] = fmaf(yv[o].x, mv[r].x, fmaf(yv[o].y, mv[r].y, fmaf(yv[o].z, mv[r].z, fmaf(yv[o].w, mv[r].w, acc[o * JB + r]))));
+                    acc[C::O * JB + o] += (yv[o].x + yv[o].y) + (yv[o].z + yv[o].w);
                 }
             }
             VB_TRACE(11);
         }
         if (valid && dh0) stg_row<C::NC>(dh0 + b * C::NC, dhc, vh);
     }
+    VB_MARK(2);
     if (since_flush > 0) flush_dw();
     tc_fence_before();
     __syncthreads();
@@ -701,10 +720,30 @@ __global__ void __launch_bounds__(TM, 4) liquid_bwd_tc_kernel(
     // ---------------- per-CTA partial gradient row (F layout)
     float* prow = partials + (int64_t)blockIdx.x * C::F_TOTAL;
     for (int idx = tid; idx < C::F_TOTAL; idx += TM) prow[idx] = 0.f;
-    float* units = reinterpret_cast<float*>(smem);   // [N_UNITS]
+    // per-thread small-gradient accumulators -> red[entry][sample group] -> one sum per entry
+    constexpr int RS = 33;
+    float* red = reinterpret_cast<float*>(smem);   // [N_SMALL][RS]; the operand planes are dead
+    if (warp < 2) {
 #pragma unroll
-    for (int k = 0; k < UPT; ++k)
-        if (tid + k * TM < N_UNITS) units[tid + k * TM] = g_small[k];
+        for (int r = 0; r < JA; ++r) {
+#pragma unroll
+            for (int i = 0; i < C::I; ++i) {
+                const int e = i * C::NI + JA * blkA + r;
+                red[e * RS + sgA] = acc[i * JA + r];
+                red[e * RS + 16 + sgA] = 0.f;
+            }
+            const int e = C::I * C::NI + C::O * C::NC + JA * blkA + r;
+            red[e * RS + sgA] = acc[C::I * JA + r];
+            red[e * RS + 16 + sgA] = 0.f;
+        }
+    } else {
+#pragma unroll
+        for (int o = 0; o < C::O; ++o) {
+#pragma unroll
+            for (int r = 0; r < JB; ++r) red[(C::I * C::NI + o * C::NC + JB * blkB + r) * RS + sgB] = acc[o * JB + r];
+            if (blkB == 0) red[(C::I * C::NI + C::O * C::NC + C::NI + o) * RS + sgB] = acc[C::O * JB + o];
+        }
+    }
     __syncthreads();
     {
         const float* d3 = d3buf + (int64_t)blockIdx.x * D3_FLOATS;
@@ -723,14 +762,23 @@ __global__ void __launch_bounds__(TM, 4) liquid_bwd_tc_kernel(
             }
         }
         for (int e = tid; e < C::N_SMALL; e += TM) {
-            const float acc = (units[e] + units[C::N_SMALL + e]) + (units[2 * C::N_SMALL + e] + units[3 * C::N_SMALL + e]);
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int g = 0; g < 32; g += 2) { a0 += red[e * RS + g]; a1 += red[e * RS + g + 1]; }
+            const float tot = a0 + a1;
             int idx;
             if (e < C::I * C::NI) idx = C::WIN_T + (e / C::NI) * C::NIp + (e % C::NI);
             else if (e < C::I * C::NI + C::O * C::NC) { const int f = e - C::I * C::NI; idx = C::WOUT + (f / C::NC) * C::NCp + (f % C::NC); }
             else if (e < C::I * C::NI + C::O * C::NC + C::NI) idx = C::B_IN + (e - C::I * C::NI - C::O * C::NC);
             else idx = C::B_OUT + (e - C::I * C::NI - C::O * C::NC - C::NI);
-            prow[idx] = acc;
+            prow[idx] = tot;
         }
+    }
+    VB_MARK(3);
+    if (trace && tid == 0 && blockIdx.x < 1024) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+        trace[1024 + blockIdx.x * 4 + 1] = (long long)gt;
     }
 }
 
@@ -790,7 +838,7 @@ static int grid_cap(K kernel, int smem, int tmem_cols, int* per_sm) {
 }
 
 template <class C>
-static int launch_fwd(const float* packed, const float* x, const float* h0, float* y, float* h_traj, int64_t B, int T, cudaStream_t stream) {
+static int launch_fwd(const float* packed, const float* x, const float* h0, float* y, float* h_traj, int64_t B, int T, int layout, cudaStream_t stream) {
     std::lock_guard<std::mutex> lock(g_mu);
     int dev;
     bool capturing;
@@ -803,7 +851,7 @@ static int launch_fwd(const float* packed, const float* x, const float* h0, floa
     int64_t cap = (int64_t)device_sms() * per_sm;
     int grid = (int)(n_tiles < cap ? n_tiles : cap);
     if (grid < 1) grid = 1;
-    int vf = vec_flags_for(x, y, h0, h_traj, nullptr, nullptr, nullptr, nullptr, T, C::I, C::O, C::NC);
+    int vf = vec_flags_for(x, y, h0, h_traj, nullptr, nullptr, nullptr, nullptr, T, C::I, C::O, C::NC) | layout;
     liquid_fwd_tc_kernel<C><<<grid, TM, FwdSmem<C>::BYTES, stream>>>(packed, x, h0, y, h_traj, B, T, vf);
     VB_LAUNCH_CHECK();
     if (!capturing) VB_CUDA(cudaEventRecord(g_ev[dev & 63], stream));
@@ -825,7 +873,7 @@ static int bwd_grid(int64_t B, int* grid_out) {
 template <class C>
 static int launch_bwd(const float* packed, const float* x, const float* h0, const float* h_traj, const float* dy,
                       const float* dh_traj, const float* dh_last, float* dx, float* dh0, float* dpacked,
-                      int64_t B, int T, void* ws, int64_t ws_bytes, cudaStream_t stream) {
+                      int64_t B, int T, int layout, void* ws, int64_t ws_bytes, cudaStream_t stream) {
     int grid = 1;
     int rc = bwd_grid<C>(B, &grid);
     if (rc) return rc;
@@ -837,16 +885,16 @@ static int launch_bwd(const float* packed, const float* x, const float* h0, cons
     bool capturing;
     rc = upload_constants(packed, C::C_TOTAL, stream, &dev, &capturing);
     if (rc) return rc;
-    int vf = vec_flags_for(x, dy, h0, h_traj, dh_traj, dh_last, dx, dh0, T, C::I, C::O, C::NC);
+    int vf = vec_flags_for(x, dy, h0, h_traj, dh_traj, dh_last, dx, dh0, T, C::I, C::O, C::NC) | layout;
     float* partials = reinterpret_cast<float*>(ws);
     float* d3buf = partials + (int64_t)grid * C::F_TOTAL;
     long long* trace = nullptr;
-    if (getenv("VB_TRACE")) cudaMalloc(&trace, 64 * 16 * sizeof(long long));
+    if (getenv("VB_TRACE")) { cudaMalloc(&trace, (1024 + 4096) * sizeof(long long)); cudaMemset(trace, 0, (1024 + 4096) * sizeof(long long)); }
     liquid_bwd_tc_kernel<C><<<grid, TM, BwdSmem<C>::BYTES, stream>>>(packed, x, h0, h_traj, dy, dh_traj, dh_last, dx, dh0, partials,
                                                                      d3buf, B, T, vf, trace);
     VB_LAUNCH_CHECK();
     if (trace) {
-        long long h[64];
+        long long h[64 * 16];
         cudaMemcpy(h, trace, sizeof(h), cudaMemcpyDeviceToHost);
         const char* names[12] = {"top(loads issued)", "inter+mish+store_z", "sync1", "issue heads", "wait heads", "gating+store ds", "sync2", "issue dz/dW",
                                  "wait dz", "du,dx", "wait dW", "small grads"};
@@ -855,6 +903,24 @@ static int launch_bwd(const float* packed, const float* x, const float* h0, cons
             for (int k = 1; k < 12; ++k) fprintf(stderr, " %s=%lld", names[k], h[st * 16 + k] - h[st * 16 + k - 1]);
             if (st < 3) fprintf(stderr, " | to next top=%lld", h[(st + 1) * 16] - h[st * 16 + 11]);
             fprintf(stderr, "\n");
+        }
+        fprintf(stderr, "[vb trace] step totals:");
+        for (int st = 0; st + 1 < T && st < 39; ++st) fprintf(stderr, " %lld", h[(st + 1) * 16] - h[st * 16]);
+        fprintf(stderr, "\n[vb trace] prologue=%lld loop=%lld epilogue=%lld\n", h[40 * 16 + 1] - h[40 * 16], h[40 * 16 + 2] - h[40 * 16 + 1],
+                h[40 * 16 + 3] - h[40 * 16 + 2]);
+        {
+            static long long hb[4096];
+            cudaMemcpy(hb, trace + 1024, sizeof(hb), cudaMemcpyDeviceToHost);
+            long long t0 = hb[0], t1 = 0;
+            for (int c = 0; c < grid && c < 1024; ++c) { if (hb[c * 4] < t0) t0 = hb[c * 4]; if (hb[c * 4 + 1] > t1) t1 = hb[c * 4 + 1]; }
+            int per_sm[256] = {0};
+            long long sm_end[256] = {0};
+            for (int c = 0; c < grid && c < 1024; ++c) { int sm = (int)hb[c * 4 + 2] & 255; per_sm[sm]++; if (hb[c * 4 + 1] - t0 > sm_end[sm]) sm_end[sm] = hb[c * 4 + 1] - t0; }
+            long long e3 = 0, e4 = 0; int n3 = 0, n4 = 0; long long latest_start = 0;
+            for (int c = 0; c < grid && c < 1024; ++c) if (hb[c * 4] - t0 > latest_start) latest_start = hb[c * 4] - t0;
+            for (int sm = 0; sm < 256; ++sm) { if (per_sm[sm] == 3) { e3 += sm_end[sm]; n3++; } if (per_sm[sm] >= 4) { e4 += sm_end[sm]; n4++; } }
+            fprintf(stderr, "[vb trace] grid %d span %lld ns, latest CTA start %lld ns; SMs with 3 CTAs: %d (avg end %lld ns), with >=4: %d (avg end %lld ns)\n",
+                    grid, t1 - t0, latest_start, n3, n3 ? e3 / n3 : 0, n4, n4 ? e4 / n4 : 0);
         }
         cudaFree(trace);
     }
@@ -874,8 +940,8 @@ bool has_tc_path(int I, int Ni, int Nc, int O) {
 }
 
 int fwd(const float* packed, const float* x, const float* h0, float* y, float* h_traj, int64_t B, int T,
-        int I, int Ni, int Nc, int O, cudaStream_t stream) {
-#define X(a, b, c, d) if (I == a && Ni == b && Nc == c && O == d) return launch_fwd<Cfg<a, b, c, d>>(packed, x, h0, y, h_traj, B, T, stream);
+        int I, int Ni, int Nc, int O, int layout, cudaStream_t stream) {
+#define X(a, b, c, d) if (I == a && Ni == b && Nc == c && O == d) return launch_fwd<Cfg<a, b, c, d>>(packed, x, h0, y, h_traj, B, T, layout, stream);
     VB_TC_SHAPES(X)
 #undef X
     set_error("no tensor-core kernel for (%d,%d,%d,%d)", I, Ni, Nc, O);
@@ -884,10 +950,10 @@ int fwd(const float* packed, const float* x, const float* h0, float* y, float* h
 
 int bwd(const float* packed, const float* x, const float* h0, const float* h_traj, const float* dy, const float* dh_traj,
         const float* dh_last, float* dx, float* dh0, float* dpacked, int64_t B, int T, int I, int Ni, int Nc, int O,
-        void* ws, int64_t ws_bytes, cudaStream_t stream) {
+        int layout, void* ws, int64_t ws_bytes, cudaStream_t stream) {
 #define X(a, b, c, d)                                            \
     if (I == a && Ni == b && Nc == c && O == d)                  \
-        return launch_bwd<Cfg<a, b, c, d>>(packed, x, h0, h_traj, dy, dh_traj, dh_last, dx, dh0, dpacked, B, T, ws, ws_bytes, stream);
+        return launch_bwd<Cfg<a, b, c, d>>(packed, x, h0, h_traj, dy, dh_traj, dh_last, dx, dh0, dpacked, B, T, layout, ws, ws_bytes, stream);
     VB_TC_SHAPES(X)
 #undef X
     set_error("no tensor-core kernel for (%d,%d,%d,%d)", I, Ni, Nc, O);

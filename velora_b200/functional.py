@@ -70,10 +70,22 @@ def _f32c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
     return t if t.is_contiguous() else t.contiguous()
 
 
-def _rowmajor(m: torch.Tensor, dev: torch.device) -> torch.Tensor:
-    if m.device != dev:
-        m = m.to(dev)
-    return m if m.is_contiguous() else m.contiguous()
+# vb_liquid_fwd / vb_liquid_bwd layout flags (include/velora_b200.h)
+X_TM, Y_TM, H_TM, DX_TM, DH_TM = 16, 32, 64, 128, 256
+
+
+def _seq(t: Optional[torch.Tensor], tm_ok: bool) -> Tuple[Optional[torch.Tensor], bool]:
+    """fp32 [B,T,F] tensor -> (tensor the kernels can read in place, stored time-major?).  Batch-major contiguous and (where
+    the kernel path accepts it) time-major storage - a permuted view of a contiguous [T,B,F] tensor - pass through."""
+    if t is None:
+        return None, False
+    if t.dtype != torch.float32:
+        t = t.to(torch.float32)
+    if t.is_contiguous():
+        return t, False
+    if tm_ok and t.permute(1, 0, 2).is_contiguous():
+        return t, True
+    return t.contiguous(), False
 
 
 class LiquidSeqFn(torch.autograd.Function):
@@ -86,9 +98,12 @@ class LiquidSeqFn(torch.autograd.Function):
         L = _lib.lib()
         _lib.require_cuda(x, "LiquidNCPNetwork.forward")
         dev = x.device
-        x = _f32c(x)
-        h0c = _f32c(h0)
         B, T, _ = x.shape
+        # time-major storage ([T,B,F], the stack of per-step batches) gives the one-thread-per-sample kernels contiguous
+        # warp accesses; the outputs are allocated that way and returned as [B,T,F] views
+        tm_ok = T > 1 and bool(L.vb_liquid_time_major_ok(I, Ni, Nc, O, flags))
+        x, x_tm = _seq(x, tm_ok)
+        h0c = _f32c(h0)
         params = [_f32c(p.detach()) for p in params]
         w_in, b_in = params[0], params[1]
         w_h = [params[2 + 2 * k] for k in range(5)]
@@ -112,17 +127,23 @@ class LiquidSeqFn(torch.autograd.Function):
                 ),
                 "vb_liquid_pack",
             )
-            y = torch.empty((B, T, O), dtype=torch.float32, device=dev)
-            h_traj = torch.empty((B, T, Nc), dtype=torch.float32, device=dev)
+            if tm_ok:
+                y = torch.empty((T, B, O), dtype=torch.float32, device=dev).permute(1, 0, 2)
+                h_traj = torch.empty((T, B, Nc), dtype=torch.float32, device=dev).permute(1, 0, 2)
+            else:
+                y = torch.empty((B, T, O), dtype=torch.float32, device=dev)
+                h_traj = torch.empty((B, T, Nc), dtype=torch.float32, device=dev)
+            lay = (X_TM if x_tm else 0) | ((Y_TM | H_TM) if tm_ok else 0)
             with _timed("liquid_fwd", 1):
                 _lib.check(
                     L.vb_liquid_fwd(_lib.ptr(packed), _lib.ptr(x), _lib.ptr(h0c), _lib.ptr(y), _lib.ptr(h_traj),
-                                    B, T, I, Ni, Nc, O, None, 0, flags, st),
+                                    B, T, I, Ni, Nc, O, None, 0, flags | lay, st),
                     "vb_liquid_fwd",
                 )
         h_last = h_traj[:, T - 1].clone()
         ctx.dims, ctx.flags, ctx.masks = dims, flags, masks
         ctx.has_h0 = h0 is not None
+        ctx.layout = (tm_ok, x_tm)
         ctx.save_for_backward(x, h0c if h0c is not None else x.new_empty(0), h_traj, packed)
         ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable()
@@ -137,9 +158,11 @@ class LiquidSeqFn(torch.autograd.Function):
         dev = x.device
         B, T, _ = x.shape
         h0p = h0 if ctx.has_h0 else None
-        dy = _f32c(dy) if dy is not None else torch.zeros((B, T, O), dtype=torch.float32, device=dev)
-        dh_traj = _f32c(dh_traj)
+        tm_ok, x_tm = ctx.layout
+        dy, dy_tm = _seq(dy, tm_ok) if dy is not None else (torch.zeros((B, T, O), dtype=torch.float32, device=dev), False)
+        dh_traj, dh_tm = _seq(dh_traj, tm_ok)
         dh_last = _f32c(dh_last)
+        lay = (X_TM | DX_TM if x_tm else 0) | (H_TM if tm_ok else 0) | (Y_TM if dy_tm else 0) | (DH_TM if dh_tm else 0)
         need_x = ctx.needs_input_grad[0]
         need_h0 = ctx.has_h0 and ctx.needs_input_grad[1]
         with torch.cuda.device(dev):
@@ -153,7 +176,7 @@ class LiquidSeqFn(torch.autograd.Function):
                 _lib.check(
                     L.vb_liquid_bwd(_lib.ptr(packed), _lib.ptr(x), _lib.ptr(h0p), _lib.ptr(h_traj), _lib.ptr(dy),
                                     _lib.ptr(dh_traj), _lib.ptr(dh_last), _lib.ptr(dx), _lib.ptr(dh0), _lib.ptr(dpacked),
-                                    B, T, I, Ni, Nc, O, _lib.ptr(ws), ws.numel(), ctx.flags, st),
+                                    B, T, I, Ni, Nc, O, _lib.ptr(ws), ws.numel(), ctx.flags | lay, st),
                     "vb_liquid_bwd",
                 )
             # data-parallel: ONE collective over the flat pre-masked gradient block
