@@ -173,6 +173,46 @@ __device__ __forceinline__ float mish_fwd_grad(float x, float& dmish) {
     return x * t;
 }
 
+// ---- MUFU-lean variants for kernels bound by the XU pipe (16 lanes/clk/SM): several reciprocals share one MUFU.RCP
+// (1/a = b * 1/(ab)).  Operands are clamped where the function is already saturated in fp32 so that the products stay
+// finite: e^18 * e^18 * e^30 < 2^128.
+// tanh(sg), tanh(sh), sigmoid(sf)
+__device__ __forceinline__ void tanh2_sigmoid(float sg, float sh, float sf, float& tg, float& th, float& gate) {
+    float a = ex2_approx(fminf(sg, 9.0f) * (2.0f * kLog2e)) + 1.0f;
+    float b = ex2_approx(fminf(sh, 9.0f) * (2.0f * kLog2e)) + 1.0f;
+    float c = ex2_approx(fminf(-sf, 30.0f) * kLog2e) + 1.0f;
+    float ab = a * b;
+    float r = rcp_approx(ab * c);
+    float rab = c * r;
+    gate = ab * r;
+    tg = fmaf(-2.0f * b, rab, 1.0f);
+    th = fmaf(-2.0f * a, rab, 1.0f);
+}
+// w = n (n + 2), n = e^min(x, 9): tanh(softplus x) = w / (w + 2) equals 1 to fp32 precision beyond x = 9
+__device__ __forceinline__ float mish_w(float x) {
+    float n = ex2_approx(fminf(x, 9.0f) * kLog2e);
+    return n * (n + 2.0f);
+}
+__device__ __forceinline__ void mish2(float x0, float x1, float& y0, float& y1) {
+    float w0 = mish_w(x0), w1 = mish_w(x1);
+    float d0 = w0 + 2.0f, d1 = w1 + 2.0f;
+    float r = rcp_approx(d0 * d1);
+    y0 = x0 * (w0 * (d1 * r));
+    y1 = x1 * (w1 * (d0 * r));
+}
+__device__ __forceinline__ void mish4(const float (&x)[4], float (&y)[4]) {
+    float w[4], d[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { w[i] = mish_w(x[i]); d[i] = w[i] + 2.0f; }
+    float p01 = d[0] * d[1], p23 = d[2] * d[3];
+    float r = rcp_approx(p01 * p23);
+    float r01 = p23 * r, r23 = p01 * r;
+    y[0] = x[0] * (w[0] * (d[1] * r01));
+    y[1] = x[1] * (w[1] * (d[0] * r01));
+    y[2] = x[2] * (w[2] * (d[3] * r23));
+    y[3] = x[3] * (w[3] * (d[2] * r23));
+}
+
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 #endif  // __CUDACC__
 

@@ -287,12 +287,25 @@ __device__ __forceinline__ void store_z(unsigned char* zP, int row, const float 
 template <class C>
 struct FwdSmem {
     static constexpr int Z = 0;                                  // 9 z~ planes + the shared zero plane
-    static constexpr int WB = Z + 10 * PLANE;                    // 3 parts x 4 chunks x 32 rows x 16 B
-    static constexpr int BAR = WB + 3 * 4 * 32 * 16;
+    static constexpr int WB = Z + 10 * PLANE;                    // stacked heads operand: 10 K-chunks x 96 rows x 16 B
+    static constexpr int BAR = WB + 10 * 96 * 16;
     static constexpr int BYTES = BAR + 64;
 };
 
-template <class C>
+// Forward heads in FIVE MMAs: the three bf16 parts of z~ are stacked along K (the 9 part planes + the zero plane are
+// contiguous: K = 80) and the three parts of the weights along N (96 rows), D[128 x 96] = [z1|z2|z3|0] B^T with
+// B[row(pb, n')][pa * 24 + f] = W_pb[n'][f].  Column group pb then holds z W_pb (all nine part products); the epilogue adds
+// the three groups, smallest first.  An M = 128, K = 16 MMA costs ~50 cycles of shared-memory operand fetch whatever its N
+// (A is 4 KB), so 5 wide MMAs replace 12 narrow ones.  Row order: row = (n' / 8) * 24 + pb * 8 + n' % 8, i.e. the three groups
+// of one 8-column chunk (= two neurons) are adjacent TMEM columns.
+__device__ __forceinline__ void issue_heads_stacked(uint32_t d_tmem, uint32_t z_planes, uint32_t w_planes) {
+    constexpr uint32_t idesc = make_idesc(128, 96, 0, 0);
+#pragma unroll
+    for (int ks = 0; ks < 5; ++ks)
+        mma_bf16(d_tmem, make_desc(z_planes + ks * 2 * PLANE, PLANE, 128), make_desc(w_planes + ks * 2 * (96 * 16), 96 * 16, 128), idesc, ks != 0);
+}
+
+template <class C, bool VEC>
 __global__ void __launch_bounds__(TM) liquid_fwd_tc_kernel(const float* __restrict__ packed, const float* __restrict__ x,
                                                            const float* __restrict__ h0, float* __restrict__ y,
                                                            float* __restrict__ h_traj, int64_t B, int T, int vec_flags) {
@@ -303,18 +316,37 @@ __global__ void __launch_bounds__(TM) liquid_fwd_tc_kernel(const float* __restri
     uint64_t* bar1 = reinterpret_cast<uint64_t*>(smem + S::BAR);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::BAR + 16);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const bool vx = vec_flags & 1, vy = vec_flags & 2, vh = vec_flags & 4;
+    // VEC: every row pointer is aligned for its widest vector access (decided on the host); the scalar variant serves odd views
+    constexpr bool vx = VEC, vy = VEC, vh = VEC;
     const RowMap rx(vec_flags & LAY_X, B, T), ry(vec_flags & LAY_Y, B, T), rh(vec_flags & LAY_H, B, T), rdx(vec_flags & LAY_DX, B, T), rdh(vec_flags & LAY_DH, B, T);
 
-    // heads operand: B[n][k] = W_heads[k][n] for k < K, bias for k == ONE
-    // rows in NEURON-MAJOR head order n' = 4 j + hs, so that one 8-column TMEM load holds two complete neurons
-    build_weight_planes(wB, [&](int n, int k) {
+    // stacked heads operand (see issue_heads_stacked); head outputs in NEURON-MAJOR order n' = 4 j + hs, so that one 8-column
+    // chunk holds two complete neurons
+    if (warp < 3) {
+        const int n = lane, c = warp;     // features 8c .. 8c+7 of output n'
         const int col = (n & 3) * C::NCp + (n >> 2);
-        return k < C::K ? __ldg(packed + C::WH_T + k * C::H4 + col) : (k == C::ONE ? __ldg(packed + C::B_H + col) : 0.f);
-    });
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int k = 8 * c + e;
+            v[e] = k < C::K ? __ldg(packed + C::WH_T + k * C::H4 + col) : (k == C::ONE ? __ldg(packed + C::B_H + col) : 0.f);
+        }
+        uint4 part[3];
+        split3(v[0], v[1], part[0].x, part[1].x, part[2].x);
+        split3(v[2], v[3], part[0].y, part[1].y, part[2].y);
+        split3(v[4], v[5], part[0].z, part[1].z, part[2].z);
+        split3(v[6], v[7], part[0].w, part[1].w, part[2].w);
+        uint4* q = reinterpret_cast<uint4*>(wB);
+#pragma unroll
+        for (int pa = 0; pa < 3; ++pa)
+#pragma unroll
+            for (int pb = 0; pb < 3; ++pb) q[(pa * 3 + c) * 96 + (n >> 3) * 24 + pb * 8 + (n & 7)] = part[pb];
+    } else {
+        for (int r = lane; r < 96; r += 32) reinterpret_cast<uint4*>(wB)[9 * 96 + r] = make_uint4(0, 0, 0, 0);
+    }
     reinterpret_cast<uint4*>(zP)[9 * TM + tid] = make_uint4(0, 0, 0, 0);   // the shared zero plane
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 32;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(tmem_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
@@ -351,8 +383,13 @@ __global__ void __launch_bounds__(TM) liquid_fwd_tc_kernel(const float* __restri
             {
                 float u[C::NI];
                 inter_layer<C>(xr, u);
+                static_assert(C::NI % 4 == 0, "inter neurons are activated four at a time");
 #pragma unroll
-                for (int j = 0; j < C::NI; ++j) a[j] = mish_f(u[j]);
+                for (int j = 0; j < C::NI; j += 4) {
+                    float u4[4] = {u[j], u[j + 1], u[j + 2], u[j + 3]}, a4[4];
+                    mish4(u4, a4);
+                    a[j] = a4[0]; a[j + 1] = a4[1]; a[j + 2] = a4[2]; a[j + 3] = a4[3];
+                }
             }
             store_z<C>(zP, tid, a, h);
             fence_async_smem();
@@ -360,7 +397,7 @@ __global__ void __launch_bounds__(TM) liquid_fwd_tc_kernel(const float* __restri
             __syncthreads();
             if (tid == 0) {
                 tc_fence_after();
-                issue_heads(tmem, z_addr, w_addr);
+                issue_heads_stacked(tmem, z_addr, w_addr);
                 mma_commit(bar1);
             }
             mbar_wait(bar1, ph1);
@@ -370,15 +407,24 @@ __global__ void __launch_bounds__(TM) liquid_fwd_tc_kernel(const float* __restri
 #pragma unroll
             for (int c = 0; c < C::NC / 2; ++c) {
                 float s8[8];
-                tmem_ld8(taddr + 8 * c, s8);
+                {
+                    float hi[8], mid[8], lo[8];
+                    tmem_ld8(taddr + 24 * c, hi);
+                    tmem_ld8(taddr + 24 * c + 8, mid);
+                    tmem_ld8(taddr + 24 * c + 16, lo);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) s8[e] = (lo[e] + mid[e]) + hi[e];
+                }
+                float cc[2];
 #pragma unroll
                 for (int jj = 0; jj < 2; ++jj) {
-                    const int j = 2 * c + jj;
-                    float tg = tanh_f(s8[4 * jj + 0]), th = tanh_f(s8[4 * jj + 1]), gate = sigmoid_f(s8[4 * jj + 2]);
+                    float tg, th, gate;
+                    tanh2_sigmoid(s8[4 * jj + 0], s8[4 * jj + 1], s8[4 * jj + 2], tg, th, gate);
                     float hn = fmaf(gate, th - tg, tg);
-                    h[j] = hn;
-                    m[j] = mish_f(s8[4 * jj + 3] + hn);
+                    h[2 * c + jj] = hn;
+                    cc[jj] = s8[4 * jj + 3] + hn;
                 }
+                mish2(cc[0], cc[1], m[2 * c], m[2 * c + 1]);
             }
             float yo[C::O];
 #pragma unroll
@@ -396,7 +442,7 @@ __global__ void __launch_bounds__(TM) liquid_fwd_tc_kernel(const float* __restri
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 32;" ::"r"(tmem) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem) : "memory");
 }
 
 // ================================================================================================ backward
@@ -415,24 +461,32 @@ constexpr int D3_COLS = 96;                 // flush buffer columns per thread (
 constexpr int D3_FLOATS = TM * D3_COLS;     // per-CTA flush buffer
 constexpr int SBUF_STRIDE = 132;            // fp32 transposition buffer row stride (floats): 128 samples + 4 pad
 
-template <class C>
+template <class C, bool VEC>
 __global__ void __launch_bounds__(TM, 4) liquid_bwd_tc_kernel(
     const float* __restrict__ packed, const float* __restrict__ x, const float* __restrict__ h0, const float* __restrict__ h_traj,
     const float* __restrict__ dy, const float* __restrict__ dh_traj, const float* __restrict__ dh_last,
     float* __restrict__ dx, float* __restrict__ dh0, float* __restrict__ partials, float* __restrict__ d3buf,
     int64_t B, int T, int vec_flags, long long* __restrict__ trace) {
     using S = BwdSmem<C>;
+    // phase timing for profiles/microbench/trace_run.py: compiled in only with -DVB_ENABLE_TRACE (VB_TRACE_BUILD=1 build.sh)
+#ifdef VB_ENABLE_TRACE
 #define VB_TRACE(slot) do { if (trace && blockIdx.x == 0 && tid == 0 && T - 1 - t < 40) trace[(T - 1 - t) * 16 + (slot)] = clock64(); } while (0)
 #define VB_MARK(slot) do { if (trace && blockIdx.x == 0 && tid == 0) trace[40 * 16 + (slot)] = clock64(); } while (0)
+#else
+#define VB_TRACE(slot) do { } while (0)
+#define VB_MARK(slot) do { } while (0)
+#endif
     extern __shared__ __align__(1024) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     VB_MARK(0);
+#ifdef VB_ENABLE_TRACE
     if (trace && tid == 0 && blockIdx.x < 1024) {
         unsigned long long gt; unsigned smid;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
         asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
         trace[1024 + blockIdx.x * 4] = (long long)gt; trace[1024 + blockIdx.x * 4 + 2] = smid;
     }
+#endif
     unsigned char* zP = smem + S::Z;
     unsigned char* dsP = smem + S::DS;
     unsigned char* wB = smem + S::WB;
@@ -442,7 +496,8 @@ __global__ void __launch_bounds__(TM, 4) liquid_bwd_tc_kernel(
     uint64_t* bar2 = bar1 + 1;                                     // dz ready
     uint64_t* bar3 = bar1 + 2;                                     // dW batch done (z~ and ds planes may be overwritten)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::BAR + 32);
-    const bool vx = vec_flags & 1, vy = vec_flags & 2, vh = vec_flags & 4;
+    // VEC: every row pointer is aligned for its widest vector access (decided on the host); the scalar variant serves odd views
+    constexpr bool vx = VEC, vy = VEC, vh = VEC;
     const RowMap rx(vec_flags & LAY_X, B, T), ry(vec_flags & LAY_Y, B, T), rh(vec_flags & LAY_H, B, T), rdx(vec_flags & LAY_DX, B, T), rdh(vec_flags & LAY_DH, B, T);
 
     // heads operand B[n][k]: W_heads[k][n] for k < K, bias for k == ONE, zero elsewhere
@@ -458,9 +513,11 @@ __global__ void __launch_bounds__(TM, 4) liquid_bwd_tc_kernel(
         for (int i = tid; i < (S::BYTES - S::DS) / 16; i += TM)
             if (i < 12 * TM || i >= (S::TAIL - S::DS + 15) / 16) q[i] = z4;
     }
-    float* d3row = d3buf + (int64_t)blockIdx.x * D3_FLOATS + tid * D3_COLS;   // this thread's (stack) row of the dW accumulator
+    // fp32 flush buffer of the dW accumulator: element (stack row = thread, column c) at ((c / 4) * TM + row) * 4 + c % 4, so that the
+    // 32 lanes of one vector access touch 512 contiguous bytes
+    float* d3row = d3buf + (int64_t)blockIdx.x * D3_FLOATS + tid * 4;
 #pragma unroll
-    for (int q = 0; q < D3_COLS / 4; ++q) reinterpret_cast<float4*>(d3row)[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = 0; q < D3_COLS / 4; ++q) *reinterpret_cast<float4*>(d3row + q * (TM * 4)) = make_float4(0.f, 0.f, 0.f, 0.f);
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(tmem_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -500,6 +557,42 @@ __global__ void __launch_bounds__(TM, 4) liquid_bwd_tc_kernel(
     const float* duA = rowsA + (R_DU + JA * blkA) * SBUF_STRIDE;
     const float* mB = mstrip + (JB * blkB) * TM + 4 * sgB;
 
+    // Reduction of the rows parked in sbuf / mstrip by the previous step (see the step tail).  It only needs shared memory, so it
+    // runs while the tensor core works on the next step's heads, before the gating pass overwrites the ds planes.
+    bool pending = false;
+    auto reduce_small = [&]() {
+        if (warp < 2) {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                float4 xv[C::I], dv[JA];
+#pragma unroll
+                for (int i = 0; i < C::I; ++i) xv[i] = *reinterpret_cast<const float4*>(rowsA + (R_X + i) * SBUF_STRIDE + 64 * half);
+#pragma unroll
+                for (int r = 0; r < JA; ++r) dv[r] = *reinterpret_cast<const float4*>(duA + r * SBUF_STRIDE + 64 * half);
+#pragma unroll
+                for (int r = 0; r < JA; ++r) {
+#pragma unroll
+                    for (int i = 0; i < C::I; ++i)
+                        acc[i * JA + r] = fmaf(xv[i].x, dv[r].x, fmaf(xv[i].y, dv[r].y, fmaf(xv[i].z, dv[r].z, fmaf(xv[i].w, dv[r].w, acc[i * JA + r]))));
+                    acc[C::I * JA + r] += (dv[r].x + dv[r].y) + (dv[r].z + dv[r].w);
+                }
+            }
+        } else {
+            float4 yv[C::O], mv[JB];
+#pragma unroll
+            for (int o = 0; o < C::O; ++o) yv[o] = *reinterpret_cast<const float4*>(rowsB + (R_DY + o) * SBUF_STRIDE);
+#pragma unroll
+            for (int r = 0; r < JB; ++r) mv[r] = *reinterpret_cast<const float4*>(mB + r * TM);
+#pragma unroll
+            for (int o = 0; o < C::O; ++o) {
+#pragma unroll
+                for (int r = 0; r < JB; ++r)
+                    acc[o * JB + r] = fmaf(yv[o].x, mv[r].x, fmaf(yv[o].y, mv[r].y, fmaf(yv[o].z, mv[r].z, fmaf(yv[o].w, mv[r].w, acc[o * JB + r]))));
+                acc[C::O * JB + o] += (yv[o].x + yv[o].y) + (yv[o].z + yv[o].w);
+            }
+        }
+    };
+
     auto flush_dw = [&]() {   // all threads; requires the dW batch to be complete
         tc_fence_after();
 #pragma unroll
@@ -509,7 +602,7 @@ __global__ void __launch_bounds__(TM, 4) liquid_bwd_tc_kernel(
             // fire-and-forget vector reductions into this thread's private row: no load, nothing to wait for
 #pragma unroll
             for (int q = 0; q < 8; ++q)
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d3row + 32 * g + 4 * q), "f"(v[4 * q]), "f"(v[4 * q + 1]),
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d3row + (8 * g + q) * (TM * 4)), "f"(v[4 * q]), "f"(v[4 * q + 1]),
                              "f"(v[4 * q + 2]), "f"(v[4 * q + 3]) : "memory");
         }
         since_flush = 0;
@@ -566,12 +659,16 @@ __global__ void __launch_bounds__(TM, 4) liquid_bwd_tc_kernel(
             tc_fence_before();
             __syncthreads();                    // also: everybody is done reading the fp32 buffer of the previous step
             VB_TRACE(2);
-            if (tid == 0) {
+            if (tid == 96) {                  // a lane of the lighter (dW_out) reduction warps issues
                 tc_fence_after();
                 issue_heads(tmem + 0, z_addr, wb_addr);
                 mma_commit(bar1);
             }
             VB_TRACE(3);
+            if (pending) {
+                reduce_small();
+                __syncthreads();              // everybody has read sbuf / mstrip: the gating pass may overwrite them
+            }
             mbar_wait(bar1, ph);
             tc_fence_after();
             VB_TRACE(4);
@@ -676,40 +773,14 @@ __global__ void __launch_bounds__(TM, 4) liquid_bwd_tc_kernel(
             for (int i = 0; i < C::I; ++i) sbuf[(R_X + i) * SBUF_STRIDE + tid] = xr[i];
 #pragma unroll
             for (int o = 0; o < C::O; ++o) sbuf[(R_DY + o) * SBUF_STRIDE + tid] = dyr[o];
-            __syncthreads();
-            if (warp < 2) {
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    float4 xv[C::I], dv[JA];
-#pragma unroll
-                    for (int i = 0; i < C::I; ++i) xv[i] = *reinterpret_cast<const float4*>(rowsA + (R_X + i) * SBUF_STRIDE + 64 * half);
-#pragma unroll
-                    for (int r = 0; r < JA; ++r) dv[r] = *reinterpret_cast<const float4*>(duA + r * SBUF_STRIDE + 64 * half);
-#pragma unroll
-                    for (int r = 0; r < JA; ++r) {
-#pragma unroll
-                        for (int i = 0; i < C::I; ++i)
-                            acc[i * JA + r] = fmaf(xv[i].x, dv[r].x, fmaf(xv[i].y, dv[r].y, fmaf(xv[i].z, dv[r].z, fmaf(xv[i].w, dv[r].w, acc[i * JA + r]))));
-                        acc[C::I * JA + r] += (dv[r].x + dv[r].y) + (dv[r].z + dv[r].w);
-                    }
-                }
-            } else {
-                float4 yv[C::O], mv[JB];
-#pragma unroll
-                for (int o = 0; o < C::O; ++o) yv[o] = *reinterpret_cast<const float4*>(rowsB + (R_DY + o) * SBUF_STRIDE);
-#pragma unroll
-                for (int r = 0; r < JB; ++r) mv[r] = *reinterpret_cast<const float4*>(mB + r * TM);
-#pragma unroll
-                for (int o = 0; o < C::O; ++o) {
-#pragma unroll
-                    for (int r = 0; r < JB; ++r)
-                        acc[o * JB + r] = fmaf(yv[o].x, mv[r].x, fmaf(yv[o].y, mv[r].y, fmaf(yv[o].z, mv[r].z, fmaf(yv[o].w, mv[r].w, acc[o * JB + r]))));
-                    acc[C::O * JB + o] += (yv[o].x + yv[o].y) + (yv[o].z + yv[o].w);
-                }
-            }
+            pending = true;      // reduced in the shadow of the next step's heads MMAs (or after the loop)
             VB_TRACE(11);
         }
         if (valid && dh0) stg_row<C::NC>(dh0 + b * C::NC, dhc, vh);
+    }
+    if (pending) {
+        __syncthreads();
+        reduce_small();
     }
     VB_MARK(2);
     if (since_flush > 0) flush_dw();
@@ -756,7 +827,7 @@ __global__ void __launch_bounds__(TM, 4) liquid_bwd_tc_kernel(
 #pragma unroll
                 for (int pa = 0; pa < 3; ++pa)
 #pragma unroll
-                    for (int pb = 2; pb >= 0; --pb) acc += d3[(pa * 32 + r) * D3_COLS + pb * 24 + i];
+                    for (int pb = 2; pb >= 0; --pb) acc += d3[(((pb * 24 + i) >> 2) * TM + pa * 32 + r) * 4 + ((pb * 24 + i) & 3)];
                 if (i < C::K) prow[C::WH_T + i * C::H4 + col] = acc;
                 else prow[C::B_H + col] = acc;
             }
@@ -775,11 +846,15 @@ __global__ void __launch_bounds__(TM, 4) liquid_bwd_tc_kernel(
         }
     }
     VB_MARK(3);
+#ifdef VB_ENABLE_TRACE
     if (trace && tid == 0 && blockIdx.x < 1024) {
         unsigned long long gt;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
         trace[1024 + blockIdx.x * 4 + 1] = (long long)gt;
     }
+#else
+    (void)trace;
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -844,24 +919,25 @@ static int launch_fwd(const float* packed, const float* x, const float* h0, floa
     bool capturing;
     int rc = upload_constants(packed, C::C_TOTAL, stream, &dev, &capturing);
     if (rc) return rc;
+    int vf = vec_flags_for(x, y, h0, h_traj, nullptr, nullptr, nullptr, nullptr, T, C::I, C::O, C::NC) | layout;
+    auto kern = (vf & 7) == 7 ? liquid_fwd_tc_kernel<C, true> : liquid_fwd_tc_kernel<C, false>;
     int per_sm = 1;
-    rc = grid_cap(liquid_fwd_tc_kernel<C>, FwdSmem<C>::BYTES, 32, &per_sm);
+    rc = grid_cap(kern, FwdSmem<C>::BYTES, 128, &per_sm);
     if (rc) return rc;
     int64_t n_tiles = (B + TM - 1) / TM;
     int64_t cap = (int64_t)device_sms() * per_sm;
     int grid = (int)(n_tiles < cap ? n_tiles : cap);
     if (grid < 1) grid = 1;
-    int vf = vec_flags_for(x, y, h0, h_traj, nullptr, nullptr, nullptr, nullptr, T, C::I, C::O, C::NC) | layout;
-    liquid_fwd_tc_kernel<C><<<grid, TM, FwdSmem<C>::BYTES, stream>>>(packed, x, h0, y, h_traj, B, T, vf);
+    kern<<<grid, TM, FwdSmem<C>::BYTES, stream>>>(packed, x, h0, y, h_traj, B, T, vf);
     VB_LAUNCH_CHECK();
     if (!capturing) VB_CUDA(cudaEventRecord(g_ev[dev & 63], stream));
     return 0;
 }
 
-template <class C>
-static int bwd_grid(int64_t B, int* grid_out) {
+template <class C, class K>
+static int bwd_grid(K kern, int64_t B, int* grid_out) {
     int per_sm = 1;
-    int rc = grid_cap(liquid_bwd_tc_kernel<C>, BwdSmem<C>::BYTES, 128, &per_sm);
+    int rc = grid_cap(kern, BwdSmem<C>::BYTES, 128, &per_sm);
     if (rc) return rc;
     int64_t n_tiles = (B + TM - 1) / TM;
     int64_t cap = (int64_t)device_sms() * per_sm;
@@ -874,8 +950,10 @@ template <class C>
 static int launch_bwd(const float* packed, const float* x, const float* h0, const float* h_traj, const float* dy,
                       const float* dh_traj, const float* dh_last, float* dx, float* dh0, float* dpacked,
                       int64_t B, int T, int layout, void* ws, int64_t ws_bytes, cudaStream_t stream) {
+    int vf = vec_flags_for(x, dy, h0, h_traj, dh_traj, dh_last, dx, dh0, T, C::I, C::O, C::NC) | layout;
+    auto kern = (vf & 7) == 7 ? liquid_bwd_tc_kernel<C, true> : liquid_bwd_tc_kernel<C, false>;
     int grid = 1;
-    int rc = bwd_grid<C>(B, &grid);
+    int rc = bwd_grid<C>(kern, B, &grid);
     if (rc) return rc;
     const int64_t need = (int64_t)grid * (C::F_TOTAL + D3_FLOATS) * (int64_t)sizeof(float);
     VB_CHECK_ARG(ws && ws_bytes >= need, VB_ERR_WORKSPACE, "vb_liquid_bwd: workspace too small (%lld bytes, need %lld)",
@@ -885,13 +963,13 @@ static int launch_bwd(const float* packed, const float* x, const float* h0, cons
     bool capturing;
     rc = upload_constants(packed, C::C_TOTAL, stream, &dev, &capturing);
     if (rc) return rc;
-    int vf = vec_flags_for(x, dy, h0, h_traj, dh_traj, dh_last, dx, dh0, T, C::I, C::O, C::NC) | layout;
     float* partials = reinterpret_cast<float*>(ws);
     float* d3buf = partials + (int64_t)grid * C::F_TOTAL;
     long long* trace = nullptr;
+#ifdef VB_ENABLE_TRACE
     if (getenv("VB_TRACE")) { cudaMalloc(&trace, (1024 + 4096) * sizeof(long long)); cudaMemset(trace, 0, (1024 + 4096) * sizeof(long long)); }
-    liquid_bwd_tc_kernel<C><<<grid, TM, BwdSmem<C>::BYTES, stream>>>(packed, x, h0, h_traj, dy, dh_traj, dh_last, dx, dh0, partials,
-                                                                     d3buf, B, T, vf, trace);
+#endif
+    kern<<<grid, TM, BwdSmem<C>::BYTES, stream>>>(packed, x, h0, h_traj, dy, dh_traj, dh_last, dx, dh0, partials, d3buf, B, T, vf, trace);
     VB_LAUNCH_CHECK();
     if (trace) {
         long long h[64 * 16];
