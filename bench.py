@@ -431,7 +431,16 @@ def run_ours(args) -> None:
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # captured graphs hold NCCL work: drop them before the communicator, and do not let interpreter teardown order
+        # (graphs / communicator / sampler thread) decide whether the process exits
+        graphs = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main() -> None:

@@ -37,9 +37,26 @@ namespace tc {
 
 // Row index of (sample b, step t) in a [B,T,F] tensor stored batch-major (row b*T + t) or time-major (row t*B + b).
 // One thread owns one sample, so time-major storage makes every warp access one contiguous run of 32 rows.
-struct RowMap {
+// MODE 0: every sequence tensor batch-major, 1: every one time-major (strides come straight from the kernel parameters, no
+// registers), 2: per-tensor at run time.
+template <int MODE>
+struct RowMap;
+template <>
+struct RowMap<0> {
+    int T;
+    __device__ __forceinline__ RowMap(bool, int64_t, int T_) : T(T_) {}
+    __device__ __forceinline__ int64_t operator()(int64_t b, int t) const { return b * T + t; }
+};
+template <>
+struct RowMap<1> {
+    int64_t B;
+    __device__ __forceinline__ RowMap(bool, int64_t B_, int) : B(B_) {}
+    __device__ __forceinline__ int64_t operator()(int64_t b, int t) const { return (int64_t)t * B + b; }
+};
+template <>
+struct RowMap<2> {
     int64_t sb, st;
-    __host__ __device__ RowMap(bool time_major, int64_t B, int T) : sb(time_major ? 1 : T), st(time_major ? B : 1) {}
+    __device__ __forceinline__ RowMap(bool time_major, int64_t B, int T) : sb(time_major ? 1 : T), st(time_major ? B : 1) {}
     __device__ __forceinline__ int64_t operator()(int64_t b, int t) const { return b * sb + (int64_t)t * st; }
 };
 constexpr int LAY_X = 16, LAY_Y = 32, LAY_H = 64, LAY_DX = 128, LAY_DH = 256;   // = VB_FLAG_*_TIME_MAJOR
@@ -155,6 +172,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+                   "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+                   "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+                   "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])) : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
 // x0, x1 -> three packed bf16x2 words (low half = x0): x = p1 + p2 + p3 to 24 bits
@@ -305,7 +331,7 @@ __device__ __forceinline__ void issue_heads_stacked(uint32_t d_tmem, uint32_t z_
         mma_bf16(d_tmem, make_desc(z_planes + ks * 2 * PLANE, PLANE, 128), make_desc(w_planes + ks * 2 * (96 * 16), 96 * 16, 128), idesc, ks != 0);
 }
 
-template <class C, bool VEC>
+template <class C, bool VEC, int LAY>
 __global__ void __launch_bounds__(TM) liquid_fwd_tc_kernel(const float* __restrict__ packed, const float* __restrict__ x,
                                                            const float* __restrict__ h0, float* __restrict__ y,
                                                            float* __restrict__ h_traj, int64_t B, int T, int vec_flags) {
@@ -318,7 +344,8 @@ __global__ void __launch_bounds__(TM) liquid_fwd_tc_kernel(const float* __restri
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // VEC: every row pointer is aligned for its widest vector access (decided on the host); the scalar variant serves odd views
     constexpr bool vx = VEC, vy = VEC, vh = VEC;
-    const RowMap rx(vec_flags & LAY_X, B, T), ry(vec_flags & LAY_Y, B, T), rh(vec_flags & LAY_H, B, T), rdx(vec_flags & LAY_DX, B, T), rdh(vec_flags & LAY_DH, B, T);
+    const RowMap<LAY> rx(vec_flags & LAY_X, B, T), ry(vec_flags & LAY_Y, B, T), rh(vec_flags & LAY_H, B, T), rdx(vec_flags & LAY_DX, B, T),
+        rdh(vec_flags & LAY_DH, B, T);
 
     // stacked heads operand (see issue_heads_stacked); head outputs in NEURON-MAJOR order n' = 4 j + hs, so that one 8-column
     // chunk holds two complete neurons
@@ -461,7 +488,7 @@ constexpr int D3_COLS = 96;                 // flush buffer columns per thread (
 constexpr int D3_FLOATS = TM * D3_COLS;     // per-CTA flush buffer
 constexpr int SBUF_STRIDE = 132;            // fp32 transposition buffer row stride (floats): 128 samples + 4 pad
 
-template <class C, bool VEC>
+template <class C, bool VEC, int LAY>
 __global__ void __launch_bounds__(TM, 4) liquid_bwd_tc_kernel(
     const float* __restrict__ packed, const float* __restrict__ x, const float* __restrict__ h0, const float* __restrict__ h_traj,
     const float* __restrict__ dy, const float* __restrict__ dh_traj, const float* __restrict__ dh_last,
@@ -498,7 +525,8 @@ __global__ void __launch_bounds__(TM, 4) liquid_bwd_tc_kernel(
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::BAR + 32);
     // VEC: every row pointer is aligned for its widest vector access (decided on the host); the scalar variant serves odd views
     constexpr bool vx = VEC, vy = VEC, vh = VEC;
-    const RowMap rx(vec_flags & LAY_X, B, T), ry(vec_flags & LAY_Y, B, T), rh(vec_flags & LAY_H, B, T), rdx(vec_flags & LAY_DX, B, T), rdh(vec_flags & LAY_DH, B, T);
+    const RowMap<LAY> rx(vec_flags & LAY_X, B, T), ry(vec_flags & LAY_Y, B, T), rh(vec_flags & LAY_H, B, T), rdx(vec_flags & LAY_DX, B, T),
+        rdh(vec_flags & LAY_DH, B, T);
 
     // heads operand B[n][k]: W_heads[k][n] for k < K, bias for k == ONE, zero elsewhere
     // rows in NEURON-MAJOR head order n' = 4 j + hs, so that one 8-column TMEM load holds two complete neurons
@@ -646,12 +674,17 @@ __global__ void __launch_bounds__(TM, 4) liquid_bwd_tc_kernel(
             }
             VB_TRACE(0);
             // ---------------- recompute: inter layer on CUDA cores, heads on the tensor cores
-            float dmu[C::NI];
             {
-                float a[C::NI], u[C::NI];
+                float a[C::NI], u[C::NI], park[16];
                 inter_layer<C>(xr, u);
 #pragma unroll
-                for (int j = 0; j < C::NI; ++j) a[j] = mish_fwd_grad(u[j], dmu[j]);
+                for (int j = 0; j < C::NI; ++j) a[j] = mish_fwd_grad(u[j], park[j]);
+                // Mish'(u) and x_t are next needed after the dz MMA: they wait in this thread's TMEM lane (the 16 columns the
+                // accumulators leave free) instead of holding 16 registers through the gating pass
+                static_assert(C::NI + C::I <= 16, "parking area is 16 TMEM columns");
+#pragma unroll
+                for (int i = 0; i < 16 - C::NI; ++i) park[C::NI + i] = i < C::I ? xr[i < C::I ? i : 0] : 0.f;
+                tmem_st16(taddr + 112, park);
                 store_z<C>(zP, tid, a, hp);     // the previous dW batch was waited for at the end of the previous step
             }
             VB_TRACE(1);
@@ -734,8 +767,12 @@ __global__ void __launch_bounds__(TM, 4) liquid_bwd_tc_kernel(
             mbar_wait(bar2, ph);
             tc_fence_after();
             VB_TRACE(8);
-            float du[C::NI];
+            float du[C::NI], xr2[C::I];
             {
+                float dmu[16];
+                tmem_ld16(taddr + 112, dmu);
+#pragma unroll
+                for (int i = 0; i < C::I; ++i) xr2[i] = dmu[C::NI + i];
                 float dz[16];
                 tmem_ld16(taddr + 0, dz);
 #pragma unroll
@@ -770,7 +807,7 @@ __global__ void __launch_bounds__(TM, 4) liquid_bwd_tc_kernel(
 #pragma unroll
             for (int j = 0; j < C::NI; ++j) sbuf[(R_DU + j) * SBUF_STRIDE + tid] = du[j];
 #pragma unroll
-            for (int i = 0; i < C::I; ++i) sbuf[(R_X + i) * SBUF_STRIDE + tid] = xr[i];
+            for (int i = 0; i < C::I; ++i) sbuf[(R_X + i) * SBUF_STRIDE + tid] = xr2[i];
 #pragma unroll
             for (int o = 0; o < C::O; ++o) sbuf[(R_DY + o) * SBUF_STRIDE + tid] = dyr[o];
             pending = true;      // reduced in the shadow of the next step's heads MMAs (or after the loop)
@@ -920,7 +957,11 @@ static int launch_fwd(const float* packed, const float* x, const float* h0, floa
     int rc = upload_constants(packed, C::C_TOTAL, stream, &dev, &capturing);
     if (rc) return rc;
     int vf = vec_flags_for(x, y, h0, h_traj, nullptr, nullptr, nullptr, nullptr, T, C::I, C::O, C::NC) | layout;
-    auto kern = (vf & 7) == 7 ? liquid_fwd_tc_kernel<C, true> : liquid_fwd_tc_kernel<C, false>;
+    // fast variants: aligned rows and one storage order for every sequence tensor; anything else takes the generic variant
+    const int all = LAY_X | LAY_Y | LAY_H;
+    const bool vec = (vf & 7) == 7;
+    auto kern = (vec && (layout & all) == all) ? liquid_fwd_tc_kernel<C, true, 1>
+              : (vec && (layout & all) == 0)   ? liquid_fwd_tc_kernel<C, true, 0> : liquid_fwd_tc_kernel<C, false, 2>;
     int per_sm = 1;
     rc = grid_cap(kern, FwdSmem<C>::BYTES, 128, &per_sm);
     if (rc) return rc;
@@ -951,7 +992,10 @@ static int launch_bwd(const float* packed, const float* x, const float* h0, cons
                       const float* dh_traj, const float* dh_last, float* dx, float* dh0, float* dpacked,
                       int64_t B, int T, int layout, void* ws, int64_t ws_bytes, cudaStream_t stream) {
     int vf = vec_flags_for(x, dy, h0, h_traj, dh_traj, dh_last, dx, dh0, T, C::I, C::O, C::NC) | layout;
-    auto kern = (vf & 7) == 7 ? liquid_bwd_tc_kernel<C, true> : liquid_bwd_tc_kernel<C, false>;
+    const int all = LAY_X | LAY_Y | LAY_H | (dx ? LAY_DX : 0) | (dh_traj ? LAY_DH : 0);
+    const bool vec = (vf & 7) == 7;
+    auto kern = (vec && (layout & all) == all) ? liquid_bwd_tc_kernel<C, true, 1>
+              : (vec && (layout & all) == 0)   ? liquid_bwd_tc_kernel<C, true, 0> : liquid_bwd_tc_kernel<C, false, 2>;
     int grid = 1;
     int rc = bwd_grid<C>(kern, B, &grid);
     if (rc) return rc;
