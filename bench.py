@@ -245,12 +245,19 @@ def run_ours(args) -> None:
         torch.cuda.current_stream(dev).wait_stream(side)
         barrier()
         graphs, pool = [], None
-        for i in range(R):
-            gr = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(gr, pool=pool):
-                step(i)
-            pool = gr.pool()
-            graphs.append(gr)
+        try:
+            for i in range(R):
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr, pool=pool):
+                    step(i)
+                pool = gr.pool()
+                graphs.append(gr)
+        except Exception as e:       # a failed capture must not cost the measurement: time the eager loop instead
+            if world > 1:
+                raise                # ranks must not diverge; rerun with --no-graph
+            print(f"[bench] CUDA graph capture failed ({e!r}); timing the eager loop", file=sys.stderr)
+            graphs = None
+            torch.cuda.synchronize()
 
     def timed_step(i: int) -> None:
         if graphs is None:
