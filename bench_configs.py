@@ -140,6 +140,12 @@ def main():
              torch_six_index_kernels_ms=ref_ms)
         tms = gpu_time_ms(lambda: big._train_step(B), warmup=3, iters=10)
         emit(config=f"cfg5 sample + NeuroFlowCT update, batch {B}, 1 GPU", metric="transitions_per_s", value=B / (tms * 1e-3), ms=tms)
+        bigg = make_agent(dev, 1_000_000, capturable=True)
+        replay_big = bigg.capture_train_step(B)
+        gms2 = gpu_time_ms(replay_big, warmup=3, iters=20)
+        emit(config=f"cfg5 sample + NeuroFlowCT update captured in one CUDA graph, batch {B}, 1 GPU", metric="transitions_per_s",
+             value=B / (gms2 * 1e-3), ms=gms2)
+        del bigg, replay_big
     if not args.no_cpu:
         B = 131072
         o = cpu_train_oracle(big)

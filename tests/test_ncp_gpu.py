@@ -44,7 +44,7 @@ def test_ncp_vs_reference(golden, name):
         net(torch.zeros(2, 2, 2))
 
 
-@pytest.mark.parametrize("B", [1, 33, 1000, 65536])
+@pytest.mark.parametrize("B", [1, 33, 1000, 10001, 20003, 65536])   # 10001 / 20003: the 64- and 128-row register-blocked tiles, ragged
 def test_ncp_ragged_vs_oracle(golden, B):
     d = golden("ncp")
     net = _build(d, "critic_ct")

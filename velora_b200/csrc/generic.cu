@@ -25,12 +25,20 @@ struct Plan {
     int rows;
 };
 
-static Plan make_plan(int rows, int packed_floats, int grad_floats, bool backward) {
+// big_B > 0: the caller also compiled the register-blocked 128 / 64-row tiles; they are used when the batch fills the GPU with
+// them and the activations (plus, backward, the shared-memory gradient accumulator) still fit.
+static Plan make_plan(int rows, int packed_floats, int grad_floats, bool backward, int64_t big_B = 0) {
     Plan p{0, false, false, 0, rows};
     const int budget = device_max_smem_optin() > 0 ? device_max_smem_optin() : 232448;
     const int fixed = 64;   // mbarrier + alignment slack
-    for (int bm : {32, 16, 8}) {
+    const int sms = device_sms() > 0 ? device_sms() : 148;
+    for (int bm : {128, 64, 32, 16, 8}) {
         int act = rows * (bm + 4) * 4;
+        if (bm > 32) {   // only while two CTAs (16 warps) still fit per SM: the phases of a tile are separated by CTA barriers
+            if (big_B < (int64_t)bm * sms) continue;
+            const int g = (backward && grad_floats <= kModeAMaxFloats) ? grad_floats * 4 : 0;
+            if (act + fixed + g > budget / 2) continue;
+        }
         if (act + fixed <= budget) { p.BM = bm; p.smem_bytes = act + fixed; break; }
     }
     if (!p.BM) return p;
@@ -420,14 +428,14 @@ int liquid_bwd(const float* packed, const float* x, const float* h0, const float
 
 int ncp_fwd(const float* packed, const float* x, float* y, int64_t B, int I, int Ni, int Nc, int O, cudaStream_t stream) {
     NcpLayout L(I, Ni, Nc, O);
-    Plan p = make_plan(ncp_fwd_rows(L), L.total, 0, false);
+    Plan p = make_plan(ncp_fwd_rows(L), L.total, 0, false, B);
     VB_CHECK_ARG(p.BM, VB_ERR_TOO_LARGE, "ncp forward: activations of (%d,%d,%d,%d) do not fit shared memory", I, Ni, Nc, O);
     int grid = 1, rc = 0;
 #define LAUNCH(BM_)                                                                                  \
     rc = grid_for(ncp_fwd_kernel<BM_>, p.smem_bytes, (B + BM_ - 1) / BM_, 0, &grid);                 \
     if (rc) return rc;                                                                               \
     ncp_fwd_kernel<BM_><<<grid, kTileThreads, p.smem_bytes, stream>>>(packed, L, x, y, B, p.stage_w);
-    if (p.BM == 32) { LAUNCH(32) } else if (p.BM == 16) { LAUNCH(16) } else { LAUNCH(8) }
+    if (p.BM == 128) { LAUNCH(128) } else if (p.BM == 64) { LAUNCH(64) } else if (p.BM == 32) { LAUNCH(32) } else if (p.BM == 16) { LAUNCH(16) } else { LAUNCH(8) }
 #undef LAUNCH
     VB_LAUNCH_CHECK();
     return 0;
@@ -444,7 +452,7 @@ int64_t ncp_bwd_workspace_bytes(int I, int Ni, int Nc, int O) {
 int ncp_bwd(const float* packed, const float* x, const float* dy, float* dx, float* dpacked, int64_t B,
             int I, int Ni, int Nc, int O, void* ws, int64_t ws_bytes, cudaStream_t stream) {
     NcpLayout L(I, Ni, Nc, O);
-    Plan p = make_plan(ncp_bwd_rows(L), L.total, L.f_total, true);
+    Plan p = make_plan(ncp_bwd_rows(L), L.total, L.f_total, true, B);
     VB_CHECK_ARG(p.BM, VB_ERR_TOO_LARGE, "ncp backward: activations of (%d,%d,%d,%d) do not fit shared memory", I, Ni, Nc, O);
     int grid = 1, rc = 0;
     if (p.smem_acc) {
@@ -453,7 +461,7 @@ int ncp_bwd(const float* packed, const float* x, const float* dy, float* dx, flo
     rc = grid_for(ncp_bwd_kernel<BM_, false>, p.smem_bytes, (B + BM_ - 1) / BM_, 2, &grid);                    \
     if (rc) return rc;                                                                                        \
     ncp_bwd_kernel<BM_, false><<<grid, kTileThreads, p.smem_bytes, stream>>>(packed, L, x, dy, dx, reinterpret_cast<float*>(ws), B, p.stage_w);
-        if (p.BM == 32) { LAUNCH(32) } else if (p.BM == 16) { LAUNCH(16) } else { LAUNCH(8) }
+        if (p.BM == 128) { LAUNCH(128) } else if (p.BM == 64) { LAUNCH(64) } else if (p.BM == 32) { LAUNCH(32) } else if (p.BM == 16) { LAUNCH(16) } else { LAUNCH(8) }
 #undef LAUNCH
         VB_LAUNCH_CHECK();
         reduce_rows_kernel<<<(L.f_total + 31) / 32, 1024, 0, stream>>>(reinterpret_cast<float*>(ws), grid, L.f_total, dpacked);
@@ -464,7 +472,7 @@ int ncp_bwd(const float* packed, const float* x, const float* dy, float* dx, flo
     rc = grid_for(ncp_bwd_kernel<BM_, true>, p.smem_bytes, (B + BM_ - 1) / BM_, 0, &grid);                     \
     if (rc) return rc;                                                                                        \
     ncp_bwd_kernel<BM_, true><<<grid, kTileThreads, p.smem_bytes, stream>>>(packed, L, x, dy, dx, dpacked, B, p.stage_w);
-        if (p.BM == 32) { LAUNCH(32) } else if (p.BM == 16) { LAUNCH(16) } else { LAUNCH(8) }
+        if (p.BM == 128) { LAUNCH(128) } else if (p.BM == 64) { LAUNCH(64) } else if (p.BM == 32) { LAUNCH(32) } else if (p.BM == 16) { LAUNCH(16) } else { LAUNCH(8) }
 #undef LAUNCH
         VB_LAUNCH_CHECK();
     }

@@ -16,16 +16,58 @@ constexpr int kTileThreads = 256;
 template <int BM>
 struct Geo {
     static constexpr int S = BM + 4;                 // row stride in floats
-    static constexpr int G = kTileThreads / BM;      // output groups
+    static constexpr int RS = BM >= 64 ? 4 : 1;      // samples per thread in dense(): big tiles are register-blocked 4 x 8
+    static constexpr int LN = BM / RS;               // threads along the sample axis
+    static constexpr int G = kTileThreads / LN;      // output groups
 };
 
 // out[j][s] = epi(bias[j] + sum_i Wt[i][j] * in[i][s]),  j < n_out (Wt rows are ldw floats, ldw % 4 == 0, zero padded)
 template <int BM, class Epi>
 __device__ __forceinline__ void dense(const float* __restrict__ in, int n_in, const float* __restrict__ Wt, int ldw,
                                       const float* __restrict__ bias, int n_out, Epi epi) {
-    constexpr int S = Geo<BM>::S, G = Geo<BM>::G;
-    const int s = threadIdx.x % BM, g = threadIdx.x / BM;
+    constexpr int S = Geo<BM>::S, G = Geo<BM>::G, RS = Geo<BM>::RS, LN = Geo<BM>::LN;
+    const int sl = threadIdx.x % LN, g = threadIdx.x / LN;
     const int n_blk = (n_out + 3) >> 2;
+    if constexpr (RS == 4) {
+        // 4 samples x 8 outputs per thread: one 128-bit activation read + two warp-uniform 128-bit weight reads feed 32 FMAs
+        // (the 1 x 8 variant below issues 3 shared-memory reads per 8 FMAs and is bound by the LSU, not the FMA pipe)
+        const float* ip = in + 4 * sl;
+        for (int jb = 2 * g; jb < n_blk; jb += 2 * G) {
+            const bool two = (jb + 1) < n_blk;
+            const float4 b0 = bias ? *reinterpret_cast<const float4*>(bias + 4 * jb) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 b1 = (bias && two) ? *reinterpret_cast<const float4*>(bias + 4 * jb + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float acc[4][8];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                acc[r][0] = b0.x; acc[r][1] = b0.y; acc[r][2] = b0.z; acc[r][3] = b0.w;
+                acc[r][4] = b1.x; acc[r][5] = b1.y; acc[r][6] = b1.z; acc[r][7] = b1.w;
+            }
+            const float* w = Wt + 4 * jb;
+#pragma unroll 2
+            for (int i = 0; i < n_in; ++i) {
+                const float4 v4 = *reinterpret_cast<const float4*>(ip + i * S);
+                const float4 w0 = *reinterpret_cast<const float4*>(w + (int64_t)i * ldw);
+                const float4 w1 = two ? *reinterpret_cast<const float4*>(w + (int64_t)i * ldw + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    acc[r][0] = fmaf(v[r], w0.x, acc[r][0]); acc[r][1] = fmaf(v[r], w0.y, acc[r][1]);
+                    acc[r][2] = fmaf(v[r], w0.z, acc[r][2]); acc[r][3] = fmaf(v[r], w0.w, acc[r][3]);
+                    acc[r][4] = fmaf(v[r], w1.x, acc[r][4]); acc[r][5] = fmaf(v[r], w1.y, acc[r][5]);
+                    acc[r][6] = fmaf(v[r], w1.z, acc[r][6]); acc[r][7] = fmaf(v[r], w1.w, acc[r][7]);
+                }
+            }
+            const int j = 4 * jb;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (j + k < n_out && (k < 4 || two)) {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) epi(j + k, 4 * sl + r, acc[r][k]);
+                }
+        }
+        return;
+    }
+    const int s = sl;
     for (int jb = 2 * g; jb < n_blk; jb += 2 * G) {
         const bool two = (jb + 1) < n_blk;
         float4 a0 = bias ? *reinterpret_cast<const float4*>(bias + 4 * jb) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -68,37 +110,40 @@ template <int BM, bool ATOMIC>
 __device__ __forceinline__ void wgrad(float* dWt, int ldw, float* db, const float* __restrict__ in, int n_in,
                                       const float* __restrict__ dout, int n_out) {
     constexpr int S = Geo<BM>::S;
-    const int n_blk = (n_out + 3) >> 2;
-    const int total = n_in * n_blk;
+    // dWt[i][j] += sum_s in[i][s] * dout[j][s].  One thread owns a 2 (inputs) x 8 (outputs) block: 10 128-bit reads feed 64 FMAs
+    // per four samples.  Rows past n_in / n_out are clamped to a valid row for the loads and skipped at the store.
+    const int n_blk8 = (n_out + 7) >> 3, n_ip = (n_in + 1) >> 1;
+    const int total = n_ip * n_blk8;
     for (int e = threadIdx.x; e < total; e += kTileThreads) {
-        const int i = e / n_blk, jb = e - i * n_blk;
-        const float* ip = in + i * S;
-        const float* dp = dout + (4 * jb) * S;
-        const int nj = min(4, n_out - 4 * jb);
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        const int ipair = e / n_blk8, jb = e - ipair * n_blk8;
+        const int i0 = 2 * ipair, i1 = min(i0 + 1, n_in - 1);
+        const float* ip0 = in + i0 * S;
+        const float* ip1 = in + i1 * S;
+        const float* dp[8];
 #pragma unroll
+        for (int k = 0; k < 8; ++k) dp[k] = dout + min(8 * jb + k, n_out - 1) * S;
+        float a0[8], a1[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { a0[k] = 0.f; a1[k] = 0.f; }
+#pragma unroll 2
         for (int q = 0; q < BM / 4; ++q) {
-            float4 v = *reinterpret_cast<const float4*>(ip + 4 * q);
-            float4 d0 = *reinterpret_cast<const float4*>(dp + 4 * q);
-            a0 = fmaf(v.x, d0.x, a0); a0 = fmaf(v.y, d0.y, a0); a0 = fmaf(v.z, d0.z, a0); a0 = fmaf(v.w, d0.w, a0);
-            if (nj > 1) {
-                float4 d1 = *reinterpret_cast<const float4*>(dp + S + 4 * q);
-                a1 = fmaf(v.x, d1.x, a1); a1 = fmaf(v.y, d1.y, a1); a1 = fmaf(v.z, d1.z, a1); a1 = fmaf(v.w, d1.w, a1);
-            }
-            if (nj > 2) {
-                float4 d2 = *reinterpret_cast<const float4*>(dp + 2 * S + 4 * q);
-                a2 = fmaf(v.x, d2.x, a2); a2 = fmaf(v.y, d2.y, a2); a2 = fmaf(v.z, d2.z, a2); a2 = fmaf(v.w, d2.w, a2);
-            }
-            if (nj > 3) {
-                float4 d3 = *reinterpret_cast<const float4*>(dp + 3 * S + 4 * q);
-                a3 = fmaf(v.x, d3.x, a3); a3 = fmaf(v.y, d3.y, a3); a3 = fmaf(v.z, d3.z, a3); a3 = fmaf(v.w, d3.w, a3);
+            const float4 v0 = *reinterpret_cast<const float4*>(ip0 + 4 * q);
+            const float4 v1 = *reinterpret_cast<const float4*>(ip1 + 4 * q);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float4 d = *reinterpret_cast<const float4*>(dp[k] + 4 * q);
+                a0[k] = fmaf(v0.x, d.x, fmaf(v0.y, d.y, fmaf(v0.z, d.z, fmaf(v0.w, d.w, a0[k]))));
+                a1[k] = fmaf(v1.x, d.x, fmaf(v1.y, d.y, fmaf(v1.z, d.z, fmaf(v1.w, d.w, a1[k]))));
             }
         }
-        float* o = dWt + (int64_t)i * ldw + 4 * jb;
-        acc_add<ATOMIC>(o + 0, a0);
-        if (nj > 1) acc_add<ATOMIC>(o + 1, a1);
-        if (nj > 2) acc_add<ATOMIC>(o + 2, a2);
-        if (nj > 3) acc_add<ATOMIC>(o + 3, a3);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int j = 8 * jb + k;
+            if (j < n_out) {
+                acc_add<ATOMIC>(dWt + (int64_t)i0 * ldw + j, a0[k]);
+                if (i0 + 1 < n_in) acc_add<ATOMIC>(dWt + (int64_t)(i0 + 1) * ldw + j, a1[k]);
+            }
+        }
     }
     if (db) {
         for (int j = threadIdx.x; j < n_out; j += kTileThreads) {
