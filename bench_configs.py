@@ -58,13 +58,13 @@ def emit(**kw):
     print(json.dumps(kw), flush=True)
 
 
-def make_agent(dev, buffer_rows, seed=64, capturable=False):
+def make_agent(dev, buffer_rows, seed=64, capturable=False, fused=False):
     import torch
 
     from velora_b200.models.nf import NeuroFlowCTCore
 
     agent = NeuroFlowCTCore(4, 1, 20, 128, torch.tensor([3.0]), torch.tensor([0.0]), buffer_size=buffer_rows, seed=seed, device=dev,
-                            capturable=capturable)
+                            capturable=capturable, fused=fused)
     g = torch.Generator(device=dev).manual_seed(0)
     b = agent.buffer
     b.states.copy_(torch.randn(b.states.shape, device=dev, generator=g))
@@ -113,6 +113,12 @@ def main():
     gms = gpu_time_ms(replay, warmup=10, iters=200)
     emit(config="cfg1/2 NeuroFlowCT._train_step captured in one CUDA graph, batch 64", metric="us_per_train_step", value=1e3 * gms,
          cpu_port_us=None if cpu_ms is None else 1e3 * cpu_ms, cpu_cores=cores)
+    fagent = make_agent(dev, 100_000, capturable=True, fused=True)
+    freplay = fagent.capture_train_step(64)
+    fms = gpu_time_ms(freplay, warmup=10, iters=200)
+    emit(config="cfg1/2 NeuroFlowCT._train_step, one CUDA graph + fused Adam / Polyak kernels, batch 64", metric="us_per_train_step",
+         value=1e3 * fms, graph_nodes=None)
+    del fagent, freplay
     emit(config="cfg1/2 NeuroFlowCT._train_step, actor 20 / critic 128, batch 64", metric="us_per_train_step", value=1e3 * ms,
          cpu_port_us=None if cpu_ms is None else 1e3 * cpu_ms, cpu_cores=cores,
          note="sample (fused gather) + 2 liquid fwd + 1 liquid bwd + 6 NCP fwd + 4 NCP bwd through the C ABI; SAC head math, Adam, "
@@ -124,6 +130,20 @@ def main():
     with torch.no_grad():
         ms1 = gpu_time_ms(lambda: agent.actor.network.ncp(x1, h1), warmup=20, iters=200)
     emit(config="cfg2b LiquidNCPNetwork(4,20,2) forward, batch 1 (predict)", metric="us_per_call", value=1e3 * ms1)
+    act = gagent.capture_predict(1)
+    s1 = torch.randn(4, device=dev)
+    hcur = [None]
+
+    def act_once():
+        _, hcur[0] = act(s1, hcur[0])
+
+    ms1g = gpu_time_ms(act_once, warmup=20, iters=500)
+    t0 = time.perf_counter()
+    for _ in range(500):
+        act_once()
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) / 500
+    emit(config="cfg2b NeuroFlowCT.predict captured in one CUDA graph, batch 1", metric="us_per_call", value=1e3 * ms1g, wall_us=1e6 * wall)
 
     # ------------------------------------------------------------------ cfg 5: gather + train step at large batch
     big = make_agent(dev, 1_000_000)
@@ -140,10 +160,10 @@ def main():
              torch_six_index_kernels_ms=ref_ms)
         tms = gpu_time_ms(lambda: big._train_step(B), warmup=3, iters=10)
         emit(config=f"cfg5 sample + NeuroFlowCT update, batch {B}, 1 GPU", metric="transitions_per_s", value=B / (tms * 1e-3), ms=tms)
-        bigg = make_agent(dev, 1_000_000, capturable=True)
+        bigg = make_agent(dev, 1_000_000, capturable=True, fused=True)
         replay_big = bigg.capture_train_step(B)
         gms2 = gpu_time_ms(replay_big, warmup=3, iters=20)
-        emit(config=f"cfg5 sample + NeuroFlowCT update captured in one CUDA graph, batch {B}, 1 GPU", metric="transitions_per_s",
+        emit(config=f"cfg5 sample + NeuroFlowCT update, one CUDA graph + fused Adam / Polyak, batch {B}, 1 GPU", metric="transitions_per_s",
              value=B / (gms2 * 1e-3), ms=gms2)
         del bigg, replay_big
     if not args.no_cpu:

@@ -160,6 +160,16 @@ int vb_ncp_unpack_grads(const float* dpacked, const void* const* m, int m_type,
 int vb_gather_rows(const float* const* src, float* const* dst, const int* row_floats, int n_arrays,
                    const int64_t* idx, int64_t B, int64_t n_rows, void* stream);
 
+/* ------------------------------------------------------------------------------------------------ optimizer */
+/* torch.optim.Adam step (no weight decay / amsgrad; modules.py:116-118, 409-415, 715-717 construct it with defaults) over
+ * n_tensors fp32 tensors in one launch.  Host arrays of device pointers; steps[k] is the tensor's device-resident step
+ * counter (torch's capturable layout), already incremented for this step; sizes in elements. */
+int vb_adam_multi(float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+                  const float* const* steps, const int64_t* sizes, int n_tensors,
+                  float lr, float beta1, float beta2, float eps, void* stream);
+/* soft_update (velora/utils/torch.py:53-64): target = tau * source + (1 - tau) * target over all tensors in one launch */
+int vb_polyak_multi(float* const* target, const float* const* source, const int64_t* sizes, int n_tensors, float tau, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,16 +22,23 @@ class NeuroFlowCTCore:
                  action_bias: torch.Tensor, *, optim: Type[optim.Optimizer] = optim.Adam, buffer_size: int = 1_000_000,
                  actor_lr: float = 3e-4, critic_lr: float = 3e-4, alpha_lr: float = 3e-4, initial_alpha: float = 1.0,
                  log_std: tuple = (-5, 2), tau: float = 0.005, gamma: float = 0.99, device: torch.device | None = None,
-                 seed: int | None = None, capturable: bool = False) -> None:
+                 seed: int | None = None, capturable: bool = False, fused: bool = False) -> None:
         self.device = device
         self.seed = set_seed(seed)
         self.state_dim, self.action_dim = state_dim, action_dim
         self.gamma, self.tau = gamma, tau
         # capturable=True keeps the optimizer state on the device so that a whole train step can be captured in a CUDA graph
         okw = {"capturable": True} if capturable else None
+        if fused:   # one-launch Adam and Polyak updates (velora_b200/optim.py); same optimizer state layout as Adam(capturable=True)
+            from velora_b200.optim import FusedAdam
+
+            if optim is not torch.optim.Adam:
+                raise ValueError("fused=True replaces torch.optim.Adam only")
+            optim, okw = FusedAdam, None
         self.actor = ActorModule(state_dim, actor_neurons, action_dim, action_scale.to(device), action_bias.to(device),
                                  log_std_min=log_std[0], log_std_max=log_std[1], optim=optim, lr=actor_lr, device=device, optim_kwargs=okw)
-        self.critic = CriticModule(state_dim, critic_neurons, action_dim, optim=optim, lr=critic_lr, tau=tau, device=device, optim_kwargs=okw)
+        self.critic = CriticModule(state_dim, critic_neurons, action_dim, optim=optim, lr=critic_lr, tau=tau, device=device, optim_kwargs=okw,
+                                   fused_update=fused)
         self.hidden_dim = self.actor.hidden_size
         self.entropy = EntropyModule(action_dim, initial_alpha=initial_alpha, optim=optim, lr=alpha_lr, device=device, optim_kwargs=okw)
         self.loss = nn.MSELoss()
@@ -66,6 +73,56 @@ class NeuroFlowCTCore:
         self.entropy.gradient_step(entropy_loss)
         self.critic.update_targets()
         return {"critic": critic_loss.detach(), "actor": actor_loss.detach(), "entropy": entropy_loss.detach()}
+
+    def predict(self, state: torch.Tensor, hidden: torch.Tensor | None = None, *, train_mode: bool = False):
+        """Action for the given state (agent.py:356-388): deterministic `tanh(mean)` when `train_mode` is False, a sampled
+        action otherwise; returns (action, new hidden)."""
+        self.actor.eval_mode()
+        with torch.no_grad():
+            state = state.unsqueeze(0) if state.dim() < 2 else state
+            if not train_mode:
+                action, hidden = self.actor.predict(state, hidden)
+            else:
+                action, _, hidden = self.actor.forward(state, hidden)
+        self.actor.train_mode()
+        return action, hidden
+
+    def capture_predict(self, num_envs: int = 1, *, train_mode: bool = False):
+        """The per-environment-step `predict` as ONE CUDA graph (pack + forward kernel + the policy head) with static buffers.
+
+        Returns `act(state [num_envs, S] or [S], hidden [num_envs, H] | None) -> (action, hidden)`; the outputs are the
+        graph's static tensors (overwritten by the next call).  The graph reads the live parameters, so it stays valid
+        across `_train_step` / graph replays of the train step.  An eager batch-1 `predict` is ~100 us of Python dispatch
+        and ~270 us on the device timeline; the replay is two tiny copies and one graph launch.
+        """
+        if self.device is None or torch.device(self.device).type != "cuda":
+            raise RuntimeError("capture_predict needs a CUDA device")
+        dev = self.device
+        s_state = torch.zeros(num_envs, self.state_dim, device=dev)
+        s_hidden = torch.zeros(num_envs, self.hidden_dim, device=dev)
+        cur = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                self.predict(s_state, s_hidden, train_mode=train_mode)
+        cur.wait_stream(side)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = self.predict(s_state, s_hidden, train_mode=train_mode)
+
+        def act(state: torch.Tensor, hidden: torch.Tensor | None = None):
+            s_state.copy_(state.reshape(num_envs, self.state_dim), non_blocking=True)
+            if hidden is None:
+                s_hidden.zero_()
+            else:
+                s_hidden.copy_(hidden.reshape(num_envs, self.hidden_dim), non_blocking=True)
+            graph.replay()
+            return out
+
+        act.graph = graph
+        return act
 
     def capture_train_step(self, batch_size: int, warmup: int = 3):
         """Captures one `_train_step(batch_size)` - index draw, fused gather, every network forward/backward, the SAC head

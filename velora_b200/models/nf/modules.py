@@ -36,11 +36,21 @@ class ActorModule:
     def forward(self, obs: torch.Tensor, hidden: torch.Tensor | None = None):
         return self.network(obs, hidden)
 
+    def eval_mode(self) -> None:
+        """modules.py:157-159"""
+        self.network.eval()
+
+    def train_mode(self) -> None:
+        """modules.py:161-163"""
+        self.network.train()
+
 
 class CriticModule:
     def __init__(self, state_dim: int, n_neurons: int, action_dim: int, *, optim: Type[optim.Optimizer] = optim.Adam,
-                 lr: float = 3e-4, tau: float = 0.005, device: torch.device | None = None, optim_kwargs: dict | None = None):
+                 lr: float = 3e-4, tau: float = 0.005, device: torch.device | None = None, optim_kwargs: dict | None = None,
+                 fused_update: bool = False):
         self.tau = tau
+        self.fused_update = fused_update
         self.device = device
         self.network1 = SACCriticNCP(state_dim, n_neurons, action_dim, device=device).to(device)
         self.network2 = SACCriticNCP(state_dim, n_neurons, action_dim, device=device).to(device)
@@ -56,6 +66,12 @@ class CriticModule:
         self.target2 = torch.jit.script(self.target2)
 
     def update_targets(self) -> None:
+        if self.fused_update:      # one launch per network pair (velora_b200/optim.py)
+            from velora_b200.optim import soft_update as fused_soft_update
+
+            fused_soft_update(self.network1, self.target1, tau=self.tau)
+            fused_soft_update(self.network2, self.target2, tau=self.tau)
+            return
         soft_update(self.network1, self.target1, tau=self.tau)
         soft_update(self.network2, self.target2, tau=self.tau)
 
