@@ -16,7 +16,7 @@ constexpr int kTileThreads = 256;
 template <int BM>
 struct Geo {
     static constexpr int S = BM + 4;                 // row stride in floats
-    static constexpr int RS = BM >= 64 ? 4 : 1;      // samples per thread in dense(): big tiles are register-blocked 4 x 8
+    static constexpr int RS = BM >= 64 ? 4 : (BM == 32 ? 2 : 1);   // samples per thread in dense(): RS x 8 register blocks
     static constexpr int LN = BM / RS;               // threads along the sample axis
     static constexpr int G = kTileThreads / LN;      // output groups
 };
@@ -28,29 +28,35 @@ __device__ __forceinline__ void dense(const float* __restrict__ in, int n_in, co
     constexpr int S = Geo<BM>::S, G = Geo<BM>::G, RS = Geo<BM>::RS, LN = Geo<BM>::LN;
     const int sl = threadIdx.x % LN, g = threadIdx.x / LN;
     const int n_blk = (n_out + 3) >> 2;
-    if constexpr (RS == 4) {
-        // 4 samples x 8 outputs per thread: one 128-bit activation read + two warp-uniform 128-bit weight reads feed 32 FMAs
+    if constexpr (RS > 1) {
+        // RS samples x 8 outputs per thread: one vector activation read + two warp-uniform 128-bit weight reads feed 8 RS FMAs
         // (the 1 x 8 variant below issues 3 shared-memory reads per 8 FMAs and is bound by the LSU, not the FMA pipe)
-        const float* ip = in + 4 * sl;
+        const float* ip = in + RS * sl;
         for (int jb = 2 * g; jb < n_blk; jb += 2 * G) {
             const bool two = (jb + 1) < n_blk;
             const float4 b0 = bias ? *reinterpret_cast<const float4*>(bias + 4 * jb) : make_float4(0.f, 0.f, 0.f, 0.f);
             const float4 b1 = (bias && two) ? *reinterpret_cast<const float4*>(bias + 4 * jb + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-            float acc[4][8];
+            float acc[RS][8];
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
+            for (int r = 0; r < RS; ++r) {
                 acc[r][0] = b0.x; acc[r][1] = b0.y; acc[r][2] = b0.z; acc[r][3] = b0.w;
                 acc[r][4] = b1.x; acc[r][5] = b1.y; acc[r][6] = b1.z; acc[r][7] = b1.w;
             }
             const float* w = Wt + 4 * jb;
 #pragma unroll 2
             for (int i = 0; i < n_in; ++i) {
-                const float4 v4 = *reinterpret_cast<const float4*>(ip + i * S);
+                float v[RS];
+                if constexpr (RS == 4) {
+                    const float4 v4 = *reinterpret_cast<const float4*>(ip + i * S);
+                    v[0] = v4.x; v[1] = v4.y; v[2] = v4.z; v[3] = v4.w;
+                } else {
+                    const float2 v2 = *reinterpret_cast<const float2*>(ip + i * S);
+                    v[0] = v2.x; v[1] = v2.y;
+                }
                 const float4 w0 = *reinterpret_cast<const float4*>(w + (int64_t)i * ldw);
                 const float4 w1 = two ? *reinterpret_cast<const float4*>(w + (int64_t)i * ldw + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                const float v[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
+                for (int r = 0; r < RS; ++r) {
                     acc[r][0] = fmaf(v[r], w0.x, acc[r][0]); acc[r][1] = fmaf(v[r], w0.y, acc[r][1]);
                     acc[r][2] = fmaf(v[r], w0.z, acc[r][2]); acc[r][3] = fmaf(v[r], w0.w, acc[r][3]);
                     acc[r][4] = fmaf(v[r], w1.x, acc[r][4]); acc[r][5] = fmaf(v[r], w1.y, acc[r][5]);
@@ -62,7 +68,7 @@ __device__ __forceinline__ void dense(const float* __restrict__ in, int n_in, co
             for (int k = 0; k < 8; ++k)
                 if (j + k < n_out && (k < 4 || two)) {
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) epi(j + k, 4 * sl + r, acc[r][k]);
+                    for (int r = 0; r < RS; ++r) epi(j + k, RS * sl + r, acc[r][k]);
                 }
         }
         return;
@@ -110,35 +116,37 @@ template <int BM, bool ATOMIC>
 __device__ __forceinline__ void wgrad(float* dWt, int ldw, float* db, const float* __restrict__ in, int n_in,
                                       const float* __restrict__ dout, int n_out) {
     constexpr int S = Geo<BM>::S;
-    // dWt[i][j] += sum_s in[i][s] * dout[j][s].  One thread owns a 2 (inputs) x 8 (outputs) block: 10 128-bit reads feed 64 FMAs
-    // per four samples.  Rows past n_in / n_out are clamped to a valid row for the loads and skipped at the store.
-    const int n_blk8 = (n_out + 7) >> 3, n_ip = (n_in + 1) >> 1;
-    const int total = n_ip * n_blk8;
+    // dWt[i][j] += sum_s in[i][s] * dout[j][s].  One thread owns 2 inputs x 4 outputs: six 128-bit reads feed 32 FMAs per four
+    // samples.  The four outputs of a thread are J = ceil(n_out / 4) apart and consecutive threads own consecutive outputs, so
+    // that a warp's reads of dout rows (row stride = 4 mod 32 banks) and its read-modify-writes of dWt are conflict-free
+    // (with 4 adjacent outputs per thread ncu showed 17 wavefronts per LDS.128 instead of 4).
+    const int J = (n_out + 3) >> 2, n_ip = (n_in + 1) >> 1;
+    const int total = n_ip * J;
     for (int e = threadIdx.x; e < total; e += kTileThreads) {
-        const int ipair = e / n_blk8, jb = e - ipair * n_blk8;
+        const int ipair = e / J, j0 = e - ipair * J;
         const int i0 = 2 * ipair, i1 = min(i0 + 1, n_in - 1);
         const float* ip0 = in + i0 * S;
         const float* ip1 = in + i1 * S;
-        const float* dp[8];
+        const float* dp[4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) dp[k] = dout + min(8 * jb + k, n_out - 1) * S;
-        float a0[8], a1[8];
+        for (int k = 0; k < 4; ++k) dp[k] = dout + min(j0 + k * J, n_out - 1) * S;
+        float a0[4], a1[4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { a0[k] = 0.f; a1[k] = 0.f; }
-#pragma unroll 2
+        for (int k = 0; k < 4; ++k) { a0[k] = 0.f; a1[k] = 0.f; }
+#pragma unroll 4
         for (int q = 0; q < BM / 4; ++q) {
             const float4 v0 = *reinterpret_cast<const float4*>(ip0 + 4 * q);
             const float4 v1 = *reinterpret_cast<const float4*>(ip1 + 4 * q);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
+            for (int k = 0; k < 4; ++k) {
                 const float4 d = *reinterpret_cast<const float4*>(dp[k] + 4 * q);
                 a0[k] = fmaf(v0.x, d.x, fmaf(v0.y, d.y, fmaf(v0.z, d.z, fmaf(v0.w, d.w, a0[k]))));
                 a1[k] = fmaf(v1.x, d.x, fmaf(v1.y, d.y, fmaf(v1.z, d.z, fmaf(v1.w, d.w, a1[k]))));
             }
         }
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int j = 8 * jb + k;
+        for (int k = 0; k < 4; ++k) {
+            const int j = j0 + k * J;
             if (j < n_out) {
                 acc_add<ATOMIC>(dWt + (int64_t)i0 * ldw + j, a0[k]);
                 if (i0 + 1 < n_in) acc_add<ATOMIC>(dWt + (int64_t)(i0 + 1) * ldw + j, a1[k]);
