@@ -51,6 +51,7 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
         self.active = False
+        self.windows = []          # (t0, t1) host times of the timed regions; only samples inside them are reported
         try:
             import pynvml
 
@@ -74,24 +75,26 @@ class ClockSampler(threading.Thread):
         while not self.stop_flag:
             if self.active:
                 try:
-                    self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                    self.samples.append((time.perf_counter(), nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
                     try:
                         mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
                     except Exception:
                         mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    now = time.perf_counter()
                     for bit, name in names.items():
                         if mask & bit:
-                            self.reasons.add(name)
+                            self.reasons.add((now, name))
                 except Exception:
                     pass
             time.sleep(0.004)
 
     def summary(self):
-        s = sorted(self.samples)
+        inside = lambda t: any(a <= t <= b for a, b in self.windows)   # noqa: E731
+        s = sorted(v for t, v in self.samples if inside(t))
         return {
             "sm_mhz": s[len(s) // 2] if s else None,
             "sm_max_mhz": self.max_mhz,
-            "reasons": sorted(self.reasons),
+            "reasons": sorted({name for t, name in self.reasons if inside(t)}),
             "samples": len(s),
         }
 
@@ -278,16 +281,20 @@ def run_ours(args) -> None:
     # all-reduce run ~15-40 % slower than steady state (measured at 8 GPUs: 0.43-0.54 ms for the first 50 steps, 0.371 ms
     # for every later block of 50), so the multi-rank run gets extra untimed replays on top of the W requested ones.
     extra_warm = 100 if (world > 1 and graphs is not None) else 0
+    # NVML polling starts during the warm-up: the first queries of a process take milliseconds inside the driver and, with
+    # 8 ranks in lock step, showed up as 0.43-0.81 ms steps when they fell into the timed region
+    sampler.active = True
     for i in range(W + extra_warm):
         timed_step(i)
     barrier()
-    sampler.active = True
     align()
+    w0 = time.perf_counter()
     e0.record()
     for i in range(K):
         timed_step(W + i)
     e1.record()
     barrier()
+    sampler.windows.append((w0, time.perf_counter()))
     sampler.active = False
     ms_total = e0.elapsed_time(e1)
     if world > 1:
@@ -443,11 +450,13 @@ def run_ours(args) -> None:
     barrier()
     sampler.active = True
     align()
+    w0 = time.perf_counter()
     e0.record()
     for i in range(3, 3 + K):
         e2e_step(i)
     e1.record()
     barrier()
+    sampler.windows.append((w0, time.perf_counter()))
     sampler.active = False
     e2e_ms = e0.elapsed_time(e1)
     if world > 1:
