@@ -366,6 +366,85 @@ def gen_train(ref) -> dict:
     return out
 
 
+def categorical_from_uniform(probs: torch.Tensor, u: torch.Tensor) -> torch.Tensor:
+    """Inverse-CDF draw from `probs` [B, A] with recorded uniforms u [B]: the stand-in for Categorical.sample() that both the
+    golden generator and the GPU test use, so that the same noise replays on any device."""
+    cdf = torch.cumsum(probs, dim=-1)
+    return torch.clamp((cdf < u.to(probs).unsqueeze(-1)).sum(dim=-1), max=probs.shape[-1] - 1)
+
+
+def gen_train_discrete(ref) -> dict:
+    """Three NeuroFlow._train_step calls (discrete agent, velora/models/nf/agent.py:549-636) on a synthetic buffer with
+    CartPole shapes (S=4, 2 actions; actor 20 / critic 128 neurons = BASELINE config 1), batch 32; the categorical draws and
+    the sampled indices are supplied from outside."""
+    import torch.nn as nn
+    import velora.models.sac.discrete as disc
+    from velora.buffer.experience import BatchExperience
+
+    out = {}
+    UNI, IDX = [], []
+
+    def get_sample(self, probs):
+        actions = categorical_from_uniform(probs, UNI.pop(0))
+        return actions, torch.log(torch.gather(probs, -1, actions.unsqueeze(-1)))   # == Categorical(probs).log_prob(actions)[:, None]
+
+    orig = disc.SACActorDiscrete.get_sample
+    disc.SACActorDiscrete.get_sample = torch.jit.ignore(get_sample)
+    try:
+        S, A, B, steps = 4, 2, 32, 3
+        ref.set_seed(64)
+        agent = object.__new__(ref.NeuroFlow)
+        agent.device = None
+        agent.gamma, agent.tau = 0.99, 0.005
+        agent.actor = ref.ActorModuleDiscrete(S, 20, A)
+        agent.critic = ref.CriticModuleDiscrete(S, 128, A)
+        agent.entropy = ref.EntropyModuleDiscrete(A)
+        agent.loss = nn.MSELoss()
+        agent.buffer = ref.ReplayBuffer(512, S, 1, agent.actor.hidden_size)
+        g = torch.Generator().manual_seed(3)
+        n = 300
+        feed = (torch.randn(n, S, generator=g), torch.randint(0, A, (n, 1), generator=g).float(), torch.ones(n),
+                torch.randn(n, S, generator=g), (torch.rand(n, generator=g) < 0.02), 0.3 * torch.randn(n, 8, generator=g))
+        agent.buffer.add_multi(*feed)
+        for k, v in agent.buffer.state_dict().items():
+            out[f"buf_{k}"] = t2n(v)
+        for k, v in agent.actor.network.state_dict().items():
+            out[f"init_actor_{k}"] = t2n(v)
+        for k, v in agent.critic.network1.state_dict().items():
+            out[f"init_critic1_{k}"] = t2n(v)
+        for k, v in agent.critic.network2.state_dict().items():
+            out[f"init_critic2_{k}"] = t2n(v)
+
+        def sample(batch_size):
+            idx = IDX.pop(0)
+            b = agent.buffer
+            return BatchExperience(b.states[idx], b.actions[idx], b.rewards[idx], b.next_states[idx], b.dones[idx], b.hiddens[idx])
+
+        agent.buffer.sample = sample
+        uni_all = torch.rand(steps * 2, B, generator=g)
+        idx_all = torch.randint(0, n, (steps, B), generator=g)
+        out["uni"], out["idx"] = t2n(uni_all), t2n(idx_all)
+        losses = []
+        for s in range(steps):
+            UNI.extend([uni_all[2 * s], uni_all[2 * s + 1]])
+            IDX.append(idx_all[s])
+            r = agent._train_step(B)
+            assert not UNI and not IDX, "the recorded noise / indices were not consumed: the patched hooks are not in use"
+            losses.append([float(r["critic"]), float(r["actor"]), float(r["entropy"])])
+        out["losses"] = np.array(losses, dtype=np.float64)
+        for k, v in agent.actor.network.state_dict().items():
+            out[f"final_actor_{k}"] = t2n(v)
+        for k, v in agent.critic.network1.state_dict().items():
+            out[f"final_critic1_{k}"] = t2n(v)
+        for k, v in agent.critic.target1.state_dict().items():
+            out[f"final_target1_{k}"] = t2n(v)
+        out["final_log_alpha"] = t2n(agent.entropy.log_alpha)
+        out["dims"] = np.array([S, A, B, steps, n], dtype=np.int64)
+    finally:
+        disc.SACActorDiscrete.get_sample = orig
+    return out
+
+
 def main() -> None:
     # The reference writes polarities with `mask[rows, cols] = pol` where (row, col) pairs repeat
     # (np.random.choice draws with replacement, wiring.py:245-251).  With several intra-op threads torch's
@@ -376,7 +455,7 @@ def main() -> None:
     ref = ref_import.import_reference()
     os.makedirs(OUT, exist_ok=True)
     for name, fn in (("wiring", gen_wiring), ("liquid", gen_liquid), ("cell", gen_cell), ("ncp", gen_ncp), ("buffer", gen_buffer),
-                     ("train", gen_train)):
+                     ("train", gen_train), ("train_discrete", gen_train_discrete)):
         data = fn(ref)
         path = os.path.join(OUT, f"{name}.npz")
         np.savez_compressed(path, **data)

@@ -115,9 +115,11 @@ def import_reference():
     try:   # the agent layer (only needed for the train-step goldens); heavier stubs, optional
         _shell("velora.models.nf", os.path.join(vroot, "models", "nf"))
         from velora.models.nf.modules import ActorModule, CriticModule, EntropyModule
-        from velora.models.nf.agent import NeuroFlowCT
+        from velora.models.nf.modules import ActorModuleDiscrete, CriticModuleDiscrete, EntropyModuleDiscrete
+        from velora.models.nf.agent import NeuroFlow, NeuroFlowCT
     except Exception as e:   # pragma: no cover
         ActorModule = CriticModule = EntropyModule = NeuroFlowCT = None
+        ActorModuleDiscrete = CriticModuleDiscrete = EntropyModuleDiscrete = NeuroFlow = None
         print(f"[ref_import] agent layer not importable: {e!r}")
 
     ns = types.SimpleNamespace(
@@ -125,6 +127,10 @@ def import_reference():
         CriticModule=CriticModule,
         EntropyModule=EntropyModule,
         NeuroFlowCT=NeuroFlowCT,
+        ActorModuleDiscrete=ActorModuleDiscrete,
+        CriticModuleDiscrete=CriticModuleDiscrete,
+        EntropyModuleDiscrete=EntropyModuleDiscrete,
+        NeuroFlow=NeuroFlow,
         NCPLiquidCell=NCPLiquidCell,
         LiquidNCPNetwork=LiquidNCPNetwork,
         NCPNetwork=NCPNetwork,

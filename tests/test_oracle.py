@@ -180,3 +180,23 @@ def test_train_oracle_vs_reference(golden):
     for k, v in pre("final_actor_ncp.").items():
         assert np.allclose(o.actor[k].detach().numpy(), v, atol=1e-6), k
     assert abs(float(o.log_alpha) - float(d["final_log_alpha"])) < 1e-6
+
+
+def test_train_discrete_golden_regenerates(golden):
+    """tests/golden/train_discrete.npz is what the unmodified reference's discrete agent produces here (no oracle port of
+    that step exists: the GPU parity test compares NeuroFlowCore with these reference outputs directly)."""
+    from oracle import make_golden, ref_import
+
+    if not ref_import.reference_available():
+        pytest.skip("reference tree not present (GPU box)")
+
+    d = golden("train_discrete")
+    n_threads = torch.get_num_threads()
+    torch.set_num_threads(1)
+    try:
+        fresh = make_golden.gen_train_discrete(ref_import.import_reference())
+    finally:
+        torch.set_num_threads(n_threads)
+    assert set(fresh) == set(d.keys())
+    for k, v in fresh.items():
+        assert np.array_equal(np.asarray(v), d[k]), k

@@ -1,4 +1,6 @@
-from velora_b200.models.nf.agent import NeuroFlowCTCore
-from velora_b200.models.nf.modules import ActorModule, CriticModule, EntropyModule
+from velora_b200.models.nf.agent import NeuroFlowCore, NeuroFlowCTCore
+from velora_b200.models.nf.modules import (ActorModule, ActorModuleDiscrete, CriticModule, CriticModuleDiscrete, EntropyModule,
+                                           EntropyModuleDiscrete)
 
-__all__ = ["NeuroFlowCTCore", "ActorModule", "CriticModule", "EntropyModule"]
+__all__ = ["NeuroFlowCore", "NeuroFlowCTCore", "ActorModule", "ActorModuleDiscrete", "CriticModule", "CriticModuleDiscrete",
+           "EntropyModule", "EntropyModuleDiscrete"]

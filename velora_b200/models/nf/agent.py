@@ -13,7 +13,8 @@ import torch.nn as nn
 from torch import optim
 
 from velora_b200.buffer import BatchExperience, ReplayBuffer
-from velora_b200.models.nf.modules import ActorModule, CriticModule, EntropyModule
+from velora_b200.models.nf.modules import (ActorModule, ActorModuleDiscrete, CriticModule, CriticModuleDiscrete, EntropyModule,
+                                           EntropyModuleDiscrete)
 from velora_b200.utils.core import set_seed
 
 
@@ -152,3 +153,78 @@ class NeuroFlowCTCore:
 
         replay.graph = graph
         return replay
+
+
+class NeuroFlowCore(NeuroFlowCTCore):
+    """The environment-free core of the reference's discrete agent NeuroFlow (velora/models/nf/agent.py:411-650): liquid
+    actor with a softmax head, two NCP critics emitting Q for every action, discrete-SAC entropy tuning.  BASELINE config 1
+    (`NeuroFlow("CartPole-v1", 20, 128)`) is `NeuroFlowCore(4, 2, 20, 128)`.  Shares `predict`, `capture_train_step` and
+    `capture_predict` with the continuous core."""
+
+    def __init__(self, state_dim: int, action_dim: int, actor_neurons: int, critic_neurons: int, *,
+                 optim: Type[optim.Optimizer] = optim.Adam, buffer_size: int = 1_000_000, actor_lr: float = 3e-4,
+                 critic_lr: float = 3e-4, alpha_lr: float = 3e-4, initial_alpha: float = 1.0, tau: float = 0.005,
+                 gamma: float = 0.99, device: torch.device | None = None, seed: int | None = None, capturable: bool = False,
+                 fused: bool = False) -> None:
+        self.device = device
+        self.seed = set_seed(seed)
+        self.state_dim, self.action_dim = state_dim, action_dim
+        self.gamma, self.tau = gamma, tau
+        okw = {"capturable": True} if capturable else None
+        if fused:
+            from velora_b200.optim import FusedAdam
+
+            if optim is not torch.optim.Adam:
+                raise ValueError("fused=True replaces torch.optim.Adam only")
+            optim, okw = FusedAdam, None
+        self.actor = ActorModuleDiscrete(state_dim, actor_neurons, action_dim, optim=optim, lr=actor_lr, device=device, optim_kwargs=okw)
+        self.critic = CriticModuleDiscrete(state_dim, critic_neurons, action_dim, optim=optim, lr=critic_lr, tau=tau, device=device,
+                                           optim_kwargs=okw, fused_update=fused)
+        self.hidden_dim = self.actor.hidden_size
+        self.entropy = EntropyModuleDiscrete(action_dim, initial_alpha=initial_alpha, optim=optim, lr=alpha_lr, device=device, optim_kwargs=okw)
+        self.loss = nn.MSELoss()
+        self.buffer = ReplayBuffer(buffer_size, state_dim, 1, self.actor.hidden_size, device=device)   # action index stored as one float
+
+    def _update_critics(self, batch: BatchExperience) -> torch.Tensor:
+        """agent.py:549-590"""
+        with torch.no_grad():
+            _, next_probs, _, _ = self.actor.forward(batch.next_states, batch.hiddens)
+            next_log_probs = torch.log(next_probs + 1e-8)
+            min_next_q = self.critic.target_predict(batch.next_states)
+            next_q = next_probs * (min_next_q - self.entropy.alpha * next_log_probs)
+            next_q = torch.sum(next_q, dim=-1, keepdim=True)
+            target_q = batch.rewards + (1 - batch.dones) * self.gamma * next_q
+        current_q1, current_q2 = self.critic.predict(batch.states)
+        current_q1 = current_q1.gather(1, batch.actions.long())
+        current_q2 = current_q2.gather(1, batch.actions.long())
+        c1_loss = self.loss(current_q1, target_q)
+        c2_loss = self.loss(current_q2, target_q)
+        critic_loss = c1_loss + c2_loss
+        self.critic.gradient_step(c1_loss, c2_loss)
+        return critic_loss
+
+    def _train_on(self, batch: BatchExperience) -> Dict[str, torch.Tensor]:
+        """agent.py:592-636"""
+        critic_loss = self._update_critics(batch)
+        _, probs, log_probs, _ = self.actor.forward(batch.states, batch.hiddens)
+        q1, q2 = self.critic.predict(batch.states)
+        next_q = torch.min(q1, q2)
+        actor_loss = probs * (self.entropy.alpha * log_probs - next_q)
+        actor_loss = torch.sum(actor_loss, dim=-1, keepdim=False).mean()
+        entropy_loss = self.entropy.compute_loss(probs, torch.log(probs + 1e-8))
+        self.actor.gradient_step(actor_loss)
+        self.entropy.gradient_step(entropy_loss)
+        self.critic.update_targets()
+        return {"critic": critic_loss.detach(), "actor": actor_loss.detach(), "entropy": entropy_loss.detach()}
+
+    def predict(self, state: torch.Tensor, hidden: torch.Tensor | None = None, *, train_mode: bool = False):
+        """agent.py:700-732: greedy action when `train_mode` is False, a sampled one otherwise."""
+        self.actor.eval_mode()
+        with torch.no_grad():
+            state = state.unsqueeze(0) if state.dim() < 2 else state
+            if not train_mode:
+                action, hidden = self.actor.predict(state, hidden)
+            else:
+                action, _, _, hidden = self.actor.forward(state, hidden)
+        self.actor.train_mode()
+        return action, hidden

@@ -9,6 +9,7 @@ import torch.nn as nn
 from torch import optim
 
 from velora_b200.models.sac.continuous import SACActor, SACCriticNCP
+from velora_b200.models.sac.discrete import SACActorDiscrete, SACCriticNCPDiscrete
 from velora_b200.utils.torch import soft_update
 
 
@@ -106,6 +107,93 @@ class EntropyModule:
     def compute_loss(self, log_probs: torch.Tensor) -> torch.Tensor:
         entropy = (log_probs + self.target).detach()
         return -(self.log_alpha * entropy).mean()
+
+    def gradient_step(self, loss: torch.Tensor) -> None:
+        self.optim.zero_grad()
+        loss.backward()
+        self.optim.step()
+
+
+class ActorModuleDiscrete:
+    """modules.py:190-318"""
+
+    def __init__(self, state_dim: int, n_neurons: int, action_dim: int, *, optim: Type[optim.Optimizer] = optim.Adam,
+                 lr: float = 3e-4, device: torch.device | None = None, optim_kwargs: dict | None = None):
+        self.device = device
+        self.network = SACActorDiscrete(state_dim, n_neurons, action_dim, device=device).to(device)
+        self.hidden_size = self.network.ncp.hidden_size
+        self.optim = optim(self.network.parameters(), lr=lr, **(optim_kwargs or {}))
+        self.active_params = self.network.ncp.active_params
+        self.total_params = self.network.ncp.total_params
+        self.network = torch.jit.script(self.network)
+
+    def gradient_step(self, loss: torch.Tensor) -> None:
+        self.optim.zero_grad()
+        loss.backward()
+        self.optim.step()
+
+    def predict(self, obs: torch.Tensor, hidden: torch.Tensor | None = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        return self.network.predict(obs, hidden)
+
+    def forward(self, obs: torch.Tensor, hidden: torch.Tensor | None = None):
+        return self.network(obs, hidden)
+
+    def eval_mode(self) -> None:
+        self.network.eval()
+
+    def train_mode(self) -> None:
+        self.network.train()
+
+
+class CriticModuleDiscrete:
+    """modules.py:485-644"""
+
+    def __init__(self, state_dim: int, n_neurons: int, action_dim: int, *, optim: Type[optim.Optimizer] = optim.Adam,
+                 lr: float = 3e-4, tau: float = 0.005, device: torch.device | None = None, optim_kwargs: dict | None = None,
+                 fused_update: bool = False):
+        self.tau = tau
+        self.fused_update = fused_update
+        self.device = device
+        self.network1 = SACCriticNCPDiscrete(state_dim, n_neurons, action_dim, device=device).to(device)
+        self.network2 = SACCriticNCPDiscrete(state_dim, n_neurons, action_dim, device=device).to(device)
+        self.target1 = deepcopy(self.network1)
+        self.target2 = deepcopy(self.network2)
+        self.optim1 = optim(self.network1.parameters(), lr=lr, **(optim_kwargs or {}))
+        self.optim2 = optim(self.network2.parameters(), lr=lr, **(optim_kwargs or {}))
+        self.active_params = self.network1.ncp.active_params + self.network2.ncp.active_params
+        self.total_params = self.network1.ncp.total_params + self.network2.ncp.total_params
+        self.network1 = torch.jit.script(self.network1)
+        self.network2 = torch.jit.script(self.network2)
+        self.target1 = torch.jit.script(self.target1)
+        self.target2 = torch.jit.script(self.target2)
+
+    update_targets = CriticModule.update_targets
+    gradient_step = CriticModule.gradient_step
+
+    def predict(self, obs: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        return self.network1(obs), self.network2(obs)
+
+    def target_predict(self, obs: torch.Tensor) -> torch.Tensor:
+        return torch.min(self.target1(obs), self.target2(obs))
+
+
+class EntropyModuleDiscrete:
+    """modules.py:751-855 (target entropy 0.98 log(1 / |A|))"""
+
+    def __init__(self, action_dim: int, *, initial_alpha: float = 1.0, optim: Type[optim.Optimizer] = optim.Adam,
+                 lr: float = 3e-4, device: torch.device | None = None, optim_kwargs: dict | None = None):
+        self.target = 0.98 * torch.tensor(1 / action_dim, device=device).log()
+        self.log_alpha = nn.Parameter(torch.tensor(initial_alpha, device=device).log())
+        self.optim = optim([self.log_alpha], lr=lr, **(optim_kwargs or {}))
+
+    @property
+    def alpha(self) -> torch.Tensor:
+        return self.log_alpha.exp()
+
+    def compute_loss(self, probs: torch.Tensor, log_probs: torch.Tensor) -> torch.Tensor:
+        with torch.no_grad():
+            entropy_mean = -torch.sum(probs * log_probs, dim=1).mean()
+        return self.log_alpha * (entropy_mean - self.target)
 
     def gradient_step(self, loss: torch.Tensor) -> None:
         self.optim.zero_grad()

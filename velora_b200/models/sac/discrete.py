@@ -1,0 +1,53 @@
+"""Discrete-action SAC heads over the fused networks (mirror of velora/models/sac/discrete.py:10-184)."""
+from typing import Optional, Tuple
+
+import torch
+import torch.nn as nn
+from torch.distributions import Categorical
+
+from velora_b200.models.lnn.ncp import LiquidNCPNetwork, NCPNetwork
+
+
+class SACActorDiscrete(nn.Module):
+    """Liquid actor emitting a categorical distribution over actions (discrete.py:10-96)."""
+
+    def __init__(self, num_obs: int, n_neurons: int, num_actions: int, *, device: torch.device | None = None) -> None:
+        super().__init__()
+        self.device = device
+        self.ncp = LiquidNCPNetwork(num_obs, n_neurons, num_actions, device=device).to(device)
+        self.num_actions = num_actions
+        self.softmax = nn.Softmax(dim=-1)
+
+    @torch.jit.ignore
+    def get_sample(self, probs: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Sampled actions and their log-probabilities (discrete.py:41-57)."""
+        # argument validation reads a device flag back to the host, which is illegal while a CUDA graph is being captured
+        validate = not (probs.is_cuda and torch.cuda.is_current_stream_capturing())
+        dist = Categorical(probs=probs, validate_args=validate)
+        actions = dist.sample()
+        return actions, dist.log_prob(actions).unsqueeze(-1)
+
+    @torch.jit.ignore
+    def predict(self, obs: torch.Tensor, hidden: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Greedy action (discrete.py:59-78)."""
+        logits, new_hidden = self.ncp(obs, hidden)
+        return torch.argmax(self.softmax(logits), dim=-1), new_hidden
+
+    def forward(self, obs: torch.Tensor, hidden: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+        """(obs, hidden) -> (actions, probs, log_prob of the actions, new hidden)   (discrete.py:80-101)"""
+        logits, new_hidden = self.ncp(obs, hidden)
+        probs = self.softmax(logits)
+        actions, log_prob = self.get_sample(probs)
+        return actions, probs, log_prob, new_hidden
+
+
+class SACCriticNCPDiscrete(nn.Module):
+    """NCP critic: Q(obs, .) for every action through the fused three-layer NCPNetwork (discrete.py:147-184)."""
+
+    def __init__(self, num_obs: int, n_neurons: int, num_actions: int, *, device: torch.device | None = None) -> None:
+        super().__init__()
+        self.device = device
+        self.ncp = NCPNetwork(num_obs, n_neurons, num_actions, device=device).to(device)
+
+    def forward(self, obs: torch.Tensor) -> torch.Tensor:
+        return self.ncp(obs)
