@@ -124,6 +124,26 @@ def main():
          note="sample (fused gather) + 2 liquid fwd + 1 liquid bwd + 6 NCP fwd + 4 NCP bwd through the C ABI; SAC head math, Adam, "
               "soft update are framework ops (next rows)")
 
+    # ------------------------------------------------------------------ cfg 1: the discrete agent (CartPole shapes: 4 obs, 2 actions)
+    from velora_b200.models.nf import NeuroFlowCore
+
+    dagent = NeuroFlowCore(4, 2, 20, 128, buffer_size=100_000, seed=64, device=dev, capturable=True, fused=True)
+    gd = torch.Generator(device=dev).manual_seed(0)
+    db = dagent.buffer
+    db.states.copy_(torch.randn(db.states.shape, device=dev, generator=gd))
+    db.next_states.copy_(torch.randn(db.states.shape, device=dev, generator=gd))
+    db.actions.copy_(torch.randint(0, 2, db.actions.shape, device=dev, generator=gd).float())
+    db.rewards.fill_(1.0)
+    db.dones.copy_((torch.rand(db.dones.shape, device=dev, generator=gd) < 0.02).float())
+    db.hiddens.copy_(0.3 * torch.randn(db.hiddens.shape, device=dev, generator=gd))
+    db.size = 100_000
+    dms = gpu_time_ms(lambda: dagent._train_step(64), warmup=10, iters=50)
+    dreplay = dagent.capture_train_step(64)
+    dgms = gpu_time_ms(dreplay, warmup=10, iters=200)
+    emit(config="cfg1 NeuroFlow (discrete) _train_step, actor 20 / critic 128, batch 64: one CUDA graph + fused Adam / Polyak",
+         metric="us_per_train_step", value=1e3 * dgms, eager_us=1e3 * dms)
+    del dagent, dreplay
+
     # ------------------------------------------------------------------ cfg 2b: batch-1 actor forward
     x1 = torch.randn(1, 4, device=dev)
     h1 = torch.zeros(1, 8, device=dev)

@@ -53,6 +53,10 @@ int bwd(const float*, const float*, const float*, const float*, const float*, co
         int64_t, int, int, int, int, int, int, void*, int64_t, cudaStream_t);
 int64_t bwd_workspace_bytes(int, int, int, int);
 }  // namespace tc
+namespace ncp_tc {
+bool has_path(int I, int Ni, int Nc, int O);
+int fwd(const float*, const float*, float*, int64_t, int, int, int, int, cudaStream_t);
+}  // namespace ncp_tc
 namespace generic {
 int liquid_fwd(const float*, const float*, const float*, float*, float*, int64_t, int, int, int, int, int, cudaStream_t);
 int64_t liquid_bwd_workspace_bytes(int, int, int, int);
@@ -154,10 +158,12 @@ extern "C" int vb_liquid_bwd(const float* packed, const float* x, const float* h
 }
 
 extern "C" int vb_ncp_fwd(const float* packed, const float* x, float* y, int64_t B, int I, int Ni, int Nc, int O, int flags, void* stream) {
-    (void)flags;
     VB_CHECK_ARG(dims_ok(I, Ni, Nc, O) && B >= 0, VB_ERR_BAD_DIMS, "vb_ncp_fwd: bad dims");
     VB_CHECK_ARG(packed && x && y, VB_ERR_NULL_POINTER, "vb_ncp_fwd: null pointer");
     if (B == 0) return 0;
+    // tensor-core forward for the critic shapes once the batch fills a few tiles per SM; small batches stay on the tile kernels
+    if (!(flags & (VB_FLAG_FORCE_GENERIC | VB_FLAG_FORCE_FFMA)) && B >= 4096 && ncp_tc::has_path(I, Ni, Nc, O))
+        return ncp_tc::fwd(packed, x, y, B, I, Ni, Nc, O, (cudaStream_t)stream);
     return generic::ncp_fwd(packed, x, y, B, I, Ni, Nc, O, (cudaStream_t)stream);
 }
 
