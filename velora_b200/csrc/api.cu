@@ -53,9 +53,13 @@ int bwd(const float*, const float*, const float*, const float*, const float*, co
         int64_t, int, int, int, int, int, int, void*, int64_t, cudaStream_t);
 int64_t bwd_workspace_bytes(int, int, int, int);
 }  // namespace tc
+// the tensor-core critic kernels take over once the batch fills a few 128-sample tiles per SM
+static constexpr int64_t kNcpTcMinBatch = 4096;
 namespace ncp_tc {
 bool has_path(int I, int Ni, int Nc, int O);
 int fwd(const float*, const float*, float*, int64_t, int, int, int, int, cudaStream_t);
+int bwd(const float*, const float*, const float*, float*, float*, int64_t, int, int, int, int, void*, int64_t, cudaStream_t);
+int64_t bwd_workspace_bytes(int, int, int, int);
 }  // namespace ncp_tc
 namespace generic {
 int liquid_fwd(const float*, const float*, const float*, float*, float*, int64_t, int, int, int, int, int, cudaStream_t);
@@ -115,9 +119,9 @@ extern "C" int64_t vb_liquid_bwd_workspace_bytes(int I, int Ni, int Nc, int O, i
     return max64(max64(g, s), t);
 }
 extern "C" int64_t vb_ncp_bwd_workspace_bytes(int I, int Ni, int Nc, int O, int64_t B) {
-    (void)B;
     if (!dims_ok(I, Ni, Nc, O)) return VB_ERR_BAD_DIMS;
-    return generic::ncp_bwd_workspace_bytes(I, Ni, Nc, O);
+    int64_t t = (B >= kNcpTcMinBatch && ncp_tc::has_path(I, Ni, Nc, O)) ? ncp_tc::bwd_workspace_bytes(I, Ni, Nc, O) : 0;
+    return max64(generic::ncp_bwd_workspace_bytes(I, Ni, Nc, O), t);
 }
 
 extern "C" int vb_liquid_fwd(const float* packed, const float* x, const float* h0, float* y, float* h_traj,
@@ -162,19 +166,20 @@ extern "C" int vb_ncp_fwd(const float* packed, const float* x, float* y, int64_t
     VB_CHECK_ARG(packed && x && y, VB_ERR_NULL_POINTER, "vb_ncp_fwd: null pointer");
     if (B == 0) return 0;
     // tensor-core forward for the critic shapes once the batch fills a few tiles per SM; small batches stay on the tile kernels
-    if (!(flags & (VB_FLAG_FORCE_GENERIC | VB_FLAG_FORCE_FFMA)) && B >= 4096 && ncp_tc::has_path(I, Ni, Nc, O))
+    if (!(flags & (VB_FLAG_FORCE_GENERIC | VB_FLAG_FORCE_FFMA)) && B >= kNcpTcMinBatch && ncp_tc::has_path(I, Ni, Nc, O))
         return ncp_tc::fwd(packed, x, y, B, I, Ni, Nc, O, (cudaStream_t)stream);
     return generic::ncp_fwd(packed, x, y, B, I, Ni, Nc, O, (cudaStream_t)stream);
 }
 
 extern "C" int vb_ncp_bwd(const float* packed, const float* x, const float* dy, float* dx, float* dpacked,
                           int64_t B, int I, int Ni, int Nc, int O, void* workspace, int64_t workspace_bytes, int flags, void* stream) {
-    (void)flags;
     VB_CHECK_ARG(dims_ok(I, Ni, Nc, O) && B >= 0, VB_ERR_BAD_DIMS, "vb_ncp_bwd: bad dims");
     VB_CHECK_ARG(packed && x && dy && dpacked, VB_ERR_NULL_POINTER, "vb_ncp_bwd: null pointer");
     if (B == 0) {
         VB_CUDA(cudaMemsetAsync(dpacked, 0, (size_t)NcpLayout(I, Ni, Nc, O).f_total * 4, (cudaStream_t)stream));
         return 0;
     }
+    if (!(flags & (VB_FLAG_FORCE_GENERIC | VB_FLAG_FORCE_FFMA)) && B >= kNcpTcMinBatch && ncp_tc::has_path(I, Ni, Nc, O))
+        return ncp_tc::bwd(packed, x, dy, dx, dpacked, B, I, Ni, Nc, O, workspace, workspace_bytes, (cudaStream_t)stream);
     return generic::ncp_bwd(packed, x, dy, dx, dpacked, B, I, Ni, Nc, O, workspace, workspace_bytes, (cudaStream_t)stream);
 }
