@@ -213,7 +213,7 @@ struct BwdSmem {
     static constexpr int S_D = S_A + 3 * C::KC * PLANE;         // du2: 3 parts x DC planes; the [du2_3; *] stack over-reads DC planes
     static constexpr int S_WB = S_D + 3 * DC * PLANE;           // layer-2 operand (finite bytes behind the du2 planes)
     static constexpr int S_STRIP = S_WB + C::KC * 3 * C::NP * 16;   // fp32 strips: a2 [8 EC][SS], x [I][SS], dy [O][SS]
-    static constexpr int S_W1 = S_STRIP + (8 * C::EC + C::I + C::O) * SS * 4;
+    static constexpr int S_W1 = S_STRIP + (8 * C::EC + 2 * C::I + C::O) * SS * 4;     // + dx partial sums [I][SS]
     static constexpr int S_W3 = S_W1 + (C::I + 1) * C::KF * 4;
     static constexpr int S_BAR = S_W3 + (C::O * C::NP + 4) * 4;
     static constexpr int BYTES = S_BAR + 64;
@@ -225,7 +225,7 @@ struct BwdSmem {
 };
 
 template <class C>
-__global__ void __launch_bounds__(TM, 1) ncp_bwd_tc_kernel(const float* __restrict__ packed, const float* __restrict__ x,
+__global__ void __launch_bounds__(2 * TM, 1) ncp_bwd_tc_kernel(const float* __restrict__ packed, const float* __restrict__ x,
                                                            const float* __restrict__ dy, float* __restrict__ dx,
                                                            float* __restrict__ partials, float* __restrict__ d3buf, int64_t B) {
     using S = BwdSmem<C>;
@@ -238,15 +238,21 @@ __global__ void __launch_bounds__(TM, 1) ncp_bwd_tc_kernel(const float* __restri
     float* a2s = reinterpret_cast<float*>(smem + S::S_STRIP);             // [8 EC][SS]
     float* xs = a2s + 8 * C::EC * SS;                                     // [I][SS]
     float* dys = xs + C::I * SS;                                          // [O][SS]
+    float* dxs = dys + C::O * SS;                                         // [I][SS]: dx partial sums of the second half
     float* w1s = reinterpret_cast<float*>(smem + S::S_W1);
     float* w3s = reinterpret_cast<float*>(smem + S::S_W3);
     uint64_t* bar1 = reinterpret_cast<uint64_t*>(smem + S::S_BAR);        // u2 ready
     uint64_t* bar2 = bar1 + 1;                                            // da1 ready
     uint64_t* bar3 = bar1 + 2;                                            // dW batch done
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::S_BAR + 32);
+    // TWO threads per sample: thread (row, half) works on the plane chunks c = half, half + 2, ...; both halves of a row sit in
+    // warps w and w + 4, which address the same TMEM lanes.  With the accumulators taking all 512 TMEM columns only one CTA
+    // fits per SM, so the second half doubles the warps that hide each other's latency.
+    constexpr int NT = 2 * TM;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row = tid & (TM - 1), half = tid >> 7;
 
-    for (int item = tid; item < C::NP * C::KC; item += TM) {
+    for (int item = tid; item < C::NP * C::KC; item += NT) {
         const int n = item % C::NP, kc = item / C::NP;
         float v[8];
 #pragma unroll
@@ -263,19 +269,18 @@ __global__ void __launch_bounds__(TM, 1) ncp_bwd_tc_kernel(const float* __restri
 #pragma unroll
         for (int pb = 0; pb < 3; ++pb) q[kc * (3 * C::NP) + pb * C::NP + n] = part[pb];
     }
-    for (int e = tid; e < (C::I + 1) * C::KF; e += TM) {
+    for (int e = tid; e < (C::I + 1) * C::KF; e += NT) {
         const int i = e / C::KF, j = e % C::KF;
         w1s[e] = j < C::NI ? __ldg(packed + (i < C::I ? C::W1_T + i * C::NIp : C::B1) + j) : 0.f;
     }
-    for (int e = tid; e < C::O * C::NP + 4; e += TM) {
+    for (int e = tid; e < C::O * C::NP + 4; e += NT) {
         const int o = e / C::NP, j = e % C::NP;
         w3s[e] = e < C::O * C::NP ? (j < C::NC ? __ldg(packed + C::W3 + o * C::NCp + j) : 0.f)
                                   : (e - C::O * C::NP < C::O ? __ldg(packed + C::B3 + e - C::O * C::NP) : 0.f);
     }
     // fp32 flush buffer of the two dW2 accumulators: element (lane = thread, column c) at ((c / 4) * TM + lane) * 4 + c % 4
-    float* d3row = d3buf + (int64_t)blockIdx.x * (TM * S::D3_COLS) + tid * 4;
-#pragma unroll 4
-    for (int q = 0; q < S::D3_COLS / 4; ++q) *reinterpret_cast<float4*>(d3row + q * (TM * 4)) = make_float4(0.f, 0.f, 0.f, 0.f);
+    float* d3row = d3buf + (int64_t)blockIdx.x * (TM * S::D3_COLS) + row * 4;
+    for (int q = half; q < S::D3_COLS / 4; q += 2) *reinterpret_cast<float4*>(d3row + q * (TM * 4)) = make_float4(0.f, 0.f, 0.f, 0.f);
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -291,7 +296,7 @@ __global__ void __launch_bounds__(TM, 1) ncp_bwd_tc_kernel(const float* __restri
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t a_addr = smem_u32(aP), d_addr = smem_u32(dP), w_addr = smem_u32(wB);
     uint32_t ph = 0;
     int since_flush = 0;
@@ -303,13 +308,13 @@ __global__ void __launch_bounds__(TM, 1) ncp_bwd_tc_kernel(const float* __restri
     float acc3[C::O], accb3[C::O];
 #pragma unroll
     for (int o = 0; o < C::O; ++o) { acc3[o] = 0.f; accb3[o] = 0.f; }
-    static_assert(C::KF + 8 * C::EC <= 2 * TM, "row-sum ownership");
-    const int n3 = tid - (TM - 8 * C::EC);          // dW3 row of this thread (threads TM - 8 EC .. TM - 1), else negative
+    static_assert(C::KF <= TM && 8 * C::EC <= TM, "row-sum ownership");
+    const int n3 = (half == 1 && row < 8 * C::EC) ? row : -1;      // dW3 row of this thread (second half of the CTA), else negative
 
     auto flush_dw = [&]() {
         tc_fence_after();
 #pragma unroll 1
-        for (int g = 0; g < S::D3_COLS / 32; ++g) {
+        for (int g = half; g < S::D3_COLS / 32; g += 2) {
             float v[32];
             tmem_ld32(taddr + S::T_DWA + 32 * g, v);
 #pragma unroll
@@ -323,20 +328,22 @@ __global__ void __launch_bounds__(TM, 1) ncp_bwd_tc_kernel(const float* __restri
 
     const int64_t n_tiles = (B + TM - 1) / TM;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t b = tile * TM + tid;
+        const int64_t b = tile * TM + row;
         const bool valid = b < B;
         float xr[C::I], dyr[C::O];
 #pragma unroll
         for (int i = 0; i < C::I; ++i) xr[i] = valid ? __ldg(x + b * C::I + i) : 0.f;
 #pragma unroll
         for (int o = 0; o < C::O; ++o) dyr[o] = valid ? __ldg(dy + b * C::O + o) : 0.f;
+        if (half == 0) {
 #pragma unroll
-        for (int i = 0; i < C::I; ++i) xs[i * SS + tid] = xr[i];
+            for (int i = 0; i < C::I; ++i) xs[i * SS + row] = xr[i];
 #pragma unroll
-        for (int o = 0; o < C::O; ++o) dys[o * SS + tid] = dyr[o];
+            for (int o = 0; o < C::O; ++o) dys[o * SS + row] = dyr[o];
+        }
         // ---------------- layer 1 + Mish -> a~1 planes
-#pragma unroll 2
-        for (int c = 0; c < C::KC; ++c) {
+#pragma unroll 1
+        for (int c = half; c < C::KC; c += 2) {
             float u[8];
             {
                 const float4 b0 = *reinterpret_cast<const float4*>(w1s + C::I * C::KF + 8 * c);
@@ -365,7 +372,7 @@ __global__ void __launch_bounds__(TM, 1) ncp_bwd_tc_kernel(const float* __restri
                 if (k == C::NI) a[e] = 1.0f;
                 else if (k > C::NI) a[e] = 0.f;
             }
-            store_chunk3<C::KC>(aP, c, tid, a);
+            store_chunk3<C::KC>(aP, c, row, a);
         }
         fence_async_smem();
         tc_fence_before();
@@ -385,7 +392,7 @@ __global__ void __launch_bounds__(TM, 1) ncp_bwd_tc_kernel(const float* __restri
         tc_fence_after();
         // ---------------- Mish, Mish', du2 = (dy W3) * Mish'(u2) -> du2 planes; a2 -> strip
 #pragma unroll 1
-        for (int c = 0; c < DC; ++c) {
+        for (int c = half; c < DC; c += 2) {
             float du2[8];
             if (c < C::EC) {
                 float s8[8];
@@ -401,7 +408,7 @@ __global__ void __launch_bounds__(TM, 1) ncp_bwd_tc_kernel(const float* __restri
                 for (int e = 0; e < 8; ++e) {
                     float dm;
                     const float a2 = mish_fwd_grad(s8[e], dm);
-                    a2s[(8 * c + e) * SS + tid] = a2;
+                    a2s[(8 * c + e) * SS + row] = a2;
                     float da = 0.f;
 #pragma unroll
                     for (int o = 0; o < C::O; ++o) da = fmaf(dyr[o], w3s[o * C::NP + 8 * c + e], da);
@@ -411,7 +418,7 @@ __global__ void __launch_bounds__(TM, 1) ncp_bwd_tc_kernel(const float* __restri
 #pragma unroll
                 for (int e = 0; e < 8; ++e) du2[e] = 0.f;
             }
-            store_chunk3<DC>(dP, c, tid, du2);
+            store_chunk3<DC>(dP, c, row, du2);
         }
         fence_async_smem();
         tc_fence_before();
@@ -455,7 +462,7 @@ __global__ void __launch_bounds__(TM, 1) ncp_bwd_tc_kernel(const float* __restri
 #pragma unroll
         for (int i = 0; i < C::I; ++i) dxr[i] = 0.f;
 #pragma unroll 1
-        for (int c = 0; c < C::KC; ++c) {
+        for (int c = half; c < C::KC; c += 2) {
             float u[8], da1[8];
             tmem_ld8(taddr + 8 * c, da1);
             {
@@ -477,17 +484,21 @@ __global__ void __launch_bounds__(TM, 1) ncp_bwd_tc_kernel(const float* __restri
                 float dm;
                 (void)mish_fwd_grad(u[e], dm);
                 const float du1 = (8 * c + e < C::NI) ? da1[e] * dm : 0.f;
-                du1s[(8 * c + e) * SS + tid] = du1;
+                du1s[(8 * c + e) * SS + row] = du1;
 #pragma unroll
                 for (int i = 0; i < C::I; ++i) dxr[i] = fmaf(du1, w[i][e], dxr[i]);
             }
         }
-        if (valid && dx) {
+        if (half == 1) {          // the two halves hold partial sums over their chunks
 #pragma unroll
-            for (int i = 0; i < C::I; ++i) dx[b * C::I + i] = dxr[i];
+            for (int i = 0; i < C::I; ++i) dxs[i * SS + row] = dxr[i];
         }
         tc_fence_before();
         __syncthreads();
+        if (half == 0 && valid && dx) {
+#pragma unroll
+            for (int i = 0; i < C::I; ++i) dx[b * C::I + i] = dxr[i] + dxs[i * SS + row];
+        }
         // ---------------- row sums: dW1 / db1 (thread j < KF), dW3 / db3 (the last 8 EC threads)
         if (tid < C::KF) {
             const float4* dr = reinterpret_cast<const float4*>(du1s + tid * SS);
@@ -525,7 +536,7 @@ __global__ void __launch_bounds__(TM, 1) ncp_bwd_tc_kernel(const float* __restri
 
     // ---------------- per-CTA partial gradient row (F layout of NcpLayout)
     float* prow = partials + (int64_t)blockIdx.x * C::F_TOTAL;
-    for (int idx = tid; idx < C::F_TOTAL; idx += TM) prow[idx] = 0.f;
+    for (int idx = tid; idx < C::F_TOTAL; idx += NT) prow[idx] = 0.f;
     __syncthreads();
     if (tid < C::NI) {
 #pragma unroll
@@ -544,7 +555,7 @@ __global__ void __launch_bounds__(TM, 1) ncp_bwd_tc_kernel(const float* __restri
         const float* d3 = d3buf + (int64_t)blockIdx.x * (TM * S::D3_COLS);
         auto at = [&](int row, int col) { return d3[((col >> 2) * TM + row) * 4 + (col & 3)]; };
         // accumulator A: rows [0, NP) = du2 part 1, [NP, 2 NP) = part 2; columns pb * KF + k.  Accumulator B: rows [0, NP) = part 3, columns 3 KF + k.
-        for (int e = tid; e < C::NC * (C::NI + 1); e += TM) {
+        for (int e = tid; e < C::NC * (C::NI + 1); e += NT) {
             const int n = e / (C::NI + 1), k = e % (C::NI + 1);
             float acc = at(C::NP + n, 2 * C::KF + k);                 // (2,3)
             acc += at(n, 2 * C::KF + k);                              // (1,3)
@@ -619,7 +630,7 @@ static int launch_bwd(const float* packed, const float* x, const float* dy, floa
                       void* ws, int64_t ws_bytes, cudaStream_t stream) {
     using S = BwdSmem<C>;
     LaunchCfg cfg;
-    int rc = cached_launch_cfg(ncp_bwd_tc_kernel<C>, TM, S::BYTES, &cfg);
+    int rc = cached_launch_cfg(ncp_bwd_tc_kernel<C>, 2 * TM, S::BYTES, &cfg);
     if (rc) return rc;
     const int64_t n_tiles = (B + TM - 1) / TM;
     const int64_t cap = device_sms();
@@ -629,7 +640,7 @@ static int launch_bwd(const float* packed, const float* x, const float* dy, floa
                  (long long)need);
     float* partials = reinterpret_cast<float*>(ws);
     float* d3buf = partials + (int64_t)grid * C::F_TOTAL;
-    ncp_bwd_tc_kernel<C><<<grid, TM, S::BYTES, stream>>>(packed, x, dy, dx, partials, d3buf, B);
+    ncp_bwd_tc_kernel<C><<<grid, 2 * TM, S::BYTES, stream>>>(packed, x, dy, dx, partials, d3buf, B);
     VB_LAUNCH_CHECK();
     reduce_rows_tc_kernel<<<(C::F_TOTAL + 31) / 32, 1024, 0, stream>>>(partials, grid, C::F_TOTAL, dpacked);
     VB_LAUNCH_CHECK();
