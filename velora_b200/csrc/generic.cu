@@ -34,6 +34,9 @@ static Plan make_plan(int rows, int packed_floats, int grad_floats, bool backwar
     const int sms = device_sms() > 0 ? device_sms() : 148;
     for (int bm : {128, 64, 32, 16, 8}) {
         int act = rows * (bm + 4) * 4;
+        // small batches: prefer small tiles so that the few rows spread over many SMs (batch 64 on 32-row tiles is 2 CTAs, each
+        // walking the whole network serially: 12 / 24 us per critic forward / backward)
+        if (big_B > 0 && bm > 8 && (big_B + bm - 1) / bm < sms / 2) continue;
         if (bm > 32) {   // only while two CTAs (16 warps) still fit per SM: the phases of a tile are separated by CTA barriers
             if (big_B < (int64_t)bm * sms) continue;
             const int g = (backward && grad_floats <= kModeAMaxFloats) ? grad_floats * 4 : 0;
