@@ -170,14 +170,17 @@ def main():
     for B in ([131072] if args.quick else [131072, 1_000_000]):
         torch.manual_seed(1)
         idx = torch.randint(0, big.buffer.size, (B,), device=dev)
-        gms = gpu_time_ms(lambda: big.buffer.gather(idx), warmup=5, iters=20)
+        big.buffer.use_shadow = False
+        pms = gpu_time_ms(lambda: big.buffer.gather(idx), warmup=5, iters=20)      # six separate arrays
+        big.buffer.use_shadow = True
+        gms = gpu_time_ms(lambda: big.buffer.gather(idx), warmup=5, iters=20)      # packed shadow table (default)
         gbs = 160.0 * B / (gms * 1e-3) / 1e9
         ref_ms = gpu_time_ms(lambda: [getattr(big.buffer, k)[idx] for k in ("states", "actions", "rewards", "next_states", "dones", "hiddens")],
                              warmup=3, iters=10)
         emit(config=f"cfg5 ReplayBuffer(1M,4,1,8) gather, batch {B}", metric="transitions_per_s", value=B / (gms * 1e-3), ms=gms,
              roofline={"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
                        "algorithmic_bytes_per_transition": 160},
-             torch_six_index_kernels_ms=ref_ms)
+             six_array_gather_ms=pms, torch_six_index_kernels_ms=ref_ms)
         tms = gpu_time_ms(lambda: big._train_step(B), warmup=3, iters=10)
         emit(config=f"cfg5 sample + NeuroFlowCT update, batch {B}, 1 GPU", metric="transitions_per_s", value=B / (tms * 1e-3), ms=tms)
         bigg = make_agent(dev, 1_000_000, capturable=True, fused=True)

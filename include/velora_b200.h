@@ -160,6 +160,16 @@ int vb_ncp_unpack_grads(const float* dpacked, const void* const* m, int m_type,
 int vb_gather_rows(const float* const* src, float* const* dst, const int* row_floats, int n_arrays,
                    const int64_t* idx, int64_t B, int64_t n_rows, void* stream);
 
+/* Packed shadow table of the replay buffer: row r = the rows r of all arrays back to back at the given offsets
+ * (floats), row_stride floats apart.  vb_pack_rows refreshes `n` rows - row0 .. row0+n-1, or the int64 device vector `rows`
+ * when it is not NULL - from the arrays after BufferBase.add / add_multi (velora/buffer/base.py:73-143) wrote them;
+ * vb_gather_packed is vb_gather_rows reading that table: one run of consecutive sectors per sampled transition instead of
+ * one sector in each of six arrays. */
+int vb_pack_rows(const float* const* src, const int* row_floats, const int* offsets, int n_arrays, float* packed,
+                 int row_stride, const int64_t* rows, int64_t row0, int64_t n, int64_t capacity, void* stream);
+int vb_gather_packed(const float* packed, int row_stride, const int* offsets, float* const* dst, const int* row_floats,
+                     int n_arrays, const int64_t* idx, int64_t B, int64_t n_rows, void* stream);
+
 /* ------------------------------------------------------------------------------------------------ optimizer */
 /* torch.optim.Adam step (no weight decay / amsgrad; modules.py:116-118, 409-415, 715-717 construct it with defaults) over
  * n_tensors fp32 tensors in one launch.  Host arrays of device pointers; steps[k] is the tensor's device-resident step

@@ -79,3 +79,56 @@ def test_gather_full_size_vs_oracle(S, A, H):
     ident = buf.gather(torch.arange(cap, device="cuda"))
     for k in FIELDS:
         assert torch.equal(getattr(ident, k), getattr(buf, k))
+
+
+def test_shadow_table_tracks_every_write_path():
+    """The packed shadow table the gather reads stays identical to torch indexing of the six arrays through add, add_multi
+    (with wrap-around), direct tensor writes and state reassignment; use_shadow=False reads the arrays themselves."""
+    from velora_b200.buffer import ReplayBuffer
+
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev).manual_seed(0)
+    buf = ReplayBuffer(100, 4, 1, 8, device=dev)
+
+    def check():
+        idx = torch.randint(0, buf.size, (257,), device=dev, generator=g)
+        for shadow in (True, False):
+            buf.use_shadow = shadow
+            got = buf.gather(idx)
+            for name in ("states", "actions", "rewards", "next_states", "dones", "hiddens"):
+                assert torch.equal(getattr(got, name), getattr(buf, name)[idx]), (name, shadow)
+        buf.use_shadow = True
+
+    def rnd(*shape):
+        return torch.randn(*shape, device=dev, generator=g)
+
+    buf.add_multi(rnd(30, 4), rnd(30, 1), rnd(30), rnd(30, 4), (rnd(30) > 0), rnd(30, 8))
+    check()                                      # first gather builds the table
+    assert buf._shadow_current()
+    for _ in range(5):
+        buf.add(rnd(4), rnd(1), 1.5, rnd(4), False, rnd(8))
+    assert buf._shadow_current()                 # row-wise refresh, no rebuild
+    check()
+    buf.add_multi(rnd(90, 4), rnd(90, 1), rnd(90), rnd(90, 4), (rnd(90) > 0), rnd(90, 8))   # wraps around the ring
+    assert buf.size == 100 and buf._shadow_current()
+    check()
+    buf.states.mul_(2.0)                         # written behind the table's back
+    assert not buf._shadow_current()
+    check()
+    buf.hiddens = buf.hiddens.clone() + 1.0      # reassigned (what load() does)
+    check()
+
+
+def test_packed_gather_bit_exact_at_scale():
+    from velora_b200.buffer import ReplayBuffer
+
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev).manual_seed(1)
+    buf = ReplayBuffer(1_000_000, 4, 1, 8, device=dev)
+    for name in ("states", "actions", "rewards", "next_states", "dones", "hiddens"):
+        getattr(buf, name).copy_(torch.randn(getattr(buf, name).shape, device=dev, generator=g))
+    buf.size = buf.capacity
+    idx = torch.randint(0, buf.size, (1_000_000,), device=dev, generator=g)
+    got = buf.gather(idx)
+    for name in ("states", "actions", "rewards", "next_states", "dones", "hiddens"):
+        assert torch.equal(getattr(got, name), getattr(buf, name)[idx]), name

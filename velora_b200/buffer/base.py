@@ -33,17 +33,47 @@ class BufferBase:
         widths = dict(states=state_dim, actions=action_dim, rewards=1, next_states=state_dim, dones=1, hiddens=hidden_dim)
         for name in FIELDS:
             setattr(self, name, torch.zeros((capacity, widths[name]), device=device))
+        # packed shadow table read by the fused gather (one run of sectors per transition); built lazily on CUDA, refreshed row-wise
+        # by add / add_multi, rebuilt when the six arrays (the truth: state_dict, save / load) were written from outside
+        self._shadow = None
+        self._shadow_key = None
+
+    # ------------------------------------------------------------------ packed shadow table
+    def _arrays_key(self):
+        return tuple((id(getattr(self, name)), getattr(self, name)._version) for name in FIELDS)
+
+    def _shadow_current(self) -> bool:
+        return self._shadow is not None and self._shadow_key == self._arrays_key()
+
+    def _refresh_shadow(self, rows=None, row0: int = 0, n: int | None = None) -> None:
+        from velora_b200 import functional as VF
+
+        arrays = [getattr(self, name) for name in FIELDS]
+        if self._shadow is None:
+            self._shadow_offsets, self._shadow_stride = VF.packed_row_layout([a.shape[1] for a in arrays])
+            self._shadow = torch.zeros((self.capacity, self._shadow_stride), device=arrays[0].device)
+        VF.pack_rows(arrays, self._shadow, self._shadow_offsets, self._shadow_stride, rows=rows, row0=row0, n=n)
+        self._shadow_key = self._arrays_key()
+
+    def _shadow_table(self):
+        """The packed table, current for rows [0, size).  Rebuilt in full when the arrays changed behind its back."""
+        if not self._shadow_current():
+            self._refresh_shadow(row0=0, n=max(self.size, 1))
+        return self._shadow, self._shadow_offsets, self._shadow_stride
 
     # ------------------------------------------------------------------ writes
     def add(self, state: torch.Tensor, action: torch.Tensor, reward: float, next_state: torch.Tensor, done: bool, hidden: torch.Tensor) -> None:
         """Appends one transition (overwriting the oldest once full)."""
         i = self.position
+        tracked = self._shadow_current()
         self.states[i] = state.to(torch.float32)
         self.actions[i] = action
         self.rewards[i] = reward
         self.next_states[i] = next_state.to(torch.float32)
         self.dones[i] = done
         self.hiddens[i] = hidden
+        if tracked:
+            self._refresh_shadow(row0=i, n=1)
         self.position = (i + 1) % self.capacity
         self.size = min(self.size + 1, self.capacity)
 
@@ -58,12 +88,15 @@ class BufferBase:
             return t.unsqueeze(-1) if t.dim() == 1 else t
 
         f32 = torch.float32
+        tracked = self._shadow_current()
         self.states[rows] = states.to(f32)
         self.actions[rows] = col(actions).to(f32)
         self.rewards[rows] = col(rewards).to(f32)
         self.next_states[rows] = next_states.to(f32)
         self.dones[rows] = col(dones).to(f32)
         self.hiddens[rows] = hiddens
+        if tracked:
+            self._refresh_shadow(rows=rows)
         self.position = end % self.capacity
         self.size = min(self.size + n, self.capacity)
 

@@ -21,6 +21,9 @@ if TYPE_CHECKING:  # pragma: no cover
 class ReplayBuffer(BufferBase):
     def __init__(self, capacity: int, state_dim: int, action_dim: int, hidden_dim: int, *, device: torch.device | None = None) -> None:
         super().__init__(capacity, state_dim, action_dim, hidden_dim, device=device)
+        # sample from the packed shadow table (velora_b200/buffer/base.py): ~1.3x fewer DRAM sectors per transition.  Set to False to
+        # read the six arrays directly (what a captured CUDA graph does: it must not depend on host-side freshness tracking).
+        self.use_shadow = True
 
     def config(self):
         from velora_b200.buffer.config import BufferConfig
@@ -43,7 +46,11 @@ class ReplayBuffer(BufferBase):
             raise RuntimeError(
                 "velora_b200.ReplayBuffer.sample has no CPU path: build the buffer with device=torch.device('cuda')"
             )
-        out = VF.gather_rows(arrays, indices, self.size)
+        if self.use_shadow and not torch.cuda.is_current_stream_capturing():
+            table, offsets, stride = self._shadow_table()
+            out = VF.gather_packed(table, offsets, stride, [a.shape[1] for a in arrays], indices, self.size)
+        else:
+            out = VF.gather_rows(arrays, indices, self.size)
         return BatchExperience(*out)
 
     def warm(self, agent: "Any", n_samples: int, num_envs: int = 8) -> None:

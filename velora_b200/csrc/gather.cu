@@ -13,6 +13,8 @@ struct GatherArgs {
     const float* src[kMaxGatherArrays];
     float* dst[kMaxGatherArrays];
     int row_floats[kMaxGatherArrays];
+    int src_stride[kMaxGatherArrays];   // floats between source rows (= row_floats for the six separate arrays, = the packed row
+                                        // length when the sources are columns of one packed shadow table)
     int vec[kMaxGatherArrays];   // 4, 2 or 1 floats per access
     int n;
 };
@@ -51,7 +53,7 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(GatherArgs a, const in
         for (int k = 0; k < kMaxGatherArrays; ++k) {
             if (k < a.n) {
                 const int n = a.row_floats[k];
-                const float* s = a.src[k] + rs * n;
+                const float* s = a.src[k] + rs * a.src_stride[k];
                 float* d = a.dst[k] + b * n;
                 if (a.vec[k] == 4) copy_row<4>(s, d, n, ok);
                 else if (a.vec[k] == 2) copy_row<2>(s, d, n, ok);
@@ -65,21 +67,23 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(GatherArgs a, const in
 
 using namespace vb;
 
-extern "C" int vb_gather_rows(const float* const* src, float* const* dst, const int* row_floats, int n_arrays,
-                              const int64_t* idx, int64_t B, int64_t n_rows, void* stream) {
-    VB_CHECK_ARG(src && dst && row_floats && idx, VB_ERR_NULL_POINTER, "vb_gather_rows: null pointer");
-    VB_CHECK_ARG(n_arrays >= 1 && n_arrays <= kMaxGatherArrays, VB_ERR_BAD_DIMS, "vb_gather_rows: n_arrays=%d not in [1,%d]", n_arrays, kMaxGatherArrays);
-    VB_CHECK_ARG(B >= 0 && n_rows >= 0, VB_ERR_BAD_DIMS, "vb_gather_rows: negative size");
+static int gather_impl(const float* const* src, const int* src_strides, float* const* dst, const int* row_floats, int n_arrays,
+                       const int64_t* idx, int64_t B, int64_t n_rows, void* stream, const char* who) {
+    VB_CHECK_ARG(src && dst && row_floats && idx, VB_ERR_NULL_POINTER, "%s: null pointer", who);
+    VB_CHECK_ARG(n_arrays >= 1 && n_arrays <= kMaxGatherArrays, VB_ERR_BAD_DIMS, "%s: n_arrays=%d not in [1,%d]", who, n_arrays, kMaxGatherArrays);
+    VB_CHECK_ARG(B >= 0 && n_rows >= 0, VB_ERR_BAD_DIMS, "%s: negative size", who);
     if (B == 0) return 0;
     GatherArgs a;
     a.n = n_arrays;
-    for (int k = 0; k < kMaxGatherArrays; ++k) { a.src[k] = nullptr; a.dst[k] = nullptr; a.row_floats[k] = 0; a.vec[k] = 1; }
+    for (int k = 0; k < kMaxGatherArrays; ++k) { a.src[k] = nullptr; a.dst[k] = nullptr; a.row_floats[k] = 0; a.src_stride[k] = 0; a.vec[k] = 1; }
     for (int k = 0; k < n_arrays; ++k) {
-        VB_CHECK_ARG(src[k] && dst[k] && row_floats[k] > 0, VB_ERR_NULL_POINTER, "vb_gather_rows: bad array %d", k);
+        VB_CHECK_ARG(src[k] && dst[k] && row_floats[k] > 0, VB_ERR_NULL_POINTER, "%s: bad array %d", who, k);
         a.src[k] = src[k]; a.dst[k] = dst[k]; a.row_floats[k] = row_floats[k];
+        a.src_stride[k] = src_strides ? src_strides[k] : row_floats[k];
+        VB_CHECK_ARG(a.src_stride[k] >= row_floats[k], VB_ERR_BAD_DIMS, "%s: source stride of array %d shorter than its rows", who, k);
         uintptr_t al = reinterpret_cast<uintptr_t>(src[k]) | reinterpret_cast<uintptr_t>(dst[k]);
-        if ((row_floats[k] & 3) == 0 && (al & 15) == 0) a.vec[k] = 4;
-        else if ((row_floats[k] & 1) == 0 && (al & 7) == 0) a.vec[k] = 2;
+        if ((row_floats[k] & 3) == 0 && (a.src_stride[k] & 3) == 0 && (al & 15) == 0) a.vec[k] = 4;
+        else if ((row_floats[k] & 1) == 0 && (a.src_stride[k] & 1) == 0 && (al & 7) == 0) a.vec[k] = 2;
     }
     int sms = device_sms();
     if (sms <= 0) sms = 148;
@@ -89,4 +93,70 @@ extern "C" int vb_gather_rows(const float* const* src, float* const* dst, const 
     gather_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, idx, B, n_rows);
     VB_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" int vb_gather_rows(const float* const* src, float* const* dst, const int* row_floats, int n_arrays,
+                              const int64_t* idx, int64_t B, int64_t n_rows, void* stream) {
+    return gather_impl(src, nullptr, dst, row_floats, n_arrays, idx, B, n_rows, stream, "vb_gather_rows");
+}
+
+// ------------------------------------------------------------------------------------------------ packed shadow table
+// One row per transition holding all arrays' rows back to back: a sampled transition is then ONE run of consecutive sectors
+// (80 B = 3 sectors for the reference's 19 floats) instead of one 32-byte sector in each of six arrays (192 B of DRAM traffic
+// for 76 useful bytes).  The six public arrays stay the truth; the shadow is refreshed for the rows that were written.
+namespace vb {
+struct PackRowsArgs {
+    const float* src[kMaxGatherArrays];
+    int row_floats[kMaxGatherArrays];
+    int offset[kMaxGatherArrays];
+    int n;
+};
+__global__ void __launch_bounds__(256) pack_rows_kernel(PackRowsArgs a, float* __restrict__ packed, int row_stride,
+                                                        const int64_t* __restrict__ rows, int64_t row0, int64_t n_rows_to_write,
+                                                        int64_t capacity, int total_floats) {
+    const int64_t total = n_rows_to_write * total_floats;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = e / total_floats;
+        int c = (int)(e - i * total_floats);
+        int64_t r = rows ? __ldg(rows + i) : row0 + i;
+        if (r < 0 || r >= capacity) continue;
+        int k = 0;
+        while (k + 1 < a.n && c >= a.row_floats[k]) { c -= a.row_floats[k]; ++k; }
+        packed[r * row_stride + a.offset[k] + c] = __ldg(a.src[k] + r * a.row_floats[k] + c);
+    }
+}
+}  // namespace vb
+
+extern "C" int vb_pack_rows(const float* const* src, const int* row_floats, const int* offsets, int n_arrays, float* packed,
+                            int row_stride, const int64_t* rows, int64_t row0, int64_t n, int64_t capacity, void* stream) {
+    VB_CHECK_ARG(src && row_floats && offsets && packed, VB_ERR_NULL_POINTER, "vb_pack_rows: null pointer");
+    VB_CHECK_ARG(n_arrays >= 1 && n_arrays <= kMaxGatherArrays && row_stride > 0 && n >= 0 && capacity >= 0, VB_ERR_BAD_DIMS, "vb_pack_rows: bad sizes");
+    if (n == 0) return 0;
+    PackRowsArgs a;
+    a.n = n_arrays;
+    int total = 0;
+    for (int k = 0; k < kMaxGatherArrays; ++k) { a.src[k] = nullptr; a.row_floats[k] = 0; a.offset[k] = 0; }
+    for (int k = 0; k < n_arrays; ++k) {
+        VB_CHECK_ARG(src[k] && row_floats[k] > 0 && offsets[k] >= 0 && offsets[k] + row_floats[k] <= row_stride, VB_ERR_BAD_DIMS,
+                     "vb_pack_rows: array %d does not fit the packed row", k);
+        a.src[k] = src[k]; a.row_floats[k] = row_floats[k]; a.offset[k] = offsets[k];
+        total += row_floats[k];
+    }
+    int sms = device_sms();
+    if (sms <= 0) sms = 148;
+    int64_t blocks = (n * total + 255) / 256;
+    int64_t cap = (int64_t)sms * 8;
+    pack_rows_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(a, packed, row_stride, rows, row0, n, capacity, total);
+    VB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int vb_gather_packed(const float* packed, int row_stride, const int* offsets, float* const* dst, const int* row_floats,
+                                int n_arrays, const int64_t* idx, int64_t B, int64_t n_rows, void* stream) {
+    VB_CHECK_ARG(packed && offsets, VB_ERR_NULL_POINTER, "vb_gather_packed: null pointer");
+    VB_CHECK_ARG(n_arrays >= 1 && n_arrays <= kMaxGatherArrays && row_stride > 0, VB_ERR_BAD_DIMS, "vb_gather_packed: bad sizes");
+    const float* src[kMaxGatherArrays];
+    int strides[kMaxGatherArrays];
+    for (int k = 0; k < n_arrays; ++k) { src[k] = packed + offsets[k]; strides[k] = row_stride; }
+    return gather_impl(src, strides, dst, row_floats, n_arrays, idx, B, n_rows, stream, "vb_gather_packed");
 }

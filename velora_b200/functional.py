@@ -291,3 +291,51 @@ def gather_rows(arrays: Sequence[torch.Tensor], indices: torch.Tensor, n_rows: i
             "vb_gather_rows",
         )
     return tuple(outs)
+
+
+def packed_row_layout(widths: Sequence[int]) -> Tuple[List[int], int]:
+    """Offsets (floats) of each array's row inside one packed shadow row and the row stride: arrays whose width is a multiple
+    of 4 first (they keep 16-byte alignment and move as 128-bit vectors), then even widths, then the rest; stride padded to 4."""
+    order = sorted(range(len(widths)), key=lambda k: (0 if widths[k] % 4 == 0 else 1 if widths[k] % 2 == 0 else 2, k))
+    offsets, off = [0] * len(widths), 0
+    for k in order:
+        offsets[k] = off
+        off += widths[k]
+    return offsets, (off + 3) // 4 * 4
+
+
+def pack_rows(arrays: Sequence[torch.Tensor], packed: torch.Tensor, offsets: Sequence[int], stride: int,
+              rows: Optional[torch.Tensor] = None, row0: int = 0, n: Optional[int] = None) -> None:
+    """Refresh rows of the packed shadow table from the arrays: the int64 CUDA vector `rows`, or row0 .. row0 + n - 1."""
+    L = _lib.lib()
+    dev = packed.device
+    widths = [a.shape[1] for a in arrays]
+    if rows is not None:
+        rows = rows.to(device=dev, dtype=torch.int64).contiguous()
+        n = rows.numel()
+    with torch.cuda.device(dev):
+        _count(1)
+        _lib.check(
+            L.vb_pack_rows(_lib.ptr_array(list(arrays)), (C.c_int * len(widths))(*widths), (C.c_int * len(widths))(*offsets), len(widths),
+                           _lib.ptr(packed), int(stride), _lib.ptr(rows), int(row0), int(n), int(packed.shape[0]), _lib.stream_ptr(dev)),
+            "vb_pack_rows",
+        )
+
+
+def gather_packed(packed: torch.Tensor, offsets: Sequence[int], stride: int, widths: Sequence[int], indices: torch.Tensor,
+                  n_rows: int) -> Tuple[torch.Tensor, ...]:
+    """gather_rows reading the packed shadow table (one run of sectors per transition)."""
+    L = _lib.lib()
+    dev = packed.device
+    if indices.dtype != torch.int64 or indices.device != dev or not indices.is_contiguous():
+        indices = indices.to(device=dev, dtype=torch.int64).contiguous()
+    B = indices.numel()
+    outs = [torch.empty((B, w), dtype=torch.float32, device=dev) for w in widths]
+    with torch.cuda.device(dev):
+        _count(1)
+        _lib.check(
+            L.vb_gather_packed(_lib.ptr(packed), int(stride), (C.c_int * len(widths))(*offsets), _lib.ptr_array(outs),
+                               (C.c_int * len(widths))(*widths), len(widths), _lib.ptr(indices), B, int(n_rows), _lib.stream_ptr(dev)),
+            "vb_gather_packed",
+        )
+    return tuple(outs)
