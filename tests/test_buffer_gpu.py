@@ -132,3 +132,14 @@ def test_packed_gather_bit_exact_at_scale():
     got = buf.gather(idx)
     for name in ("states", "actions", "rewards", "next_states", "dones", "hiddens"):
         assert torch.equal(getattr(got, name), getattr(buf, name)[idx]), name
+
+
+def test_gather_empty_index_vector():
+    from velora_b200.buffer import ReplayBuffer
+
+    buf = ReplayBuffer(16, 4, 1, 8, device=torch.device("cuda"))
+    buf.size = 16
+    for shadow in (True, False):
+        buf.use_shadow = shadow
+        got = buf.gather(torch.zeros(0, dtype=torch.int64, device="cuda"))
+        assert got.states.shape == (0, 4) and got.hiddens.shape == (0, 8) and got.rewards.shape == (0, 1)

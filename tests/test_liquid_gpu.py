@@ -222,3 +222,19 @@ def test_time_major_flag_rejected_off_the_tensor_core_path():
     h = torch.zeros(8, 3, 8, device="cuda")
     rc = L.vb_liquid_fwd(_lib.ptr(packed), _lib.ptr(x), None, _lib.ptr(y), _lib.ptr(h), 8, 3, 4, 12, 8, 2, None, 0, 2 | 16, None)
     assert rc == -6 and b"time-major" in L.vb_last_error()
+
+
+def test_empty_batch(golden):
+    """Zero rows: outputs are empty, every parameter gradient is exactly zero (what the reference's ops give for B = 0)."""
+    d = golden("liquid")
+    net = _build(d, "actor_seq")
+    dev = torch.device("cuda")
+    y, h = net(torch.zeros(0, 4, device=dev), None)
+    assert y.shape == (0, 2) and h.shape == (0, 8)
+    x = torch.zeros(0, 5, 4, device=dev, requires_grad=True)
+    ys, ht = net.forward_seq(x, None)
+    assert ys.shape == (0, 5, 2) and ht.shape == (0, 5, 8)
+    (ys.sum() + ht.sum()).backward()
+    assert x.grad.shape == (0, 5, 4)
+    for k, p in net.named_parameters():
+        assert p.grad is not None and torch.count_nonzero(p.grad) == 0, k

@@ -111,3 +111,15 @@ def test_ncp_tensor_core_tier_vs_oracle_and_tile_kernels(golden, name, B):
             mask = net.state_dict()[k.replace("weight", "mask")].cpu().numpy()
             assert np.all(tc[k][mask == 0] == 0.0), k
     assert rel_err(tc["y"], tile["y"]) < 2e-6 and rel_err(tc["dx"], tile["dx"]) < 2e-6
+
+
+def test_ncp_empty_batch(golden):
+    d = golden("ncp")
+    net = _build(d, "critic_ct")
+    x = torch.zeros(0, 5, device="cuda", requires_grad=True)
+    y = net(x)
+    assert y.shape == (0, 1)
+    y.sum().backward()
+    assert x.grad.shape == (0, 5)
+    for k, p in net.named_parameters():
+        assert p.grad is not None and torch.count_nonzero(p.grad) == 0, k

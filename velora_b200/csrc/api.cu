@@ -129,8 +129,8 @@ extern "C" int vb_liquid_fwd(const float* packed, const float* x, const float* h
                              void* workspace, int64_t workspace_bytes, int flags, void* stream) {
     (void)workspace; (void)workspace_bytes;
     VB_CHECK_ARG(dims_ok(I, Ni, Nc, O) && B >= 0 && T >= 1, VB_ERR_BAD_DIMS, "vb_liquid_fwd: bad dims B=%lld T=%d (%d,%d,%d,%d)", (long long)B, T, I, Ni, Nc, O);
+    if (B == 0) return 0;      // empty batch: nothing to launch (tensors of zero rows have no storage to point at)
     VB_CHECK_ARG(packed && x && y && h_traj, VB_ERR_NULL_POINTER, "vb_liquid_fwd: null pointer");
-    if (B == 0) return 0;
     if (!(flags & (VB_FLAG_FORCE_GENERIC | VB_FLAG_FORCE_FFMA)) && tc::has_tc_path(I, Ni, Nc, O))
         return tc::fwd(packed, x, h0, y, h_traj, B, T, I, Ni, Nc, O, flags & VB_FLAG_LAYOUT_MASK, (cudaStream_t)stream);
     VB_CHECK_ARG(!(flags & VB_FLAG_LAYOUT_MASK) || T == 1, VB_ERR_LAYOUT,
@@ -146,7 +146,7 @@ extern "C" int vb_liquid_bwd(const float* packed, const float* x, const float* h
                              int64_t B, int T, int I, int Ni, int Nc, int O,
                              void* workspace, int64_t workspace_bytes, int flags, void* stream) {
     VB_CHECK_ARG(dims_ok(I, Ni, Nc, O) && B >= 0 && T >= 1, VB_ERR_BAD_DIMS, "vb_liquid_bwd: bad dims");
-    VB_CHECK_ARG(packed && x && h_traj && dy && dpacked, VB_ERR_NULL_POINTER, "vb_liquid_bwd: null pointer");
+    VB_CHECK_ARG(dpacked && (B == 0 || (packed && x && h_traj && dy)), VB_ERR_NULL_POINTER, "vb_liquid_bwd: null pointer");
     if (B == 0) {
         VB_CUDA(cudaMemsetAsync(dpacked, 0, (size_t)LiquidLayout(I, Ni, Nc, O).f_total * 4, (cudaStream_t)stream));
         return 0;
@@ -163,8 +163,8 @@ extern "C" int vb_liquid_bwd(const float* packed, const float* x, const float* h
 
 extern "C" int vb_ncp_fwd(const float* packed, const float* x, float* y, int64_t B, int I, int Ni, int Nc, int O, int flags, void* stream) {
     VB_CHECK_ARG(dims_ok(I, Ni, Nc, O) && B >= 0, VB_ERR_BAD_DIMS, "vb_ncp_fwd: bad dims");
-    VB_CHECK_ARG(packed && x && y, VB_ERR_NULL_POINTER, "vb_ncp_fwd: null pointer");
     if (B == 0) return 0;
+    VB_CHECK_ARG(packed && x && y, VB_ERR_NULL_POINTER, "vb_ncp_fwd: null pointer");
     // tensor-core forward for the critic shapes once the batch fills a few tiles per SM; small batches stay on the tile kernels
     if (!(flags & (VB_FLAG_FORCE_GENERIC | VB_FLAG_FORCE_FFMA)) && B >= kNcpTcMinBatch && ncp_tc::has_path(I, Ni, Nc, O))
         return ncp_tc::fwd(packed, x, y, B, I, Ni, Nc, O, (cudaStream_t)stream);
@@ -174,7 +174,7 @@ extern "C" int vb_ncp_fwd(const float* packed, const float* x, float* y, int64_t
 extern "C" int vb_ncp_bwd(const float* packed, const float* x, const float* dy, float* dx, float* dpacked,
                           int64_t B, int I, int Ni, int Nc, int O, void* workspace, int64_t workspace_bytes, int flags, void* stream) {
     VB_CHECK_ARG(dims_ok(I, Ni, Nc, O) && B >= 0, VB_ERR_BAD_DIMS, "vb_ncp_bwd: bad dims");
-    VB_CHECK_ARG(packed && x && dy && dpacked, VB_ERR_NULL_POINTER, "vb_ncp_bwd: null pointer");
+    VB_CHECK_ARG(dpacked && (B == 0 || (packed && x && dy)), VB_ERR_NULL_POINTER, "vb_ncp_bwd: null pointer");
     if (B == 0) {
         VB_CUDA(cudaMemsetAsync(dpacked, 0, (size_t)NcpLayout(I, Ni, Nc, O).f_total * 4, (cudaStream_t)stream));
         return 0;

@@ -69,10 +69,10 @@ using namespace vb;
 
 static int gather_impl(const float* const* src, const int* src_strides, float* const* dst, const int* row_floats, int n_arrays,
                        const int64_t* idx, int64_t B, int64_t n_rows, void* stream, const char* who) {
+    VB_CHECK_ARG(B >= 0 && n_rows >= 0, VB_ERR_BAD_DIMS, "%s: negative size", who);
+    if (B == 0) return 0;      // empty index vector: nothing to move
     VB_CHECK_ARG(src && dst && row_floats && idx, VB_ERR_NULL_POINTER, "%s: null pointer", who);
     VB_CHECK_ARG(n_arrays >= 1 && n_arrays <= kMaxGatherArrays, VB_ERR_BAD_DIMS, "%s: n_arrays=%d not in [1,%d]", who, n_arrays, kMaxGatherArrays);
-    VB_CHECK_ARG(B >= 0 && n_rows >= 0, VB_ERR_BAD_DIMS, "%s: negative size", who);
-    if (B == 0) return 0;
     GatherArgs a;
     a.n = n_arrays;
     for (int k = 0; k < kMaxGatherArrays; ++k) { a.src[k] = nullptr; a.dst[k] = nullptr; a.row_floats[k] = 0; a.src_stride[k] = 0; a.vec[k] = 1; }
