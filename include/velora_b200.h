@@ -180,6 +180,14 @@ int vb_adam_multi(float* const* params, const float* const* grads, float* const*
 /* soft_update (velora/utils/torch.py:53-64): target = tau * source + (1 - tau) * target over all tensors in one launch */
 int vb_polyak_multi(float* const* target, const float* const* source, const int64_t* sizes, int n_tensors, float tau, void* stream);
 
+/* The tail of SACActor.forward (velora/models/sac/continuous.py:121-143) after the network: x [B, 2A] = (mean | log_std),
+ * eps [B, A] drawn by the caller (Normal.rsample's noise), scale / bias [A].  Forward writes actions [B, A], log_prob [B] and the
+ * two tensors the backward needs (tanh output a_norm, std).  Backward: d_actions [B, A] or NULL, d_log_prob [B] or NULL -> dx [B, 2A]. */
+int vb_sac_head_fwd(const float* x, const float* eps, const float* scale, const float* bias, float log_std_min, float log_std_max,
+                    int64_t B, int A, float* actions, float* log_prob, float* a_norm, float* std_out, void* stream);
+int vb_sac_head_bwd(const float* x, const float* eps, const float* scale, float log_std_min, float log_std_max, int64_t B, int A,
+                    const float* a_norm, const float* std_in, const float* d_actions, const float* d_log_prob, float* dx, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

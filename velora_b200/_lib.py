@@ -47,6 +47,8 @@ SIGNATURES = {
     "vb_pack_rows": (_i, [_pp, C.POINTER(C.c_int), C.POINTER(C.c_int), _i, _p, _i, _p, _i64, _i64, _i64, _p]),
     "vb_gather_packed": (_i, [_p, _i, C.POINTER(C.c_int), _pp, C.POINTER(C.c_int), _i, _p, _i64, _i64, _p]),
     "vb_adam_multi": (_i, [_pp, _pp, _pp, _pp, _pp, C.POINTER(C.c_int64), _i, C.c_float, C.c_float, C.c_float, C.c_float, _p]),
+    "vb_sac_head_fwd": (_i, [_p, _p, _p, _p, C.c_float, C.c_float, _i64, _i, _p, _p, _p, _p, _p]),
+    "vb_sac_head_bwd": (_i, [_p, _p, _p, C.c_float, C.c_float, _i64, _i, _p, _p, _p, _p, _p, _p]),
     "vb_polyak_multi": (_i, [_pp, _pp, C.POINTER(C.c_int64), _i, C.c_float, _p]),
 }
 

@@ -339,3 +339,62 @@ def gather_packed(packed: torch.Tensor, offsets: Sequence[int], stride: int, wid
             "vb_gather_packed",
         )
     return tuple(outs)
+
+
+def standard_normal_like(t: torch.Tensor) -> torch.Tensor:
+    """The noise `Normal(mean, std).rsample()` draws (torch/distributions/normal.py: `_standard_normal(shape, dtype, device)`):
+    the same generator call, so a seeded run consumes the RNG stream exactly like the reference."""
+    from torch.distributions.utils import _standard_normal
+
+    return _standard_normal(t.shape, dtype=t.dtype, device=t.device)
+
+
+class SacHeadFn(torch.autograd.Function):
+    """actions [B,A], log_prob [B,1] = tail of SACActor.forward (velora/models/sac/continuous.py:121-143) for x [B,2A], eps [B,A]."""
+
+    @staticmethod
+    def forward(ctx, x, eps, scale, bias, lo, hi):
+        L = _lib.lib()
+        _lib.require_cuda(x, "SACActor.forward")
+        dev = x.device
+        x, eps = _f32c(x), _f32c(eps)
+        scale, bias = _f32c(scale.reshape(-1)), _f32c(bias.reshape(-1))
+        B, A2 = x.shape
+        A = A2 // 2
+        if scale.numel() != A or bias.numel() != A:
+            scale, bias = scale.expand(A).contiguous(), bias.expand(A).contiguous()
+        actions = torch.empty((B, A), dtype=torch.float32, device=dev)
+        log_prob = torch.empty((B, 1), dtype=torch.float32, device=dev)
+        a_norm = torch.empty((B, A), dtype=torch.float32, device=dev)
+        std = torch.empty((B, A), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _count(1)
+            _lib.check(
+                L.vb_sac_head_fwd(_lib.ptr(x), _lib.ptr(eps), _lib.ptr(scale), _lib.ptr(bias), float(lo), float(hi), B, A,
+                                  _lib.ptr(actions), _lib.ptr(log_prob), _lib.ptr(a_norm), _lib.ptr(std), _lib.stream_ptr(dev)),
+                "vb_sac_head_fwd",
+            )
+        ctx.save_for_backward(x, eps, scale, a_norm, std)
+        ctx.lims = (float(lo), float(hi))
+        ctx.set_materialize_grads(False)
+        return actions, log_prob
+
+    @staticmethod
+    def backward(ctx, d_actions, d_log_prob):
+        x, eps, scale, a_norm, std = ctx.saved_tensors
+        L = _lib.lib()
+        dev = x.device
+        B, A2 = x.shape
+        dx = torch.empty_like(x)
+        if d_actions is None and d_log_prob is None:
+            return dx.zero_(), None, None, None, None, None
+        da = _f32c(d_actions) if d_actions is not None else None
+        dl = _f32c(d_log_prob.reshape(-1)) if d_log_prob is not None else None
+        with torch.cuda.device(dev):
+            _count(1)
+            _lib.check(
+                L.vb_sac_head_bwd(_lib.ptr(x), _lib.ptr(eps), _lib.ptr(scale), ctx.lims[0], ctx.lims[1], B, A2 // 2, _lib.ptr(a_norm),
+                                  _lib.ptr(std), _lib.ptr(da), _lib.ptr(dl), _lib.ptr(dx), _lib.stream_ptr(dev)),
+                "vb_sac_head_bwd",
+            )
+        return dx, None, None, None, None, None

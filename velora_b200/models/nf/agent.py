@@ -37,7 +37,8 @@ class NeuroFlowCTCore:
                 raise ValueError("fused=True replaces torch.optim.Adam only")
             optim, okw = FusedAdam, None
         self.actor = ActorModule(state_dim, actor_neurons, action_dim, action_scale.to(device), action_bias.to(device),
-                                 log_std_min=log_std[0], log_std_max=log_std[1], optim=optim, lr=actor_lr, device=device, optim_kwargs=okw)
+                                 log_std_min=log_std[0], log_std_max=log_std[1], optim=optim, lr=actor_lr, device=device, optim_kwargs=okw,
+                                 fused_head=fused)
         self.critic = CriticModule(state_dim, critic_neurons, action_dim, optim=optim, lr=critic_lr, tau=tau, device=device, optim_kwargs=okw,
                                    fused_update=fused)
         self.hidden_dim = self.actor.hidden_size

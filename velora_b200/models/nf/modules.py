@@ -16,10 +16,10 @@ from velora_b200.utils.torch import soft_update
 class ActorModule:
     def __init__(self, state_dim: int, n_neurons: int, action_dim: int, action_scale: torch.Tensor, action_bias: torch.Tensor,
                  *, log_std_min: float = -5, log_std_max: float = 2, optim: Type[optim.Optimizer] = optim.Adam,
-                 lr: float = 3e-4, device: torch.device | None = None, optim_kwargs: dict | None = None):
+                 lr: float = 3e-4, device: torch.device | None = None, optim_kwargs: dict | None = None, fused_head: bool = False):
         self.device = device
         self.network = SACActor(state_dim, n_neurons, action_dim, action_scale, action_bias, log_std_min=log_std_min,
-                                log_std_max=log_std_max, device=device).to(device)
+                                log_std_max=log_std_max, device=device, fused_head=fused_head).to(device)
         self.hidden_size = self.network.ncp.hidden_size
         self.optim = optim(self.network.parameters(), lr=lr, **(optim_kwargs or {}))
         self.active_params = self.network.ncp.active_params

@@ -21,9 +21,13 @@ class SACActor(nn.Module):
     action_bias: torch.Tensor
 
     def __init__(self, num_obs: int, n_neurons: int, num_actions: int, action_scale: torch.Tensor, action_bias: torch.Tensor,
-                 *, log_std_min: float = -5, log_std_max: float = 2, device: torch.device | None = None) -> None:
+                 *, log_std_min: float = -5, log_std_max: float = 2, device: torch.device | None = None,
+                 fused_head: bool = False) -> None:
         super().__init__()
         self.device = device
+        # True: the policy-head math after the network runs as one kernel forward / one backward (vb_sac_head_*) instead of ~50
+        # elementwise launches; same noise draw, same formula
+        self.fused_head = fused_head
         self.ncp = LiquidNCPNetwork(num_obs, n_neurons, num_actions * 2, device=device).to(device)
         self.log_std_min = log_std_min
         self.log_std_max = log_std_max
@@ -40,6 +44,15 @@ class SACActor(nn.Module):
         return x_t, dist.log_prob(x_t)
 
     @torch.jit.ignore
+    def _fused_head(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        from velora_b200 import functional as VF
+
+        mean = x[:, : x.shape[1] // 2]
+        eps = VF.standard_normal_like(mean)      # what Normal(mean, std).rsample() draws
+        actions, log_prob = VF.SacHeadFn.apply(x, eps, self.action_scale, self.action_bias, self.log_std_min, self.log_std_max)
+        return actions, log_prob
+
+    @torch.jit.ignore
     def predict(self, obs: torch.Tensor, hidden: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
         """Deterministic action (continuous.py:79-104)."""
         x, new_hidden = self.ncp(obs, hidden)
@@ -49,6 +62,9 @@ class SACActor(nn.Module):
     def forward(self, obs: torch.Tensor, hidden: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         """(obs, hidden) -> (actions, log_prob [B,1], new hidden)   (continuous.py:106-143)"""
         x, new_hidden = self.ncp(obs, hidden)
+        if self.fused_head and x.dim() == 2:
+            actions_f, log_prob_f = self._fused_head(x)
+            return actions_f, log_prob_f, new_hidden
         mean, log_std = torch.chunk(x, 2, dim=-1)
         log_std = torch.clamp(log_std, self.log_std_min, self.log_std_max)
         std = log_std.exp()
