@@ -113,6 +113,21 @@ def mask_type(t: torch.Tensor) -> int:
     return code if t.is_contiguous() else code | VB_MASK_TRANSPOSED
 
 
+def common_mask_type(masks) -> "int | None":
+    """One type code for a group of masks that the C ABI takes with a single code, or None when they really differ.  A mask with
+    a dimension of size 1 (the [1, Nc] motor mask of a one-output critic) is row-major AND column-major: it adopts the others'."""
+    codes = set()
+    dtype_codes = set()
+    for m in masks:
+        dtype_codes.add(mask_type(m) & ~VB_MASK_TRANSPOSED)
+        ambiguous = m.dim() == 2 and m.is_contiguous() and m.t().is_contiguous()
+        if not ambiguous:
+            codes.add(mask_type(m))
+    if len(dtype_codes) != 1 or len(codes) > 1:
+        return None
+    return codes.pop() if codes else mask_type(masks[0])
+
+
 def mask_arg(m: torch.Tensor, dev: torch.device) -> torch.Tensor:
     """The reference stores `abs(mask.T)`: a transposed VIEW.  Row-major and transposed-row-major masks are passed
     as they are (the kernels index them through the type code); anything else is copied once."""

@@ -111,8 +111,10 @@ class LiquidSeqFn(torch.autograd.Function):
         w_out, b_out = params[12], params[13]
         # wiring masks are stored as transposed views (abs(mask.T) keeps the strides): passed as they are, with a type code
         masks = tuple(_lib.mask_arg(m, dev) for m in masks)
-        if len({_lib.mask_type(m) for m in masks[1:6]}) != 1:
+        heads_type = _lib.common_mask_type(masks[1:6])
+        if heads_type is None:
             masks = (masks[0], *[m.contiguous() for m in masks[1:6]], masks[6])
+            heads_type = _lib.mask_type(masks[1])
         m_in, m_h, m_out = masks[0], list(masks[1:6]), masks[6]
         with torch.cuda.device(dev):
             st = _lib.stream_ptr(dev)
@@ -121,7 +123,7 @@ class LiquidSeqFn(torch.autograd.Function):
             _lib.check(
                 L.vb_liquid_pack(
                     _lib.ptr(w_in), _lib.ptr(b_in), _lib.ptr(m_in), _lib.mask_type(m_in),
-                    _lib.ptr_array(w_h), _lib.ptr_array(b_h), _lib.ptr_array(m_h), _lib.mask_type(m_h[0]),
+                    _lib.ptr_array(w_h), _lib.ptr_array(b_h), _lib.ptr_array(m_h), heads_type,
                     _lib.ptr(w_out), _lib.ptr(b_out), _lib.ptr(m_out), _lib.mask_type(m_out),
                     I, Ni, Nc, O, _lib.ptr(packed), st,
                 ),
@@ -142,6 +144,7 @@ class LiquidSeqFn(torch.autograd.Function):
                 )
         h_last = h_traj[:, T - 1].clone()
         ctx.dims, ctx.flags, ctx.masks = dims, flags, masks
+        ctx.heads_type = heads_type
         ctx.has_h0 = h0 is not None
         ctx.layout = (tm_ok, x_tm)
         ctx.save_for_backward(x, h0c if h0c is not None else x.new_empty(0), h_traj, packed)
@@ -190,7 +193,7 @@ class LiquidSeqFn(torch.autograd.Function):
             _count(1)
             _lib.check(
                 L.vb_liquid_unpack_grads(
-                    _lib.ptr(dpacked), _lib.ptr(m_in), _lib.mask_type(m_in), _lib.ptr_array(m_h), _lib.mask_type(m_h[0]),
+                    _lib.ptr(dpacked), _lib.ptr(m_in), _lib.mask_type(m_in), _lib.ptr_array(m_h), ctx.heads_type,
                     _lib.ptr(m_out), _lib.mask_type(m_out),
                     _lib.ptr(grads[0]), _lib.ptr(grads[1]),
                     _lib.ptr_array([grads[2 + 2 * k] for k in range(5)]), _lib.ptr_array([grads[3 + 2 * k] for k in range(5)]),
@@ -216,14 +219,16 @@ class NcpFn(torch.autograd.Function):
         w = [params[0], params[2], params[4]]
         b = [params[1], params[3], params[5]]
         masks = tuple(_lib.mask_arg(m, dev) for m in masks)
-        if len({_lib.mask_type(m) for m in masks}) != 1:
+        m_type = _lib.common_mask_type(masks)
+        if m_type is None:
             masks = tuple(m.contiguous() for m in masks)
+            m_type = _lib.mask_type(masks[0])
         with torch.cuda.device(dev):
             st = _lib.stream_ptr(dev)
             packed = torch.empty(L.vb_ncp_packed_floats(I, Ni, Nc, O), dtype=torch.float32, device=dev)
             _count(1)
             _lib.check(
-                L.vb_ncp_pack(_lib.ptr_array(w), _lib.ptr_array(b), _lib.ptr_array(list(masks)), _lib.mask_type(masks[0]),
+                L.vb_ncp_pack(_lib.ptr_array(w), _lib.ptr_array(b), _lib.ptr_array(list(masks)), m_type,
                               I, Ni, Nc, O, _lib.ptr(packed), st),
                 "vb_ncp_pack",
             )
@@ -231,6 +236,7 @@ class NcpFn(torch.autograd.Function):
             with _timed("ncp_fwd", 1):
                 _lib.check(L.vb_ncp_fwd(_lib.ptr(packed), _lib.ptr(x), _lib.ptr(y), B, I, Ni, Nc, O, flags, st), "vb_ncp_fwd")
         ctx.dims, ctx.flags, ctx.masks = dims, flags, masks
+        ctx.m_type = m_type
         ctx.save_for_backward(x, packed)
         return y
 
@@ -260,7 +266,7 @@ class NcpFn(torch.autograd.Function):
             grads = [torch.empty(s, dtype=torch.float32, device=dev) if need[k] else None for k, s in enumerate(shapes)]
             _count(1)
             _lib.check(
-                L.vb_ncp_unpack_grads(_lib.ptr(dpacked), _lib.ptr_array(list(masks)), _lib.mask_type(masks[0]),
+                L.vb_ncp_unpack_grads(_lib.ptr(dpacked), _lib.ptr_array(list(masks)), ctx.m_type,
                                       _lib.ptr_array([grads[0], grads[2], grads[4]]), _lib.ptr_array([grads[1], grads[3], grads[5]]),
                                       I, Ni, Nc, O, 0, st),
                 "vb_ncp_unpack_grads",
