@@ -84,11 +84,83 @@ def cpu_train_oracle(agent):
     return TrainOracle(sd(agent.actor.network), sd(agent.critic.network1), sd(agent.critic.network2))
 
 
+def main_dp(args):
+    """cfg 5 at N GPUs: replicated 1M buffer, every rank draws the same global index vector and the same
+    policy noise and keeps its shard; one all-reduce per network backward (2 critics + actor) and one for log_alpha; the whole step
+    is one CUDA graph per rank.  Launched as `torchrun --nproc-per-node N bench_configs.py --dp`.  Before timing, rank-wise
+    equivalence with the single-process step on the whole batch is checked."""
+    import torch
+    import torch.distributed as dist
+
+    import velora_b200 as vb
+
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    world, rank = dist.get_world_size(), dist.get_rank()
+
+    # ---- equivalence: N-rank data-parallel step == single-process step on the global batch (same seed, noise and indices)
+    gb = 4096 * world
+    vb.dataparallel.configure(True, reduce="mean")
+    a_dp = make_agent(dev, 100_000, seed=5, fused=True)
+    torch.manual_seed(11)
+    for _ in range(2):
+        a_dp._train_step(gb)
+    vb.dataparallel.configure(False)
+    a_one = make_agent(dev, 100_000, seed=5, fused=True)
+    torch.manual_seed(11)
+    for _ in range(2):
+        a_one._train_step(gb)
+    worst = 0.0
+    for pa, pb in zip(list(a_dp.actor.network.parameters()) + list(a_dp.critic.network1.parameters()) + [a_dp.entropy.log_alpha],
+                      list(a_one.actor.network.parameters()) + list(a_one.critic.network1.parameters()) + [a_one.entropy.log_alpha]):
+        worst = max(worst, float((pa.detach() - pb.detach()).abs().max()))
+    t = torch.tensor([worst], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    equiv = float(t.item())
+    del a_dp, a_one
+
+    # ---- timing
+    vb.dataparallel.configure(True, reduce="mean")
+    per_gpu = 131072
+    B = per_gpu * world
+    big = make_agent(dev, 1_000_000, capturable=True, fused=True)
+    replay = big.capture_train_step(B)
+    for _ in range(30):
+        replay()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = 50
+    e0.record()
+    for _ in range(iters):
+        replay()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / iters], device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        emit(config=f"cfg5 sample + NeuroFlowCT update, data-parallel, global batch {B} = {per_gpu} x {world} GPUs, one CUDA graph per rank",
+             metric="transitions_per_s", value=B / (float(ms.item()) * 1e-3), ms=float(ms.item()), n_gpus=world,
+             max_abs_param_diff_vs_single_process_after_2_steps=equiv)
+    replay = None
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
+    dist.barrier()
+    sys.stdout.flush()
+    os._exit(0)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--dp", action="store_true", help="cfg5 data-parallel update under torchrun: global batch 131072 x world, one rank per GPU")
     args = ap.parse_args()
+    if args.dp:
+        return main_dp(args)
     import torch
 
     import velora_b200 as vb

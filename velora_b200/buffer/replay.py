@@ -10,6 +10,7 @@ from typing import TYPE_CHECKING, Optional
 
 import torch
 
+from velora_b200 import dataparallel as _dp
 from velora_b200 import functional as VF
 from velora_b200.buffer.base import FIELDS, BufferBase
 from velora_b200.buffer.experience import BatchExperience
@@ -36,6 +37,11 @@ class ReplayBuffer(BufferBase):
         if len(self) < batch_size:
             raise ValueError(f"Buffer does not contain enough experiences. Available: {len(self)}, Requested: {batch_size}")
         indices = torch.randint(0, self.size, (batch_size,), device=self.device)
+        if _dp.is_enabled() and _dp.world_size() > 1:
+            # data-parallel: `batch_size` is the global batch; every rank draws the same index vector (replicated buffers, identically
+            # seeded generators) and gathers its contiguous slice - the union is bit-identical to a single-process sample(batch_size)
+            lo, hi = _dp.shard_bounds(batch_size)
+            indices = indices[lo:hi]
         return self.gather(indices)
 
     def gather(self, indices: torch.Tensor) -> BatchExperience:

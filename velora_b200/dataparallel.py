@@ -36,6 +36,12 @@ def world_size() -> int:
     return 1
 
 
+def rank() -> int:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(_state["group"])
+    return 0
+
+
 def maybe_allreduce(flat: torch.Tensor) -> None:
     """In-place all-reduce of a flat gradient block when data-parallel mode is on (no-op otherwise)."""
     if not _state["enabled"]:

@@ -349,10 +349,19 @@ def gather_packed(packed: torch.Tensor, offsets: Sequence[int], stride: int, wid
 
 def standard_normal_like(t: torch.Tensor) -> torch.Tensor:
     """The noise `Normal(mean, std).rsample()` draws (torch/distributions/normal.py: `_standard_normal(shape, dtype, device)`):
-    the same generator call, so a seeded run consumes the RNG stream exactly like the reference."""
+    the same generator call, so a seeded run consumes the RNG stream exactly like the reference.
+
+    Data-parallel mode: every rank draws the noise of the GLOBAL batch (identically seeded generators give identical draws) and
+    keeps the rows of its shard, so an N-rank step uses the same noise as the single-process step on the whole batch."""
     from torch.distributions.utils import _standard_normal
 
-    return _standard_normal(t.shape, dtype=t.dtype, device=t.device)
+    ws = _dp.world_size() if _dp.is_enabled() else 1
+    if ws == 1:
+        return _standard_normal(t.shape, dtype=t.dtype, device=t.device)
+    n = t.shape[0]
+    full = _standard_normal((n * ws, *t.shape[1:]), dtype=t.dtype, device=t.device)
+    r = _dp.rank()
+    return full[r * n:(r + 1) * n]
 
 
 class SacHeadFn(torch.autograd.Function):

@@ -10,6 +10,7 @@ from torch import optim
 
 from velora_b200.models.sac.continuous import SACActor, SACCriticNCP
 from velora_b200.models.sac.discrete import SACActorDiscrete, SACCriticNCPDiscrete
+from velora_b200 import dataparallel as _dp
 from velora_b200.utils.torch import soft_update
 
 
@@ -111,6 +112,7 @@ class EntropyModule:
     def gradient_step(self, loss: torch.Tensor) -> None:
         self.optim.zero_grad()
         loss.backward()
+        _dp.maybe_allreduce(self.log_alpha.grad)      # data-parallel: the loss is a mean over this rank's shard
         self.optim.step()
 
 

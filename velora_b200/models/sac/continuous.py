@@ -40,7 +40,9 @@ class SACActor(nn.Module):
         # argument validation reads a device flag back to the host, which is illegal while a CUDA graph is being captured
         validate = not (mean.is_cuda and torch.cuda.is_current_stream_capturing())
         dist = Normal(mean, std, validate_args=validate)
-        x_t = dist.rsample()
+        from velora_b200 import functional as VF
+
+        x_t = mean + VF.standard_normal_like(mean) * std      # == dist.rsample(): same generator call, shard-aware under data parallelism
         return x_t, dist.log_prob(x_t)
 
     @torch.jit.ignore
