@@ -125,7 +125,8 @@ def main_dp(args):
     vb.dataparallel.configure(True, reduce="mean")
     per_gpu = 131072
     B = per_gpu * world
-    big = make_agent(dev, 1_000_000, capturable=True, fused=True)
+    rows = max(1_000_000, B)      # `sample` needs at least `batch` rows (replay.py:74-77): 2^20 rows at 8 GPUs
+    big = make_agent(dev, rows, capturable=True, fused=True)
     replay = big.capture_train_step(B)
     for _ in range(30):
         replay()
@@ -142,7 +143,7 @@ def main_dp(args):
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     if rank == 0:
         emit(config=f"cfg5 sample + NeuroFlowCT update, data-parallel, global batch {B} = {per_gpu} x {world} GPUs, one CUDA graph per rank",
-             metric="transitions_per_s", value=B / (float(ms.item()) * 1e-3), ms=float(ms.item()), n_gpus=world,
+             metric="transitions_per_s", value=B / (float(ms.item()) * 1e-3), ms=float(ms.item()), n_gpus=world, buffer_rows=rows,
              max_abs_param_diff_vs_single_process_after_2_steps=equiv)
     replay = None
     import gc
