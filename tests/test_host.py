@@ -216,3 +216,50 @@ def test_library_loads_and_exports_every_declared_symbol():
     # argument errors are reported, not crashed on
     assert lib.vb_liquid_fwd(None, None, None, None, None, 1, 1, 4, 12, 8, 2, None, 0, 0, None) == -1
     assert b"null pointer" in lib.vb_last_error()
+
+
+def test_packed_row_layout_keeps_vector_alignment():
+    """Shadow-table row layout: vector-width fields first, every field's offset aligned to its own vector width, stride a
+    multiple of 4 floats, nothing overlaps."""
+    from velora_b200.functional import packed_row_layout
+
+    for widths in ([4, 1, 1, 4, 1, 8], [3, 2, 1, 3, 1, 8], [17, 6, 1, 17, 1, 40], [1], [8, 8]):
+        offsets, stride = packed_row_layout(widths)
+        assert stride % 4 == 0 and stride >= sum(widths) and stride - sum(widths) < 4
+        spans = sorted((o, o + w) for o, w in zip(offsets, widths))
+        assert spans[0][0] == 0 and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))      # contiguous, no overlap
+        for o, w in zip(offsets, widths):
+            if w % 4 == 0:
+                assert o % 4 == 0
+            elif w % 2 == 0:
+                assert o % 2 == 0
+    assert packed_row_layout([4, 1, 1, 4, 1, 8]) == ([0, 16, 17, 4, 18, 8], 20)      # the reference's buffer: 19 floats -> 80-byte rows
+
+
+def test_common_mask_type_codes():
+    """One type code per mask group: transposed views pass as they are, a single-row mask adopts the group's layout, mixed
+    layouts or dtypes are reported as such (the caller then copies)."""
+    from velora_b200 import _lib
+
+    a = torch.ones(5, 7, dtype=torch.int32).t()           # [7, 5] transposed view, as the reference stores abs(mask.T)
+    b = torch.ones(3, 7, dtype=torch.int32).t()
+    row = torch.ones(7, 1, dtype=torch.int32).t()          # [1, 7]: both row- and column-major
+    assert _lib.mask_type(a) == _lib.VB_MASK_I32 | _lib.VB_MASK_TRANSPOSED
+    assert _lib.common_mask_type([a, b, row]) == _lib.VB_MASK_I32 | _lib.VB_MASK_TRANSPOSED
+    assert _lib.common_mask_type([a.contiguous(), b.contiguous(), row]) == _lib.VB_MASK_I32
+    assert _lib.common_mask_type([a, b.contiguous()]) is None
+    assert _lib.common_mask_type([a, b.float()]) is None
+    assert _lib.common_mask_type([row]) == _lib.VB_MASK_I32
+    f = torch.ones(4, 6).t()
+    assert _lib.common_mask_type([f, f]) == _lib.VB_MASK_F32 | _lib.VB_MASK_TRANSPOSED
+
+
+def test_dataparallel_helpers_single_process():
+    from velora_b200 import dataparallel as dp
+
+    assert dp.world_size() == 1 and dp.rank() == 0 and not dp.is_enabled()
+    assert dp.shard_bounds(10, rank=0, world=4) == (0, 3) and dp.shard_bounds(10, rank=3, world=4) == (9, 10)
+    assert dp.shard_bounds(8, rank=1, world=2) == (4, 8)
+    t = torch.ones(3)
+    dp.maybe_allreduce(t)                                  # disabled: no-op
+    assert torch.equal(t, torch.ones(3))
