@@ -33,13 +33,14 @@ struct Cfg {
     static constexpr int S_WB = S_A + 3 * KC * PLANE;           // [KC][3 NP rows][16 B]
     static constexpr int S_W1 = S_WB + KC * 3 * NP * 16;        // fp32 [I + 1][KF]: W1^T rows, then b1
     static constexpr int S_W3 = S_W1 + (I + 1) * KF * 4;        // fp32 [O][NP], then b3 [4]
-    static constexpr int S_BAR = S_W3 + (O * NP + 4) * 4;
+    static constexpr int S_YS = S_W3 + (O * NP + 4) * 4;        // fp32 [O][TM]
+    static constexpr int S_BAR = S_YS + O * TM * 4;
     static constexpr int BYTES = S_BAR + 64;
     static constexpr int TMEM_COLS = 256;
 };
 
 template <class C>
-__global__ void __launch_bounds__(TM) ncp_fwd_tc_kernel(const float* __restrict__ packed, const float* __restrict__ x,
+__global__ void __launch_bounds__(2 * TM) ncp_fwd_tc_kernel(const float* __restrict__ packed, const float* __restrict__ x,
                                                         float* __restrict__ y, int64_t B) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* aP = smem + C::S_A;
@@ -48,10 +49,14 @@ __global__ void __launch_bounds__(TM) ncp_fwd_tc_kernel(const float* __restrict_
     float* w3s = reinterpret_cast<float*>(smem + C::S_W3);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + C::S_BAR);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::S_BAR + 16);
+    // two threads per sample (rows of warps w and w + 4 share TMEM lanes): each takes every other plane chunk / column chunk
+    constexpr int NT = 2 * TM;
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int row = tid & (TM - 1), half = tid >> 7;
+    float* ys = reinterpret_cast<float*>(smem + C::S_YS);      // [O][TM]: layer-3 partial sums of the second half
 
     // layer-2 operand: B[pb * NP + n][k] = part pb of (k < NI ? W2[n][k] : k == NI ? b2[n] : 0), zero rows for n >= NC
-    for (int item = tid; item < C::NP * C::KC; item += TM) {
+    for (int item = tid; item < C::NP * C::KC; item += NT) {
         const int n = item % C::NP, kc = item / C::NP;
         float v[8];
 #pragma unroll
@@ -68,11 +73,11 @@ __global__ void __launch_bounds__(TM) ncp_fwd_tc_kernel(const float* __restrict_
 #pragma unroll
         for (int pb = 0; pb < 3; ++pb) q[kc * (3 * C::NP) + pb * C::NP + n] = part[pb];
     }
-    for (int e = tid; e < (C::I + 1) * C::KF; e += TM) {
+    for (int e = tid; e < (C::I + 1) * C::KF; e += NT) {
         const int i = e / C::KF, j = e % C::KF;
         w1s[e] = j < C::NI ? __ldg(packed + (i < C::I ? C::W1_T + i * C::NIp : C::B1) + j) : 0.f;
     }
-    for (int e = tid; e < C::O * C::NP + 4; e += TM) {
+    for (int e = tid; e < C::O * C::NP + 4; e += NT) {
         const int o = e / C::NP, j = e % C::NP;
         w3s[e] = e < C::O * C::NP ? (j < C::NC ? __ldg(packed + C::W3 + o * C::NCp + j) : 0.f)
                                   : (e - C::O * C::NP < C::O ? __ldg(packed + C::B3 + e - C::O * C::NP) : 0.f);
@@ -90,20 +95,20 @@ __global__ void __launch_bounds__(TM) ncp_fwd_tc_kernel(const float* __restrict_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t a_addr = smem_u32(aP), w_addr = smem_u32(wB);
     uint32_t ph = 0;
 
     const int64_t n_tiles = (B + TM - 1) / TM;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t b = tile * TM + tid;
+        const int64_t b = tile * TM + row;
         const bool valid = b < B;
         float xr[C::I];
 #pragma unroll
         for (int i = 0; i < C::I; ++i) xr[i] = valid ? __ldg(x + b * C::I + i) : 0.f;
         // ---------------- layer 1 + Mish on CUDA cores, eight neurons (one plane chunk) at a time
-#pragma unroll 2
-        for (int c = 0; c < C::KC; ++c) {
+#pragma unroll 1
+        for (int c = half; c < C::KC; c += 2) {
             float u[8];
             {
                 const float4 b0 = *reinterpret_cast<const float4*>(w1s + C::I * C::KF + 8 * c);
@@ -132,7 +137,7 @@ __global__ void __launch_bounds__(TM) ncp_fwd_tc_kernel(const float* __restrict_
                 if (k == C::NI) a[e] = 1.0f;
                 else if (k > C::NI) a[e] = 0.f;
             }
-            store_chunk3<C::KC>(aP, c, tid, a);
+            store_chunk3<C::KC>(aP, c, row, a);
         }
         fence_async_smem();
         tc_fence_before();
@@ -154,9 +159,9 @@ __global__ void __launch_bounds__(TM) ncp_fwd_tc_kernel(const float* __restrict_
         // ---------------- Mish + layer 3
         float yo[C::O];
 #pragma unroll
-        for (int o = 0; o < C::O; ++o) yo[o] = w3s[C::O * C::NP + o];
-#pragma unroll
-        for (int c = 0; c < C::EC; ++c) {
+        for (int o = 0; o < C::O; ++o) yo[o] = half == 0 ? w3s[C::O * C::NP + o] : 0.f;
+#pragma unroll 1
+        for (int c = half; c < C::EC; c += 2) {
             float s8[8];
             {
                 float hi[8], mid[8], lo[8];
@@ -183,11 +188,16 @@ __global__ void __launch_bounds__(TM) ncp_fwd_tc_kernel(const float* __restrict_
                 yo[o] = fmaf(a2[4], w1.x, fmaf(a2[5], w1.y, fmaf(a2[6], w1.z, fmaf(a2[7], w1.w, yo[o]))));
             }
         }
-        if (valid) {
+        if (half == 1) {
 #pragma unroll
-            for (int o = 0; o < C::O; ++o) y[b * C::O + o] = yo[o];
+            for (int o = 0; o < C::O; ++o) ys[o * TM + row] = yo[o];
         }
         tc_fence_before();      // this tile's TMEM reads are ordered before the next tile's MMAs (issued after the next barrier)
+        __syncthreads();
+        if (half == 0 && valid) {
+#pragma unroll
+            for (int o = 0; o < C::O; ++o) y[b * C::O + o] = yo[o] + ys[o * TM + row];
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -599,7 +609,7 @@ bool has_path(int I, int Ni, int Nc, int O) {
 template <class C>
 static int launch_fwd(const float* packed, const float* x, float* y, int64_t B, cudaStream_t stream) {
     LaunchCfg cfg;
-    int rc = cached_launch_cfg(ncp_fwd_tc_kernel<C>, TM, C::BYTES, &cfg);
+    int rc = cached_launch_cfg(ncp_fwd_tc_kernel<C>, 2 * TM, C::BYTES, &cfg);
     if (rc) return rc;
     int smem_sm = 0;
     int dev = 0;
@@ -611,7 +621,7 @@ static int launch_fwd(const float* packed, const float* x, float* y, int64_t B, 
     const int64_t n_tiles = (B + TM - 1) / TM;
     const int64_t cap = (int64_t)device_sms() * per_sm;
     const int grid = (int)(n_tiles < cap ? n_tiles : cap);
-    ncp_fwd_tc_kernel<C><<<grid < 1 ? 1 : grid, TM, C::BYTES, stream>>>(packed, x, y, B);
+    ncp_fwd_tc_kernel<C><<<grid < 1 ? 1 : grid, 2 * TM, C::BYTES, stream>>>(packed, x, y, B);
     VB_LAUNCH_CHECK();
     return 0;
 }
