@@ -271,6 +271,34 @@ def main():
         emit(config=f"cfg5 CPU port of the NeuroFlowCT update, batch {B}", metric="transitions_per_s", value=B / (cms * 1e-3), ms=cms, cpu_cores=cores)
     del big
 
+    # ------------------------------------------------------------------ cfg 3 incumbent: the reference's op sequence, eager on this GPU
+    if not args.no_cpu:
+        from oracle import liquid_oracle as lo      # measurement baseline only (the Python reference cannot travel to the GPU box)
+
+        vb.set_seed(64)
+        rnet = LiquidNCPNetwork(4, 20, 2, device=dev)
+        rp = lo.torch_params({k: v.detach().clone() for k, v in rnet.state_dict().items()}, requires_grad=True)
+        leaves = [t for t in rp.values() if t.requires_grad]
+        B3, T3 = 65536, 32
+        g3 = torch.Generator(device=dev).manual_seed(1234)
+        x3 = torch.randn(B3, T3, 4, device=dev, generator=g3)
+        ry3 = torch.randn(B3, T3, 2, device=dev, generator=g3)
+        rh3 = torch.randn(B3, 8, device=dev, generator=g3)
+        h03 = torch.zeros(B3, 8, device=dev)
+
+        def ref_step():
+            for t_ in leaves:
+                t_.grad = None
+            y_, ht_ = lo.liquid_seq_forward_torch(rp, x3, h03)
+            ((y_ * ry3).sum() + (ht_[:, -1] * rh3).sum()).backward()
+
+        rms = gpu_time_ms(ref_step, warmup=2, iters=5)
+        emit(config="cfg3 the reference's ATen op sequence launched eagerly on this B200 (oracle torch port on cuda), 65536 x 32, fwd+bwd",
+             metric="sample_steps_per_s", value=B3 * T3 / (rms * 1e-3), ms=rms,
+             note="the incumbent a velora user has today on a GPU: ~26 launches per forward step, ~60 per backward step")
+        del rnet, rp, leaves, x3, ry3, rh3, h03
+        torch.cuda.empty_cache()
+
     # ------------------------------------------------------------------ cfg 4: 512-neuron liquid network
     vb.set_seed(64)
     net = LiquidNCPNetwork(8, 512, 1, device=dev)
