@@ -29,6 +29,10 @@ _WORKSPACES = {}
 def _workspace(dev: torch.device, nbytes: int) -> torch.Tensor:
     """Scratch buffer for the backward kernels, reused per (device, stream): work on one stream is ordered, so the
     next backward on that stream may overwrite it."""
+    if torch.cuda.is_current_stream_capturing():
+        # inside a CUDA-graph capture the buffer must come from (and live with) the graph's own memory pool: caching it under the
+        # capture stream's handle could hand it to eager work on a later stream that happens to reuse the handle
+        return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=dev)
     key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
     ws = _WORKSPACES.get(key)
     if ws is None or ws.numel() < nbytes:
