@@ -404,17 +404,20 @@ def run_ours(args) -> None:
             traffic = json.load(f).get("liquid_bwd_tc_kernel_bytes_per_launch")
 
     # ------------------------------------------------------------------ end to end: pinned host inputs, H2D + D2H inside
+    # Every step's INPUT x comes from pinned host memory (double-buffered on a copy stream, overlapping the previous step's
+    # compute); the loss weights r_y, r_h are the fixed tensors of BASELINE config 3 ("loss = sum y r_y + sum h_T r_h with fixed
+    # random r") and stay on the device; the step's result (loss + every parameter gradient) is read back to pinned host memory.
+    # The compute part is the same public-API code, captured once per input slot in a CUDA graph like the device-resident loop.
     def host_seq(F):
         return torch.randn(T, B, F).pin_memory().permute(1, 0, 2) if tm else torch.randn(B, T, F).pin_memory()
 
     hx = [host_seq(SHAPE["I"]) for _ in range(2)]
-    hry = [host_seq(SHAPE["O"]) for _ in range(2)]
-    hrh = [torch.randn(B, SHAPE["Nc"]).pin_memory() for _ in range(2)]
     n_grad = sum(p.numel() for p in params)
     hout = torch.empty(n_grad + 1).pin_memory()
     copy_stream = torch.cuda.Stream(device=dev)
     main_stream = torch.cuda.current_stream(dev)
-    dbuf = [[torch.empty_like(xs[0]), torch.empty_like(rys[0]), torch.empty_like(rhs[0])] for _ in range(2)]
+    dbuf = [torch.empty_like(xs[0]) for _ in range(2)]
+    r_y, r_h = rys[0], rhs[0]
     ready = [torch.cuda.Event() for _ in range(2)]
     freed = [torch.cuda.Event() for _ in range(2)]
 
@@ -422,37 +425,66 @@ def run_ours(args) -> None:
         s = i % 2
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(freed[s])
-            dbuf[s][0].copy_(hx[s], non_blocking=True)
-            dbuf[s][1].copy_(hry[s], non_blocking=True)
-            dbuf[s][2].copy_(hrh[s], non_blocking=True)
+            dbuf[s].copy_(hx[s], non_blocking=True)
             ready[s].record(copy_stream)
+
+    def e2e_compute(s: int) -> torch.Tensor:
+        for p in params:
+            p.grad = None
+        y, _, h_last = net.forward_seq(dbuf[s], None, return_last=True)
+        loss = (y * r_y).sum() + (h_last * r_h).sum()
+        loss.backward()
+        return torch.cat([loss.detach().reshape(1)] + [p.grad.reshape(-1) for p in params])
+
+    e2e_graphs, e2e_out = None, [None, None]
+    if graphs is not None:
+        try:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(main_stream)
+            with torch.cuda.stream(side):
+                for s in range(2):
+                    e2e_compute(s)
+            main_stream.wait_stream(side)
+            barrier()
+            e2e_graphs, pool = [], None
+            for s in range(2):
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr, pool=pool):
+                    e2e_out[s] = e2e_compute(s)
+                pool = gr.pool()
+                e2e_graphs.append(gr)
+        except Exception as e:
+            if world > 1:
+                raise
+            print(f"[bench] CUDA graph capture of the end-to-end step failed ({e!r}); running it eagerly", file=sys.stderr)
+            e2e_graphs = None
+            torch.cuda.synchronize()
 
     def e2e_step(i: int) -> None:
         s = i % 2
-        upload(i + 1)                                   # next step's inputs travel while this step computes
+        upload(i + 1)                                   # next step's input travels while this step computes
         main_stream.wait_event(ready[s])
-        for p in params:
-            p.grad = None
-        y, _, h_last = net.forward_seq(dbuf[s][0], None, return_last=True)
-        loss = (y * dbuf[s][1]).sum() + (h_last * dbuf[s][2]).sum()
-        loss.backward()
+        if e2e_graphs is not None:
+            e2e_graphs[s].replay()
+            flat = e2e_out[s]
+        else:
+            flat = e2e_compute(s)
         freed[s].record(main_stream)
-        flat = torch.cat([loss.detach().reshape(1)] + [p.grad.reshape(-1) for p in params])
         hout.copy_(flat, non_blocking=True)             # D2H of the step's result (loss + all parameter gradients)
 
     for s in range(2):
         freed[s].record(main_stream)
     upload(0)
-    for i in range(3):
+    n_warm = 3 + (extra_warm if e2e_graphs is not None else 0)      # see the device-resident loop: the first replays of a graph
+    for i in range(n_warm):                                          # holding the all-reduce are slow
         e2e_step(i)
     torch.cuda.synchronize()
-    upload(3)
     barrier()
     sampler.active = True
     align()
     w0 = time.perf_counter()
     e0.record()
-    for i in range(3, 3 + K):
+    for i in range(n_warm, n_warm + K):
         e2e_step(i)
     e1.record()
     barrier()
@@ -464,7 +496,7 @@ def run_ours(args) -> None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
     e2e_value = world * B * T * K / (e2e_ms * 1e-3)
-    h2d = 4 * (B * T * (SHAPE["I"] + SHAPE["O"]) + B * SHAPE["Nc"])
+    h2d = 4 * B * T * SHAPE["I"]
     d2h = 4 * (n_grad + 1)
     sampler.stop_flag = True
 
@@ -483,7 +515,8 @@ def run_ours(args) -> None:
             "config": {"workload": f"LiquidNCPNetwork(4,20,2) fwd+bwd, batch {B} x seq {T} per GPU, fp32 (BASELINE config 3)",
                        "batch_per_gpu": B, "global_batch": B * world, "seq_len": T,
                        "parallelism": f"dp{world}" if world > 1 else "single",
-                       "l2": f"{R} rotating input sets ({R * h2d // 2**20} MiB) + ~170 MB touched per step > 126 MB L2",
+                       "l2": f"{R} rotating input sets ({R * 4 * (B * T * (SHAPE['I'] + SHAPE['O']) + B * SHAPE['Nc']) // 2**20} MiB) + ~170 MB touched per step > 126 MB L2",
+                       "e2e_inputs": "x from pinned host memory every step; loss weights r_y, r_h fixed on the device (config 3); loss + gradients read back",
                        "layout": "time-major storage [T,B,F] viewed as [B,T,F]" if tm else "batch-major [B,T,F]",
                        "launch": f"{R} CUDA graphs (one per input set) replayed round-robin" if graphs is not None else "eager",
                        "eager_ms_per_step": eager_ms / K, "extra_untimed_graph_replays": extra_warm},
