@@ -86,7 +86,7 @@ static int upload_constants(const float* packed, int n_floats, cudaStream_t stre
     return 0;
 }
 
-constexpr int kFlush = 8;                // steps between flushes of the truncating dW accumulator
+constexpr int kFlush = 11;               // steps between flushes of the truncating dW accumulator (T = 32: three flushes)
 
 template <int I_, int NI_, int NC_, int O_>
 struct Cfg {
