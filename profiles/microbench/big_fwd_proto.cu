@@ -1,0 +1,353 @@
+// Prototype for BASELINE config 4 (LiquidNCPNetwork(8,512,1): Ni = 308, Nc = 204, 816 head outputs, K = 517):
+// forward recurrence with the heads GEMM on tcgen05 in bf16 (fp32 accumulate, fp32 state), one 128-sample tile per CTA,
+// warp-specialised: 16 element-wise warps (four threads per sample), one bulk-copy producer lane streaming the weight
+// block from L2 through a 3-stage ring, one MMA-issuing lane, accumulators double-buffered in TMEM (2 x 208 columns).
+// Not wired into the library: it exists to measure what the design of DESIGN.md section 4.7 delivers (L2 streaming rate,
+// MMA rate, element-wise cost) before the backward is designed around it.
+//
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 --expt-relaxed-constexpr -I../../velora_b200/csrc \
+//        big_fwd_proto.cu -o big_fwd_proto.bin
+#include <cuda_bf16.h>
+#include <math.h>
+#include <stdlib.h>
+#include <vector>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+using namespace vb;
+using namespace vb::tcx;
+
+constexpr int I = 8, NI = 308, NC = 204;
+constexpr int A_CHUNKS = 39;                 // a: 308 features + 4 zeros
+constexpr int H_CHUNK0 = 39;                 // h starts at feature 312
+constexpr int H_CHUNKS = 26;                 // 204 h + the constant-1 feature + 3 zeros
+constexpr int KC = 66;                       // 528 features, 33 K-steps
+constexpr int NPASS = 4, PN = 52, PROWS = 4 * PN;     // 52 neurons = 208 accumulator columns per pass
+constexpr int STAGE_CHUNKS = 6, NSTAGE_PER_PASS = KC / STAGE_CHUNKS;      // 11 stages of K = 48
+constexpr int STAGE_BYTES = STAGE_CHUNKS * PROWS * 16;                    // 19968
+constexpr int RING = 3;
+constexpr int EW = 512;                      // element-wise threads: FOUR per sample (warps w, w+4, w+8, w+12 share TMEM lanes)
+constexpr int NTHREADS = EW + 64;            // + producer warp + MMA warp
+
+constexpr int S_Z = 0;
+constexpr int S_STAGE = S_Z + KC * PLANE;
+constexpr int S_WIN = S_STAGE + RING * STAGE_BYTES;            // fp32 [I][312]
+constexpr int S_BIN = S_WIN + I * 312 * 4;                     // fp32 [312]
+constexpr int S_WOUT = S_BIN + 312 * 4;                        // fp32 [208]
+constexpr int S_YS = S_WOUT + 208 * 4;                         // fp32 [128]
+constexpr int S_BAR = S_YS + 3 * 128 * 4;
+constexpr int SMEM_BYTES = S_BAR + 128;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+// h_traj in the kernel's own tile-interleaved order: [T][tile][NC / 4][128 rows][4 floats]: a warp reads / writes 512 contiguous bytes
+__host__ __device__ __forceinline__ size_t h_index(int t, int64_t n_tiles, int64_t tile, int row, int j) {
+    return ((((size_t)t * n_tiles + tile) * (NC / 4) + j / 4) * TM + row) * 4 + (j & 3);
+}
+__device__ __forceinline__ void ew_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+
+__global__ void __launch_bounds__(NTHREADS, 1) big_fwd_kernel(const unsigned char* __restrict__ wpack, const float* __restrict__ w_in,
+                                                              const float* __restrict__ b_in, const float* __restrict__ w_out, float b_out,
+                                                              const float* __restrict__ x, float* __restrict__ y, float* __restrict__ h_traj,
+                                                              int64_t B, int T) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* zP = smem + S_Z;
+    float* wins = reinterpret_cast<float*>(smem + S_WIN);
+    float* bins = reinterpret_cast<float*>(smem + S_BIN);
+    float* wouts = reinterpret_cast<float*>(smem + S_WOUT);
+    float* ys = reinterpret_cast<float*>(smem + S_YS);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + S_BAR);       // [RING]
+    uint64_t* empty = full + RING;                                    // [RING]
+    uint64_t* acc_full = empty + RING;                                // [2]
+    uint64_t* acc_empty = acc_full + 2;                               // [2]
+    uint64_t* zready = acc_empty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(zready + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    for (int e = tid; e < I * 312; e += NTHREADS) wins[e] = (e % 312) < NI ? w_in[(e / 312) * NI + e % 312] : 0.f;
+    for (int e = tid; e < 312; e += NTHREADS) bins[e] = e < NI ? b_in[e] : 0.f;
+    for (int e = tid; e < 208; e += NTHREADS) wouts[e] = e < NC ? w_out[e] : 0.f;
+    for (int e = tid; e < TM; e += NTHREADS) reinterpret_cast<uint4*>(zP)[(KC - 1) * TM + e] = make_uint4(0, 0, 0, 0);   // chunk 65: zeros
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        for (int s = 0; s < RING; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], EW); }
+        mbar_init(zready, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const int64_t n_tiles = (B + TM - 1) / TM;
+    const int64_t my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    const int64_t n_steps = my_tiles * T;                   // steps this CTA walks (tiles are processed one after the other)
+
+    if (warp == EW / 32) {
+        // ---------------------------------------------------------------- producer: weight stages, the same 44 per step
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int64_t st = 0; st < n_steps; ++st)
+                for (int ps = 0; ps < NPASS * NSTAGE_PER_PASS; ++ps, ++it) {
+                    const int slot = it % RING;
+                    const uint32_t use = it / RING;
+                    if (use > 0) mbar_wait(&empty[slot], (use - 1) & 1);
+                    mbar_expect_tx(&full[slot], STAGE_BYTES);
+                    bulk_g2s(smem + S_STAGE + slot * STAGE_BYTES, wpack + (size_t)ps * STAGE_BYTES, STAGE_BYTES, &full[slot]);
+                }
+        }
+    } else if (warp == EW / 32 + 1) {
+        // ---------------------------------------------------------------- MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(128, PROWS, 0, 0);
+            const uint32_t z_addr = smem_u32(zP), st_addr = smem_u32(smem + S_STAGE);
+            uint32_t it = 0, acc_use[2] = {0, 0};
+            for (int64_t st = 0; st < n_steps; ++st) {
+                mbar_wait(zready, st & 1);
+                tc_fence_after();
+                for (int pass = 0; pass < NPASS; ++pass) {
+                    const int buf = pass & 1;
+                    if (acc_use[buf] > 0) { mbar_wait(&acc_empty[buf], (acc_use[buf] - 1) & 1); tc_fence_after(); }
+                    for (int s = 0; s < NSTAGE_PER_PASS; ++s, ++it) {
+                        const int slot = it % RING;
+                        mbar_wait(&full[slot], (it / RING) & 1);
+                        tc_fence_after();
+#pragma unroll
+                        for (int kk = 0; kk < STAGE_CHUNKS / 2; ++kk)
+                            mma_bf16(tmem + buf * PROWS, make_desc(z_addr + (STAGE_CHUNKS * s + 2 * kk) * PLANE, PLANE, 128),
+                                     make_desc(st_addr + slot * STAGE_BYTES + 2 * kk * (PROWS * 16), PROWS * 16, 128), idesc, (s | kk) != 0);
+                        mma_commit(&empty[slot]);
+                    }
+                    mma_commit(&acc_full[buf]);
+                    acc_use[buf]++;
+                }
+            }
+        }
+    } else {
+        // ---------------------------------------------------------------- element-wise warps: two threads per sample
+        const int row = tid & (TM - 1), part = tid >> 7;          // part 0..3
+        const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        uint32_t acc_use[2] = {0, 0};
+        int64_t st = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int64_t b = tile * TM + row;
+            const bool valid = b < B;
+            for (int t = 0; t < T; ++t, ++st) {
+                // ---- z~ = [mish(W_in x + b_in) | 0 | h_{t-1} | 1 | 0] as bf16 planes
+                float xr[I];
+#pragma unroll
+                for (int i = 0; i < I; ++i) xr[i] = valid ? __ldg(x + ((int64_t)t * B + b) * I + i) : 0.f;
+#ifdef NO_BUILD
+                const int c0 = 0, c1 = 0;
+#else
+                const int c0 = 10 * part, c1 = part == 3 ? A_CHUNKS : 10 * part + 10;
+#endif
+                for (int c = c0; c < c1; ++c) {
+                    float u[8];
+                    const float4 b0 = *reinterpret_cast<const float4*>(bins + 8 * c), b1 = *reinterpret_cast<const float4*>(bins + 8 * c + 4);
+                    u[0] = b0.x; u[1] = b0.y; u[2] = b0.z; u[3] = b0.w; u[4] = b1.x; u[5] = b1.y; u[6] = b1.z; u[7] = b1.w;
+#pragma unroll
+                    for (int i = 0; i < I; ++i) {
+                        const float4 w0 = *reinterpret_cast<const float4*>(wins + i * 312 + 8 * c);
+                        const float4 w1 = *reinterpret_cast<const float4*>(wins + i * 312 + 8 * c + 4);
+                        u[0] = fmaf(xr[i], w0.x, u[0]); u[1] = fmaf(xr[i], w0.y, u[1]); u[2] = fmaf(xr[i], w0.z, u[2]); u[3] = fmaf(xr[i], w0.w, u[3]);
+                        u[4] = fmaf(xr[i], w1.x, u[4]); u[5] = fmaf(xr[i], w1.y, u[5]); u[6] = fmaf(xr[i], w1.z, u[6]); u[7] = fmaf(xr[i], w1.w, u[7]);
+                    }
+                    float a[8];
+                    {
+                        float u4[4] = {u[0], u[1], u[2], u[3]}, a4[4];
+                        mish4(u4, a4);
+                        a[0] = a4[0]; a[1] = a4[1]; a[2] = a4[2]; a[3] = a4[3];
+                        float v4[4] = {u[4], u[5], u[6], u[7]};
+                        mish4(v4, a4);
+                        a[4] = a4[0]; a[5] = a4[1]; a[6] = a4[2]; a[7] = a4[3];
+                    }
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)
+                        if (8 * c + e >= NI) a[e] = 0.f;
+                    reinterpret_cast<uint4*>(zP)[c * TM + row] =
+                        make_uint4(pack_bf16(a[0], a[1]), pack_bf16(a[2], a[3]), pack_bf16(a[4], a[5]), pack_bf16(a[6], a[7]));
+                }
+                {
+#ifdef NO_BUILD
+                    const int hc0 = 0, hc1 = 0;
+#else
+                    const int hc0 = part < 2 ? 7 * part : 14 + 6 * (part - 2), hc1 = part < 2 ? hc0 + 7 : hc0 + 6;
+#endif
+                    for (int c = hc0; c < hc1; ++c) {
+                        float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+                        if (t > 0) {
+                            if (8 * c < NC) v0 = __ldcg(reinterpret_cast<const float4*>(h_traj + h_index(t - 1, n_tiles, tile, row, 8 * c)));
+                            if (8 * c + 4 < NC) v1 = __ldcg(reinterpret_cast<const float4*>(h_traj + h_index(t - 1, n_tiles, tile, row, 8 * c + 4)));
+                        }
+                        if (8 * c + 4 == NC) v1.x = 1.0f;        // the constant-1 (bias) feature follows the last h
+                        reinterpret_cast<uint4*>(zP)[(H_CHUNK0 + c) * TM + row] =
+                            make_uint4(pack_bf16(v0.x, v0.y), pack_bf16(v0.z, v0.w), pack_bf16(v1.x, v1.y), pack_bf16(v1.z, v1.w));
+                    }
+                }
+                fence_async_smem();
+                ew_sync();
+                if (tid == 0) mbar_arrive(zready);
+                // ---- gating epilogue per pass
+                float yacc = 0.f;
+                for (int pass = 0; pass < NPASS; ++pass) {
+                    const int buf = pass & 1;
+                    mbar_wait(&acc_full[buf], acc_use[buf] & 1);
+                    acc_use[buf]++;
+                    tc_fence_after();
+                    // the four threads of a row take 16 / 12 / 12 / 12 of the pass's 52 neurons, four neurons per iteration
+                    const int n0 = part == 0 ? 0 : 16 + 12 * (part - 1), nq = part == 0 ? 4 : 3;
+#ifdef NO_EPI
+                    for (int q = 0; q < 0; ++q) {
+#else
+#pragma unroll 1
+                    for (int q = 0; q < nq; ++q) {
+#endif
+                        float s16[16];
+                        tmem_ld16(taddr + buf * PROWS + 4 * n0 + 16 * q, s16);
+                        float hn[4], cc[4], m[4];
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            float tg, th, gate;
+                            tanh2_sigmoid(s16[4 * jj + 0], s16[4 * jj + 1], s16[4 * jj + 2], tg, th, gate);
+                            hn[jj] = fmaf(gate, th - tg, tg);
+                            cc[jj] = s16[4 * jj + 3] + hn[jj];
+                        }
+                        mish4(cc, m);
+                        const int j = pass * PN + n0 + 4 * q;
+                        if (j < NC) {
+                            const float4 w4 = *reinterpret_cast<const float4*>(wouts + j);
+                            yacc = fmaf(m[0], w4.x, fmaf(m[1], w4.y, fmaf(m[2], w4.z, fmaf(m[3], w4.w, yacc))));
+                            *reinterpret_cast<float4*>(h_traj + h_index(t, n_tiles, tile, row, j)) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+                        }
+                    }
+                    tc_fence_before();
+                    mbar_arrive(&acc_empty[buf]);
+                }
+                if (part > 0) ys[(part - 1) * TM + row] = yacc;
+                ew_sync();
+                if (part == 0 && valid) y[(int64_t)t * B + b] = ((yacc + ys[row]) + (ys[TM + row] + ys[2 * TM + row])) + b_out;
+                ew_sync();          // h_t is visible to every thread of the tile before the next step reads it; ys is free again
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ host
+static float bf16r(float v) { return __bfloat162float(__float2bfloat16(v)); }
+static float mishf(float x) { return x * tanhf(log1pf(expf(x))); }
+
+int main(int argc, char** argv) {
+    const int T = argc > 2 ? atoi(argv[2]) : 8;
+    const int64_t B = argc > 1 ? atoll(argv[1]) : 148 * 128 * 2;
+    srand(1);
+    auto rnd = [](float s) { return s * (2.0f * rand() / RAND_MAX - 1.0f); };
+    std::vector<float> w_in(I * NI), b_in(NI), wh((size_t)4 * NC * 516), bh(4 * NC), w_out(NC), x((size_t)T * B * I);
+    for (auto& v : w_in) v = rnd(0.35f);
+    for (auto& v : b_in) v = rnd(0.3f);
+    for (auto& v : wh) v = (rand() % 100 < 64) ? rnd(0.044f) : 0.f;       // 1/sqrt(512), 64 % of the entries active
+    for (auto& v : bh) v = rnd(0.04f);
+    for (auto& v : w_out) v = rnd(0.07f);
+    for (auto& v : x) v = rnd(1.7f);
+    const float b_out = 0.1f;
+    // weight block in plane order: [pass][stage][chunk (6)][row (208)][8 bf16]; row r = 4 jj + hs of neuron j = pass * 52 + jj
+    // feature k: a at [0,308), h at [312,516), bias (constant-1 feature) at 516
+    std::vector<__nv_bfloat16> wpack((size_t)NPASS * NSTAGE_PER_PASS * STAGE_CHUNKS * PROWS * 8);
+    for (int pass = 0; pass < NPASS; ++pass)
+        for (int c = 0; c < KC; ++c)
+            for (int r = 0; r < PROWS; ++r)
+                for (int e = 0; e < 8; ++e) {
+                    const int k = 8 * c + e, j = pass * PN + r / 4, hs = r % 4;
+                    float v = 0.f;
+                    if (j < NC) {
+                        const int n = 4 * j + hs;
+                        if (k < NI) v = wh[(size_t)n * 516 + k];
+                        else if (k >= 312 && k < 516) v = wh[(size_t)n * 516 + NI + (k - 312)];
+                        else if (k == 516) v = bh[n];
+                    }
+                    const int s = c / STAGE_CHUNKS, cc = c % STAGE_CHUNKS;
+                    wpack[((((size_t)pass * NSTAGE_PER_PASS + s) * STAGE_CHUNKS + cc) * PROWS + r) * 8 + e] = __float2bfloat16(v);
+                }
+    unsigned char* d_wpack; float *d_win, *d_bin, *d_wout, *d_x, *d_y, *d_h;
+    cudaMalloc(&d_wpack, wpack.size() * 2); cudaMemcpy(d_wpack, wpack.data(), wpack.size() * 2, cudaMemcpyHostToDevice);
+    cudaMalloc(&d_win, w_in.size() * 4); cudaMemcpy(d_win, w_in.data(), w_in.size() * 4, cudaMemcpyHostToDevice);
+    cudaMalloc(&d_bin, b_in.size() * 4); cudaMemcpy(d_bin, b_in.data(), b_in.size() * 4, cudaMemcpyHostToDevice);
+    cudaMalloc(&d_wout, w_out.size() * 4); cudaMemcpy(d_wout, w_out.data(), w_out.size() * 4, cudaMemcpyHostToDevice);
+    cudaMalloc(&d_x, x.size() * 4); cudaMemcpy(d_x, x.data(), x.size() * 4, cudaMemcpyHostToDevice);
+    const int64_t n_tiles_h = (B + TM - 1) / TM;
+    cudaMalloc(&d_y, (size_t)T * B * 4); cudaMalloc(&d_h, (size_t)T * n_tiles_h * TM * NC * 4);
+    cudaFuncSetAttribute(big_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    const int64_t n_tiles = (B + TM - 1) / TM;
+    const int grid = (int)(n_tiles < 148 ? n_tiles : 148);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    big_fwd_kernel<<<grid, NTHREADS, SMEM_BYTES>>>(d_wpack, d_win, d_bin, d_wout, b_out, d_x, d_y, d_h, B, T);
+    cudaError_t err = cudaDeviceSynchronize();
+    printf("first launch: %s  (smem %d B, grid %d)\n", cudaGetErrorString(err), SMEM_BYTES, grid);
+    if (err != cudaSuccess) return 1;
+    const int iters = 5;
+    cudaEventRecord(e0);
+    for (int i = 0; i < iters; ++i) big_fwd_kernel<<<grid, NTHREADS, SMEM_BYTES>>>(d_wpack, d_win, d_bin, d_wout, b_out, d_x, d_y, d_h, B, T);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= iters;
+    const double ss = (double)B * T;
+    const double flops = 2.0 * (I * NI + 517.0 * 4 * NC + NC) * ss;
+    printf("B %lld T %d: %.3f ms  %.3f G sample-steps/s  %.1f TFLOP/s (forward, bf16 operands)  weights streamed %.2f TB/s\n", (long long)B, T, ms,
+           ss / ms * 1e-6, flops / ms * 1e-9, (double)n_tiles * T * wpack.size() * 2 / ms * 1e-9);
+    // ---- check a few samples against a CPU recurrence with the same operand rounding
+    std::vector<float> y(T * B), h((size_t)T * n_tiles * TM * NC);
+    cudaMemcpy(y.data(), d_y, y.size() * 4, cudaMemcpyDeviceToHost); cudaMemcpy(h.data(), d_h, h.size() * 4, cudaMemcpyDeviceToHost);
+    double worst_y = 0, worst_h = 0, ny = 0, nh = 0;
+    const int64_t samples[4] = {0, 77, B / 2 + 5, B - 1};
+    for (int64_t b : samples) {
+        std::vector<float> hprev(NC, 0.f), z(517);
+        for (int t = 0; t < T; ++t) {
+            for (int j = 0; j < NI; ++j) {
+                float u = b_in[j];
+                for (int i = 0; i < I; ++i) u = fmaf(x[((size_t)t * B + b) * I + i], w_in[i * NI + j], u);
+                z[j] = bf16r(mishf(u));
+            }
+            for (int j = 0; j < NC; ++j) z[NI + j] = bf16r(hprev[j]);
+            float yy = b_out;
+            std::vector<float> hn(NC);
+            for (int j = 0; j < NC; ++j) {
+                float s[4];
+                for (int hs = 0; hs < 4; ++hs) {
+                    const int n = 4 * j + hs;
+                    double acc = bf16r(bh[n]);
+                    for (int k = 0; k < 512; ++k) acc += (double)z[k] * bf16r(wh[(size_t)n * 516 + k]);
+                    s[hs] = (float)acc;
+                }
+                const float tg = tanhf(s[0]), th = tanhf(s[1]), gate = 1.0f / (1.0f + expf(-s[2]));
+                hn[j] = tg * (1.0f - gate) + gate * th;
+                yy += w_out[j] * mishf(s[3] + hn[j]);
+                const double dh = fabs(hn[j] - h[h_index(t, n_tiles, b / TM, (int)(b % TM), j)]);
+                worst_h = fmax(worst_h, dh); nh = fmax(nh, fabs(hn[j]));
+            }
+            worst_y = fmax(worst_y, fabs(yy - y[(size_t)t * B + b])); ny = fmax(ny, fabs(yy));
+            hprev = hn;
+        }
+    }
+    printf("check vs CPU recurrence (bf16-rounded operands): max |dy| %.3e (max |y| %.3f), max |dh| %.3e (max |h| %.3f)\n", worst_y, ny, worst_h, nh);
+    return 0;
+}
