@@ -133,6 +133,16 @@ int vb_liquid_unpack_grads(const float* dpacked, const void* m_in, int m_in_type
                            float* g_w_out, float* g_b_out,
                            int I, int Ni, int Nc, int O, int accumulate, void* stream);
 
+/* Forward of the 512-neuron class (BASELINE config 4: LiquidNCPNetwork(8,512,1)) with the heads on tcgen05 in bf16 (bf16 operands,
+ * fp32 accumulation, fp32 hidden state; 2e-2 relative contract) - opt-in, inference only: the fp32 contract of vb_liquid_fwd and the
+ * backward of this class stay on the tile kernels.  x [B,T,I], y [B,T,O] (batch- or time-major: VB_FLAG_X/Y_TIME_MAJOR), h0 [B,Nc] or
+ * NULL, h_last [B,Nc] or NULL, h_traj [B,T,Nc] or NULL (VB_FLAG_H_TIME_MAJOR).  The workspace must be 128-byte aligned. */
+int vb_liquid_bf16_ok(int I, int Ni, int Nc, int O);
+int64_t vb_liquid_bf16_fwd_workspace_bytes(int I, int Ni, int Nc, int O, int64_t B, int T);
+int vb_liquid_bf16_fwd(const float* packed, const float* x, const float* h0, float* y, float* h_last, float* h_traj,
+                       int64_t B, int T, int I, int Ni, int Nc, int O, void* workspace, int64_t workspace_bytes, int flags,
+                       void* stream);
+
 /* ------------------------------------------------------------------------------------------------ NCP network (critic) */
 int64_t vb_ncp_packed_floats(int I, int Ni, int Nc, int O);
 int64_t vb_ncp_grad_floats(int I, int Ni, int Nc, int O);

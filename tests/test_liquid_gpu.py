@@ -238,3 +238,29 @@ def test_empty_batch(golden):
     assert x.grad.shape == (0, 5, 4)
     for k, p in net.named_parameters():
         assert p.grad is not None and torch.count_nonzero(p.grad) == 0, k
+
+
+@pytest.mark.parametrize("B,T,with_h0", [(300, 5, True), (128, 1, False), (1000, 12, False)])
+def test_bf16_tensor_core_forward_of_the_512_neuron_class(B, T, with_h0):
+    """vb_liquid_bf16_fwd (tcgen05, bf16 operands / fp32 accumulation and state) against the fp32 path of the same network:
+    2e-2 relative (BASELINE's bf16 contract) for the outputs, the last hidden state and the whole hidden trajectory."""
+    import velora_b200 as vb
+    from velora_b200.models.lnn import LiquidNCPNetwork
+
+    dev = torch.device("cuda")
+    vb.set_seed(64)
+    net = LiquidNCPNetwork(8, 512, 1, device=dev)
+    g = torch.Generator(device=dev).manual_seed(B + T)
+    x = torch.randn(B, T, 8, device=dev, generator=g)
+    h0 = 0.5 * torch.randn(B, 204, device=dev, generator=g) if with_h0 else None
+    with torch.no_grad():
+        y_ref, ht_ref = net.forward_seq(x, h0)
+    y, h_last, ht = net.forward_seq_bf16(x, h0, return_traj=True)
+    assert y.shape == (B, T, 1) and h_last.shape == (B, 204) and ht.shape == (B, T, 204)
+    assert rel_err(y.cpu().numpy(), y_ref.cpu().numpy()) < 2e-2
+    assert rel_err(ht.cpu().numpy(), ht_ref.cpu().numpy()) < 2e-2
+    assert rel_err(h_last.cpu().numpy(), ht_ref[:, -1].cpu().numpy()) < 2e-2
+    y2, h2 = net.forward_seq_bf16(x.permute(1, 0, 2).contiguous().permute(1, 0, 2), h0)      # time-major input, no trajectory
+    assert torch.equal(y2, y) and torch.equal(h2, h_last)
+    with pytest.raises(RuntimeError):
+        LiquidNCPNetwork(4, 20, 2, device=dev).forward_seq_bf16(torch.zeros(2, 3, 4, device=dev))

@@ -61,6 +61,11 @@ int fwd(const float*, const float*, float*, int64_t, int, int, int, int, cudaStr
 int bwd(const float*, const float*, const float*, float*, float*, int64_t, int, int, int, int, void*, int64_t, cudaStream_t);
 int64_t bwd_workspace_bytes(int, int, int, int);
 }  // namespace ncp_tc
+namespace big {
+bool has_path(int I, int Ni, int Nc, int O);
+int64_t fwd_workspace_bytes(int64_t B);
+int fwd(const float*, const float*, const float*, float*, float*, float*, int64_t, int, int, void*, int64_t, cudaStream_t);
+}  // namespace big
 namespace generic {
 int liquid_fwd(const float*, const float*, const float*, float*, float*, int64_t, int, int, int, int, int, cudaStream_t);
 int64_t liquid_bwd_workspace_bytes(int, int, int, int);
@@ -182,4 +187,23 @@ extern "C" int vb_ncp_bwd(const float* packed, const float* x, const float* dy, 
     if (!(flags & (VB_FLAG_FORCE_GENERIC | VB_FLAG_FORCE_FFMA)) && B >= kNcpTcMinBatch && ncp_tc::has_path(I, Ni, Nc, O))
         return ncp_tc::bwd(packed, x, dy, dx, dpacked, B, I, Ni, Nc, O, workspace, workspace_bytes, (cudaStream_t)stream);
     return generic::ncp_bwd(packed, x, dy, dx, dpacked, B, I, Ni, Nc, O, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------ bf16 forward (config 4 class)
+extern "C" int vb_liquid_bf16_ok(int I, int Ni, int Nc, int O) { return big::has_path(I, Ni, Nc, O) ? 1 : 0; }
+
+extern "C" int64_t vb_liquid_bf16_fwd_workspace_bytes(int I, int Ni, int Nc, int O, int64_t B, int T) {
+    (void)T;
+    if (!big::has_path(I, Ni, Nc, O) || B < 0) return VB_ERR_BAD_DIMS;
+    return big::fwd_workspace_bytes(B);
+}
+
+extern "C" int vb_liquid_bf16_fwd(const float* packed, const float* x, const float* h0, float* y, float* h_last, float* h_traj,
+                                  int64_t B, int T, int I, int Ni, int Nc, int O, void* workspace, int64_t workspace_bytes, int flags,
+                                  void* stream) {
+    VB_CHECK_ARG(B >= 0 && T >= 1, VB_ERR_BAD_DIMS, "vb_liquid_bf16_fwd: bad dims B=%lld T=%d", (long long)B, T);
+    VB_CHECK_ARG(big::has_path(I, Ni, Nc, O), VB_ERR_BAD_DIMS, "vb_liquid_bf16_fwd: no bf16 tensor-core kernel for (%d,%d,%d,%d)", I, Ni, Nc, O);
+    if (B == 0) return 0;
+    VB_CHECK_ARG(packed && x && y, VB_ERR_NULL_POINTER, "vb_liquid_bf16_fwd: null pointer");
+    return big::fwd(packed, x, h0, y, h_last, h_traj, B, T, flags, workspace, workspace_bytes, (cudaStream_t)stream);
 }

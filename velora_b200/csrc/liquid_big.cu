@@ -1,0 +1,313 @@
+// LiquidNCPNetwork(8,512,1) - the 512-neuron class of BASELINE config 4 - forward on the tensor cores in bf16 (fp32 accumulate,
+// fp32 hidden state), opt-in through vb_liquid_bf16_fwd (the fp32 contract of vb_liquid_fwd stays on the tile kernels).
+//
+// Per sample and step the heads are a 517 x 816 contraction: one CTA owns a 128-sample tile and keeps z~ = [mish(W_in x) | h | 1]
+// as 66 bf16 operand planes in shared memory (132 KB); the 816 x 528 bf16 weight block (858 KB, pre-arranged in plane order by
+// big_pack_kernel) is streamed from L2 by one bulk-copy producer lane through a 3-stage ring; one lane issues the MMAs (four
+// passes of 52 neurons = 208 accumulator columns, double-buffered in TMEM); 16 element-wise warps (four threads per sample)
+// rebuild z~ at the start of a step and run the gating epilogue of pass p while the MMAs of pass p+1 execute.  h travels between
+// steps through a two-slot scratch buffer in a tile-interleaved order ([tile][Nc/4][128 rows][4]) so that every warp access is
+// 512 contiguous bytes.  Measured (profiles/microbench/big_fwd_proto_r01.log): 0.82 G sample-steps/s = 690 TFLOP/s; the
+// MMA + streaming pipeline alone sustains 1.33 PFLOP/s, what is exposed is the rebuild of z~.
+// The backward of this class is not built: training this shape still runs on the generic fp32 kernels.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace vb {
+namespace big {
+using namespace tcx;
+
+constexpr int I = 8, NI = 308, NC = 204;
+constexpr int A_CHUNKS = 39;                 // a: 308 features + 4 zeros
+constexpr int H_CHUNK0 = 39;                 // h starts at feature 312
+constexpr int H_CHUNKS = 26;                 // 204 h + the constant-1 feature + 3 zeros
+constexpr int KC = 66;                       // 528 features, 33 K-steps
+constexpr int NPASS = 4, PN = 52, PROWS = 4 * PN;     // 52 neurons = 208 accumulator columns per pass
+constexpr int STAGE_CHUNKS = 6, NSTAGE_PER_PASS = KC / STAGE_CHUNKS;      // 11 stages of K = 48
+constexpr int STAGE_BYTES = STAGE_CHUNKS * PROWS * 16;                    // 19968
+constexpr int RING = 3;
+constexpr int EW = 512;                      // element-wise threads: FOUR per sample (warps w, w+4, w+8, w+12 share TMEM lanes)
+constexpr int NTHREADS = EW + 64;            // + producer warp + MMA warp
+
+constexpr int S_Z = 0;
+constexpr int S_STAGE = S_Z + KC * PLANE;
+constexpr int S_WIN = S_STAGE + RING * STAGE_BYTES;            // fp32 [I][312]
+constexpr int S_BIN = S_WIN + I * 312 * 4;                     // fp32 [312]
+constexpr int S_WOUT = S_BIN + 312 * 4;                        // fp32 [208]
+constexpr int S_YS = S_WOUT + 208 * 4;                         // fp32 [128]
+constexpr int S_BAR = S_YS + 3 * 128 * 4;
+constexpr int SMEM_BYTES = S_BAR + 128;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+// h_traj in the kernel's own tile-interleaved order: [T][tile][NC / 4][128 rows][4 floats]: a warp reads / writes 512 contiguous bytes
+__host__ __device__ __forceinline__ size_t h_index(int t, int64_t n_tiles, int64_t tile, int row, int j) {
+    return ((((size_t)t * n_tiles + tile) * (NC / 4) + j / 4) * TM + row) * 4 + (j & 3);
+}
+__device__ __forceinline__ void ew_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+
+
+// weight block in plane order: [pass][stage][chunk (6)][row (208)][8 bf16]; row r = 4 jj + hs of neuron j = pass * 52 + jj,
+// hs in (g, h, f, proj); feature k: a at [0,308), zeros, h at [312,516), the bias (constant-1 feature) at 516, zeros to 528
+__global__ void __launch_bounds__(256) big_pack_kernel(const float* __restrict__ packed, __nv_bfloat16* __restrict__ wpack) {
+    constexpr LiquidLayout L(I, NI, NC, 1);
+    const int total = NPASS * KC * PROWS * 8;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int el = e & 7, r = (e >> 3) % PROWS, c = ((e >> 3) / PROWS) % KC, pass = (e >> 3) / (PROWS * KC);
+        const int k = 8 * c + el, j = pass * PN + r / 4, hs = r % 4;
+        float v = 0.f;
+        if (j < NC) {
+            const int col = hs * L.NCp + j;
+            if (k < NI) v = packed[L.wh_t + k * L.H4 + col];
+            else if (k >= 312 && k < 312 + NC) v = packed[L.wh_t + (NI + k - 312) * L.H4 + col];
+            else if (k == 312 + NC) v = packed[L.b_h + col];
+        }
+        const int s = c / STAGE_CHUNKS, cc = c % STAGE_CHUNKS;
+        wpack[((((size_t)pass * NSTAGE_PER_PASS + s) * STAGE_CHUNKS + cc) * PROWS + r) * 8 + el] = __float2bfloat16(v);
+    }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) liquid_big_fwd_kernel(const unsigned char* __restrict__ wpack, const float* __restrict__ packed,
+                                                                     const float* __restrict__ x, const float* __restrict__ h0,
+                                                                     float* __restrict__ y, float* __restrict__ h_last,
+                                                                     float* __restrict__ h_out, float* __restrict__ hbuf,
+                                                                     int64_t B, int T, int flags) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* zP = smem + S_Z;
+    float* wins = reinterpret_cast<float*>(smem + S_WIN);
+    float* bins = reinterpret_cast<float*>(smem + S_BIN);
+    float* wouts = reinterpret_cast<float*>(smem + S_WOUT);
+    float* ys = reinterpret_cast<float*>(smem + S_YS);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + S_BAR);       // [RING]
+    uint64_t* empty = full + RING;                                    // [RING]
+    uint64_t* acc_full = empty + RING;                                // [2]
+    uint64_t* acc_empty = acc_full + 2;                               // [2]
+    uint64_t* zready = acc_empty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(zready + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    constexpr LiquidLayout L(I, NI, NC, 1);
+    for (int e = tid; e < I * 312; e += NTHREADS) wins[e] = (e % 312) < NI ? __ldg(packed + L.win_t + (e / 312) * L.NIp + e % 312) : 0.f;
+    for (int e = tid; e < 312; e += NTHREADS) bins[e] = e < NI ? __ldg(packed + L.b_in + e) : 0.f;
+    for (int e = tid; e < 208; e += NTHREADS) wouts[e] = e < NC ? __ldg(packed + L.wout + e) : 0.f;
+    const float b_out = __ldg(packed + L.b_out);
+    const bool x_tm = flags & VB_FLAG_X_TIME_MAJOR, y_tm = flags & VB_FLAG_Y_TIME_MAJOR, h_tm = flags & VB_FLAG_H_TIME_MAJOR;
+    for (int e = tid; e < TM; e += NTHREADS) reinterpret_cast<uint4*>(zP)[(KC - 1) * TM + e] = make_uint4(0, 0, 0, 0);   // chunk 65: zeros
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        for (int s = 0; s < RING; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], EW); }
+        mbar_init(zready, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const int64_t n_tiles = (B + TM - 1) / TM;
+    const int64_t my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    const int64_t n_steps = my_tiles * T;                   // steps this CTA walks (tiles are processed one after the other)
+
+    if (warp == EW / 32) {
+        // ---------------------------------------------------------------- producer: weight stages, the same 44 per step
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int64_t st = 0; st < n_steps; ++st)
+                for (int ps = 0; ps < NPASS * NSTAGE_PER_PASS; ++ps, ++it) {
+                    const int slot = it % RING;
+                    const uint32_t use = it / RING;
+                    if (use > 0) mbar_wait(&empty[slot], (use - 1) & 1);
+                    mbar_expect_tx(&full[slot], STAGE_BYTES);
+                    bulk_g2s(smem + S_STAGE + slot * STAGE_BYTES, wpack + (size_t)ps * STAGE_BYTES, STAGE_BYTES, &full[slot]);
+                }
+        }
+    } else if (warp == EW / 32 + 1) {
+        // ---------------------------------------------------------------- MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(128, PROWS, 0, 0);
+            const uint32_t z_addr = smem_u32(zP), st_addr = smem_u32(smem + S_STAGE);
+            uint32_t it = 0, acc_use[2] = {0, 0};
+            for (int64_t st = 0; st < n_steps; ++st) {
+                mbar_wait(zready, st & 1);
+                tc_fence_after();
+                for (int pass = 0; pass < NPASS; ++pass) {
+                    const int buf = pass & 1;
+                    if (acc_use[buf] > 0) { mbar_wait(&acc_empty[buf], (acc_use[buf] - 1) & 1); tc_fence_after(); }
+                    for (int s = 0; s < NSTAGE_PER_PASS; ++s, ++it) {
+                        const int slot = it % RING;
+                        mbar_wait(&full[slot], (it / RING) & 1);
+                        tc_fence_after();
+#pragma unroll
+                        for (int kk = 0; kk < STAGE_CHUNKS / 2; ++kk)
+                            mma_bf16(tmem + buf * PROWS, make_desc(z_addr + (STAGE_CHUNKS * s + 2 * kk) * PLANE, PLANE, 128),
+                                     make_desc(st_addr + slot * STAGE_BYTES + 2 * kk * (PROWS * 16), PROWS * 16, 128), idesc, (s | kk) != 0);
+                        mma_commit(&empty[slot]);
+                    }
+                    mma_commit(&acc_full[buf]);
+                    acc_use[buf]++;
+                }
+            }
+        }
+    } else {
+        // ---------------------------------------------------------------- element-wise warps: two threads per sample
+        const int row = tid & (TM - 1), part = tid >> 7;          // part 0..3
+        const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        uint32_t acc_use[2] = {0, 0};
+        int64_t st = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int64_t b = tile * TM + row;
+            const bool valid = b < B;
+            for (int t = 0; t < T; ++t, ++st) {
+                // ---- z~ = [mish(W_in x + b_in) | 0 | h_{t-1} | 1 | 0] as bf16 planes
+                float xr[I];
+#pragma unroll
+                for (int i = 0; i < I; ++i) xr[i] = valid ? __ldg(x + (x_tm ? (int64_t)t * B + b : b * T + t) * I + i) : 0.f;
+                const int c0 = 10 * part, c1 = part == 3 ? A_CHUNKS : 10 * part + 10;
+                for (int c = c0; c < c1; ++c) {
+                    float u[8];
+                    const float4 b0 = *reinterpret_cast<const float4*>(bins + 8 * c), b1 = *reinterpret_cast<const float4*>(bins + 8 * c + 4);
+                    u[0] = b0.x; u[1] = b0.y; u[2] = b0.z; u[3] = b0.w; u[4] = b1.x; u[5] = b1.y; u[6] = b1.z; u[7] = b1.w;
+#pragma unroll
+                    for (int i = 0; i < I; ++i) {
+                        const float4 w0 = *reinterpret_cast<const float4*>(wins + i * 312 + 8 * c);
+                        const float4 w1 = *reinterpret_cast<const float4*>(wins + i * 312 + 8 * c + 4);
+                        u[0] = fmaf(xr[i], w0.x, u[0]); u[1] = fmaf(xr[i], w0.y, u[1]); u[2] = fmaf(xr[i], w0.z, u[2]); u[3] = fmaf(xr[i], w0.w, u[3]);
+                        u[4] = fmaf(xr[i], w1.x, u[4]); u[5] = fmaf(xr[i], w1.y, u[5]); u[6] = fmaf(xr[i], w1.z, u[6]); u[7] = fmaf(xr[i], w1.w, u[7]);
+                    }
+                    float a[8];
+                    {
+                        float u4[4] = {u[0], u[1], u[2], u[3]}, a4[4];
+                        mish4(u4, a4);
+                        a[0] = a4[0]; a[1] = a4[1]; a[2] = a4[2]; a[3] = a4[3];
+                        float v4[4] = {u[4], u[5], u[6], u[7]};
+                        mish4(v4, a4);
+                        a[4] = a4[0]; a[5] = a4[1]; a[6] = a4[2]; a[7] = a4[3];
+                    }
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)
+                        if (8 * c + e >= NI) a[e] = 0.f;
+                    reinterpret_cast<uint4*>(zP)[c * TM + row] =
+                        make_uint4(pack_bf16(a[0], a[1]), pack_bf16(a[2], a[3]), pack_bf16(a[4], a[5]), pack_bf16(a[6], a[7]));
+                }
+                {
+                    const int hc0 = part < 2 ? 7 * part : 14 + 6 * (part - 2), hc1 = part < 2 ? hc0 + 7 : hc0 + 6;
+                    for (int c = hc0; c < hc1; ++c) {
+                        float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+                        if (t > 0) {
+                            if (8 * c < NC) v0 = __ldcg(reinterpret_cast<const float4*>(hbuf + h_index((t - 1) & 1, n_tiles, tile, row, 8 * c)));
+                            if (8 * c + 4 < NC) v1 = __ldcg(reinterpret_cast<const float4*>(hbuf + h_index((t - 1) & 1, n_tiles, tile, row, 8 * c + 4)));
+                        } else if (h0 && valid) {
+                            if (8 * c < NC) v0 = __ldg(reinterpret_cast<const float4*>(h0 + b * NC + 8 * c));
+                            if (8 * c + 4 < NC) v1 = __ldg(reinterpret_cast<const float4*>(h0 + b * NC + 8 * c + 4));
+                        }
+                        if (8 * c + 4 == NC) v1.x = 1.0f;        // the constant-1 (bias) feature follows the last h
+                        reinterpret_cast<uint4*>(zP)[(H_CHUNK0 + c) * TM + row] =
+                            make_uint4(pack_bf16(v0.x, v0.y), pack_bf16(v0.z, v0.w), pack_bf16(v1.x, v1.y), pack_bf16(v1.z, v1.w));
+                    }
+                }
+                fence_async_smem();
+                ew_sync();
+                if (tid == 0) mbar_arrive(zready);
+                // ---- gating epilogue per pass
+                float yacc = 0.f;
+                for (int pass = 0; pass < NPASS; ++pass) {
+                    const int buf = pass & 1;
+                    mbar_wait(&acc_full[buf], acc_use[buf] & 1);
+                    acc_use[buf]++;
+                    tc_fence_after();
+                    // the four threads of a row take 16 / 12 / 12 / 12 of the pass's 52 neurons, four neurons per iteration
+                    const int n0 = part == 0 ? 0 : 16 + 12 * (part - 1), nq = part == 0 ? 4 : 3;
+#pragma unroll 1
+                    for (int q = 0; q < nq; ++q) {
+                        float s16[16];
+                        tmem_ld16(taddr + buf * PROWS + 4 * n0 + 16 * q, s16);
+                        float hn[4], cc[4], m[4];
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            float tg, th, gate;
+                            tanh2_sigmoid(s16[4 * jj + 0], s16[4 * jj + 1], s16[4 * jj + 2], tg, th, gate);
+                            hn[jj] = fmaf(gate, th - tg, tg);
+                            cc[jj] = s16[4 * jj + 3] + hn[jj];
+                        }
+                        mish4(cc, m);
+                        const int j = pass * PN + n0 + 4 * q;
+                        if (j < NC) {
+                            const float4 w4 = *reinterpret_cast<const float4*>(wouts + j);
+                            yacc = fmaf(m[0], w4.x, fmaf(m[1], w4.y, fmaf(m[2], w4.z, fmaf(m[3], w4.w, yacc))));
+                            const float4 h4 = make_float4(hn[0], hn[1], hn[2], hn[3]);
+                            *reinterpret_cast<float4*>(hbuf + h_index(t & 1, n_tiles, tile, row, j)) = h4;
+                            if (valid) {
+                                if (t == T - 1 && h_last) *reinterpret_cast<float4*>(h_last + b * NC + j) = h4;
+                                if (h_out) *reinterpret_cast<float4*>(h_out + (h_tm ? (int64_t)t * B + b : b * T + t) * NC + j) = h4;
+                            }
+                        }
+                    }
+                    tc_fence_before();
+                    mbar_arrive(&acc_empty[buf]);
+                }
+                if (part > 0) ys[(part - 1) * TM + row] = yacc;
+                ew_sync();
+                if (part == 0 && valid) y[y_tm ? (int64_t)t * B + b : b * T + t] = ((yacc + ys[row]) + (ys[TM + row] + ys[2 * TM + row])) + b_out;
+                ew_sync();          // h_t is visible to every thread of the tile before the next step reads it; ys is free again
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+
+constexpr size_t kWpackBytes = (size_t)NPASS * KC * PROWS * 16;
+
+bool has_path(int I_, int Ni, int Nc, int O) { return I_ == I && Ni == NI && Nc == NC && O == 1; }
+
+int64_t fwd_workspace_bytes(int64_t B) {
+    const int64_t n_tiles = (B + TM - 1) / TM;
+    return (int64_t)kWpackBytes + 2 * n_tiles * TM * NC * (int64_t)sizeof(float);
+}
+
+int fwd(const float* packed, const float* x, const float* h0, float* y, float* h_last, float* h_traj, int64_t B, int T, int flags,
+        void* ws, int64_t ws_bytes, cudaStream_t stream) {
+    VB_CHECK_ARG(ws && ws_bytes >= fwd_workspace_bytes(B), VB_ERR_WORKSPACE, "vb_liquid_bf16_fwd: workspace too small (%lld bytes, need %lld)",
+                 (long long)ws_bytes, (long long)fwd_workspace_bytes(B));
+    VB_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 127) == 0 && (!h0 || (reinterpret_cast<uintptr_t>(h0) & 15) == 0) &&
+                     (!h_last || (reinterpret_cast<uintptr_t>(h_last) & 15) == 0) && (!h_traj || (reinterpret_cast<uintptr_t>(h_traj) & 15) == 0),
+                 VB_ERR_ALIGNMENT, "vb_liquid_bf16_fwd: workspace must be 128-byte, h tensors 16-byte aligned");
+    __nv_bfloat16* wpack = reinterpret_cast<__nv_bfloat16*>(ws);
+    float* hbuf = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(ws) + kWpackBytes);
+    big_pack_kernel<<<296, 256, 0, stream>>>(packed, wpack);
+    VB_LAUNCH_CHECK();
+    LaunchCfg cfg;
+    int rc = cached_launch_cfg(liquid_big_fwd_kernel, NTHREADS, SMEM_BYTES, &cfg);
+    if (rc) return rc;
+    const int64_t n_tiles = (B + TM - 1) / TM;
+    const int sms = device_sms() > 0 ? device_sms() : 148;
+    const int grid = (int)(n_tiles < sms ? n_tiles : sms);
+    liquid_big_fwd_kernel<<<grid, NTHREADS, SMEM_BYTES, stream>>>(reinterpret_cast<const unsigned char*>(wpack), packed, x, h0, y, h_last, h_traj, hbuf,
+                                                                  B, T, flags);
+    VB_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace big
+}  // namespace vb

@@ -417,3 +417,50 @@ class SacHeadFn(torch.autograd.Function):
                 "vb_sac_head_bwd",
             )
         return dx, None, None, None, None, None
+
+
+def liquid_bf16_forward(x: torch.Tensor, h0: Optional[torch.Tensor], dims, masks, params, want_traj: bool = False):
+    """Inference forward of the 512-neuron class on tcgen05 in bf16 (vb_liquid_bf16_fwd): x [B,T,I] -> y [B,T,O], h_T [B,Nc]
+    (+ h_traj [B,T,Nc] when asked for).  No autograd graph: the backward of this class runs on the fp32 tile kernels."""
+    I, Ni, Nc, O = dims
+    L = _lib.lib()
+    _lib.require_cuda(x, "LiquidNCPNetwork.forward_seq_bf16")
+    if not L.vb_liquid_bf16_ok(I, Ni, Nc, O):
+        raise RuntimeError(f"no bf16 tensor-core forward for a liquid network of shape (in={I}, inter={Ni}, command={Nc}, out={O})")
+    dev = x.device
+    B, T, _ = x.shape
+    x, x_tm = _seq(x, T > 1)
+    h0c = _f32c(h0)
+    params = [_f32c(p.detach()) for p in params]
+    masks = tuple(_lib.mask_arg(m, dev) for m in masks)
+    heads_type = _lib.common_mask_type(masks[1:6])
+    if heads_type is None:
+        masks = (masks[0], *[m.contiguous() for m in masks[1:6]], masks[6])
+        heads_type = _lib.mask_type(masks[1])
+    with torch.cuda.device(dev):
+        st = _lib.stream_ptr(dev)
+        packed = torch.empty(L.vb_liquid_packed_floats(I, Ni, Nc, O), dtype=torch.float32, device=dev)
+        _count(1)
+        _lib.check(
+            L.vb_liquid_pack(
+                _lib.ptr(params[0]), _lib.ptr(params[1]), _lib.ptr(masks[0]), _lib.mask_type(masks[0]),
+                _lib.ptr_array([params[2 + 2 * k] for k in range(5)]), _lib.ptr_array([params[3 + 2 * k] for k in range(5)]),
+                _lib.ptr_array(list(masks[1:6])), heads_type,
+                _lib.ptr(params[12]), _lib.ptr(params[13]), _lib.ptr(masks[6]), _lib.mask_type(masks[6]),
+                I, Ni, Nc, O, _lib.ptr(packed), st,
+            ),
+            "vb_liquid_pack",
+        )
+        y = torch.empty((T, B, O), dtype=torch.float32, device=dev).permute(1, 0, 2)
+        h_last = torch.empty((B, Nc), dtype=torch.float32, device=dev)
+        h_traj = torch.empty((T, B, Nc), dtype=torch.float32, device=dev).permute(1, 0, 2) if want_traj else None
+        ws = _workspace(dev, L.vb_liquid_bf16_fwd_workspace_bytes(I, Ni, Nc, O, B, T))
+        flags = (X_TM if x_tm else 0) | Y_TM | H_TM
+        _count(2)
+        with _timed("liquid_bf16_fwd", 0):
+            _lib.check(
+                L.vb_liquid_bf16_fwd(_lib.ptr(packed), _lib.ptr(x), _lib.ptr(h0c), _lib.ptr(y), _lib.ptr(h_last), _lib.ptr(h_traj),
+                                     B, T, I, Ni, Nc, O, _lib.ptr(ws), ws.numel(), flags, st),
+                "vb_liquid_bf16_fwd",
+            )
+    return (y, h_last, h_traj) if want_traj else (y, h_last)

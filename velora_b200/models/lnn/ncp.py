@@ -119,6 +119,29 @@ class LiquidNCPNetwork(nn.Module):
         return (y, h_traj, h_last) if return_last else (y, h_traj)
 
 
+    @torch.jit.ignore
+    def forward_seq_bf16(self, x: torch.Tensor, h0: Optional[torch.Tensor] = None, return_traj: bool = False):
+        """Inference-only `forward_seq` with the cell's heads on the tensor cores in bf16 (bf16 operands, fp32 accumulation and
+        hidden state; agrees with `forward_seq` to ~1e-2 relative).  Available for the 512-neuron class (BASELINE config 4);
+        returns (y [B,T,out], h_T [B,Nc]) and the hidden trajectory when `return_traj`."""
+        if x.dim() != 3:
+            raise ValueError(f"Unsupported dimensionality: '{x.shape}'. Should be 3 dimensional with: '(batch_size, steps, features)'.")
+        dev = self._target_device()
+        x = x.to(dtype=torch.float32, device=dev)
+        if h0 is not None:
+            h0 = h0.to(dev)
+        cmd = self.command
+        heads = [cmd.g_head, cmd.h_head, cmd.f_head_to_g, cmd.f_head_to_h, cmd.proj]
+        masks = (self.inter.mask, *[h.mask for h in heads], self.motor.mask)
+        params: List[torch.Tensor] = [self.inter.weight, self.inter.bias]
+        for h in heads:
+            params += [h.weight, h.bias]
+        params += [self.motor.weight, self.motor.bias]
+        dims = (self.in_features, int(self.inter.out_features), int(cmd.n_hidden), int(self.motor.out_features))
+        with torch.no_grad():
+            return VF.liquid_bf16_forward(x, h0, dims, masks, params, want_traj=return_traj)
+
+
 class NCPNetwork(nn.Module):
     """SparseLinear -> Mish -> SparseLinear -> Mish -> SparseLinear (the SAC critics' network)."""
 
