@@ -312,6 +312,22 @@ def main():
         y, _, hl = net.forward_seq(x, None, return_last=True)
         torch.autograd.backward([y, hl], [ry, torch.ones_like(hl)])
 
+    # forward only, bf16 operands on tcgen05 (the backward of this class is not built): per-GPU share of config 4 at 8 GPUs
+    B4, T4 = (4096, 8) if args.quick else (32768, 64)
+    x4 = torch.randn(T4, B4, 8, device=dev).permute(1, 0, 2)
+    with torch.no_grad():
+        msf = gpu_time_ms(lambda: net.forward_seq_bf16(x4), warmup=2, iters=5)
+        xs4 = torch.randn(B, T, 8, device=dev)
+        msf32 = gpu_time_ms(lambda: net.forward_seq(xs4), warmup=1, iters=3)
+    fwd_flops = 2.0 * (8 * 308 + 517 * 816 + 204) * B4 * T4
+    emit(config=f"cfg4 LiquidNCPNetwork(8,512,1) FORWARD, batch {B4} x seq {T4}, bf16 operands on tcgen05 (vb_liquid_bf16_fwd)",
+         metric="sample_steps_per_s", value=B4 * T4 / (msf * 1e-3), ms=msf,
+         roofline={"bound": "tensor", "achieved": fwd_flops / (msf * 1e-3) / 1e12, "peak": pk.get("bf16_tflops_sustained", 1400.0), "unit": "TFLOP/s",
+                   "frac": fwd_flops / (msf * 1e-3) / 1e12 / pk.get("bf16_tflops_sustained", 1400.0),
+                   "algorithmic_flops_per_sample_step": 2.0 * (8 * 308 + 517 * 816 + 204)},
+         fp32_tile_kernels_forward_sample_steps_per_s=B * T / (msf32 * 1e-3),
+         note="includes the per-call weight pack (fp32 -> bf16 plane order); forward / inference only")
+    del x4, xs4
     ms4 = gpu_time_ms(step4, warmup=2, iters=5)
     flops = 3.149e6 * B * T
     emit(config=f"cfg4 LiquidNCPNetwork(8,512,1) fwd+bwd, batch {B} x seq {T}, fp32 generic tile kernels", metric="sample_steps_per_s",
