@@ -1,6 +1,7 @@
 // Prototype for BASELINE config 4 (LiquidNCPNetwork(8,512,1): Ni = 308, Nc = 204, 816 head outputs, K = 517):
 // forward recurrence with the heads GEMM on tcgen05 in bf16 (fp32 accumulate, fp32 state), one 128-sample tile per CTA,
-// warp-specialised: 16 element-wise warps (four threads per sample), one bulk-copy producer lane streaming the weight
+// warp-specialised: 12 element-wise warps (three threads per sample; the inter layer of step t+1 is computed into registers in the
+// shadow of step t's MMAs), one bulk-copy producer lane streaming the weight
 // block from L2 through a 3-stage ring, one MMA-issuing lane, accumulators double-buffered in TMEM (2 x 208 columns).
 // Not wired into the library: it exists to measure what the design of DESIGN.md section 4.7 delivers (L2 streaming rate,
 // MMA rate, element-wise cost) before the backward is designed around it.
@@ -10,6 +11,7 @@
 #include <cuda_bf16.h>
 #include <math.h>
 #include <stdlib.h>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -17,6 +19,7 @@
 
 using namespace vb;
 using namespace vb::tcx;
+template <int V> using IC = std::integral_constant<int, V>;
 
 constexpr int I = 8, NI = 308, NC = 204;
 constexpr int A_CHUNKS = 39;                 // a: 308 features + 4 zeros
@@ -27,16 +30,16 @@ constexpr int NPASS = 4, PN = 52, PROWS = 4 * PN;     // 52 neurons = 208 accumu
 constexpr int STAGE_CHUNKS = 6, NSTAGE_PER_PASS = KC / STAGE_CHUNKS;      // 11 stages of K = 48
 constexpr int STAGE_BYTES = STAGE_CHUNKS * PROWS * 16;                    // 19968
 constexpr int RING = 3;
-constexpr int EW = 512;                      // element-wise threads: FOUR per sample (warps w, w+4, w+8, w+12 share TMEM lanes)
+constexpr int EW = 384;                      // element-wise threads: THREE per sample (warps w, w+4, w+8 share TMEM lanes)
 constexpr int NTHREADS = EW + 64;            // + producer warp + MMA warp
 
 constexpr int S_Z = 0;
 constexpr int S_STAGE = S_Z + KC * PLANE;
-constexpr int S_WIN = S_STAGE + RING * STAGE_BYTES;            // fp32 [I][312]
-constexpr int S_BIN = S_WIN + I * 312 * 4;                     // fp32 [312]
-constexpr int S_WOUT = S_BIN + 312 * 4;                        // fp32 [208]
+constexpr int S_WIN = S_STAGE + RING * STAGE_BYTES;            // fp32 [I][320]
+constexpr int S_BIN = S_WIN + I * 320 * 4;                     // fp32 [320]
+constexpr int S_WOUT = S_BIN + 320 * 4;                        // fp32 [208]
 constexpr int S_YS = S_WOUT + 208 * 4;                         // fp32 [128]
-constexpr int S_BAR = S_YS + 3 * 128 * 4;
+constexpr int S_BAR = S_YS + 2 * 128 * 4;
 constexpr int SMEM_BYTES = S_BAR + 128;
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -58,7 +61,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 __host__ __device__ __forceinline__ size_t h_index(int t, int64_t n_tiles, int64_t tile, int row, int j) {
     return ((((size_t)t * n_tiles + tile) * (NC / 4) + j / 4) * TM + row) * 4 + (j & 3);
 }
-__device__ __forceinline__ void ew_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+__device__ __forceinline__ void ew_sync() { asm volatile("bar.sync 1, 384;" ::: "memory"); }
 
 __global__ void __launch_bounds__(NTHREADS, 1) big_fwd_kernel(const unsigned char* __restrict__ wpack, const float* __restrict__ w_in,
                                                               const float* __restrict__ b_in, const float* __restrict__ w_out, float b_out,
@@ -78,8 +81,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) big_fwd_kernel(const unsigned cha
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(zready + 1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    for (int e = tid; e < I * 312; e += NTHREADS) wins[e] = (e % 312) < NI ? w_in[(e / 312) * NI + e % 312] : 0.f;
-    for (int e = tid; e < 312; e += NTHREADS) bins[e] = e < NI ? b_in[e] : 0.f;
+    for (int e = tid; e < I * 320; e += NTHREADS) wins[e] = (e % 320) < NI ? w_in[(e / 320) * NI + e % 320] : 0.f;
+    for (int e = tid; e < 320; e += NTHREADS) bins[e] = e < NI ? b_in[e] : 0.f;
     for (int e = tid; e < 208; e += NTHREADS) wouts[e] = e < NC ? w_out[e] : 0.f;
     for (int e = tid; e < TM; e += NTHREADS) reinterpret_cast<uint4*>(zP)[(KC - 1) * TM + e] = make_uint4(0, 0, 0, 0);   // chunk 65: zeros
     if (warp == 0) {
@@ -150,24 +153,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) big_fwd_kernel(const unsigned cha
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int64_t b = tile * TM + row;
             const bool valid = b < B;
-            for (int t = 0; t < T; ++t, ++st) {
-                // ---- z~ = [mish(W_in x + b_in) | 0 | h_{t-1} | 1 | 0] as bf16 planes
+            uint4 areg[13];                       // this thread's 13 chunks of a = mish(W_in x + b_in), bf16
+            auto compute_a = [&](auto lo_c, auto hi_c, int t) {
+                constexpr int LO = decltype(lo_c)::value, HI = decltype(hi_c)::value;
                 float xr[I];
 #pragma unroll
                 for (int i = 0; i < I; ++i) xr[i] = valid ? __ldg(x + ((int64_t)t * B + b) * I + i) : 0.f;
-#ifdef NO_BUILD
-                const int c0 = 0, c1 = 0;
-#else
-                const int c0 = 10 * part, c1 = part == 3 ? A_CHUNKS : 10 * part + 10;
-#endif
-                for (int c = c0; c < c1; ++c) {
+#pragma unroll
+                for (int k = LO; k < HI; ++k) {
+                    const int c = 13 * part + k;
                     float u[8];
                     const float4 b0 = *reinterpret_cast<const float4*>(bins + 8 * c), b1 = *reinterpret_cast<const float4*>(bins + 8 * c + 4);
                     u[0] = b0.x; u[1] = b0.y; u[2] = b0.z; u[3] = b0.w; u[4] = b1.x; u[5] = b1.y; u[6] = b1.z; u[7] = b1.w;
 #pragma unroll
                     for (int i = 0; i < I; ++i) {
-                        const float4 w0 = *reinterpret_cast<const float4*>(wins + i * 312 + 8 * c);
-                        const float4 w1 = *reinterpret_cast<const float4*>(wins + i * 312 + 8 * c + 4);
+                        const float4 w0 = *reinterpret_cast<const float4*>(wins + i * 320 + 8 * c);
+                        const float4 w1 = *reinterpret_cast<const float4*>(wins + i * 320 + 8 * c + 4);
                         u[0] = fmaf(xr[i], w0.x, u[0]); u[1] = fmaf(xr[i], w0.y, u[1]); u[2] = fmaf(xr[i], w0.z, u[2]); u[3] = fmaf(xr[i], w0.w, u[3]);
                         u[4] = fmaf(xr[i], w1.x, u[4]); u[5] = fmaf(xr[i], w1.y, u[5]); u[6] = fmaf(xr[i], w1.z, u[6]); u[7] = fmaf(xr[i], w1.w, u[7]);
                     }
@@ -183,14 +184,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) big_fwd_kernel(const unsigned cha
 #pragma unroll
                     for (int e = 0; e < 8; ++e)
                         if (8 * c + e >= NI) a[e] = 0.f;
-                    reinterpret_cast<uint4*>(zP)[c * TM + row] =
-                        make_uint4(pack_bf16(a[0], a[1]), pack_bf16(a[2], a[3]), pack_bf16(a[4], a[5]), pack_bf16(a[6], a[7]));
+                    areg[k] = make_uint4(pack_bf16(a[0], a[1]), pack_bf16(a[2], a[3]), pack_bf16(a[4], a[5]), pack_bf16(a[6], a[7]));
                 }
+            };
+            for (int t = 0; t < T; ++t, ++st) {
+                // ---- z~ = [mish(W_in x + b_in) | 0 | h_{t-1} | 1 | 0] as bf16 planes; the a-part was computed into registers during the
+                //      previous step's MMAs (or right here for the first step of a tile)
+                if (t == 0) compute_a(IC<0>{}, IC<13>{}, 0);
+#pragma unroll
+                for (int k = 0; k < 13; ++k) reinterpret_cast<uint4*>(zP)[(13 * part + k) * TM + row] = areg[k];
                 {
 #ifdef NO_BUILD
                     const int hc0 = 0, hc1 = 0;
 #else
-                    const int hc0 = part < 2 ? 7 * part : 14 + 6 * (part - 2), hc1 = part < 2 ? hc0 + 7 : hc0 + 6;
+                    const int hc0 = 9 * part, hc1 = part == 2 ? H_CHUNKS : hc0 + 9;
 #endif
                     for (int c = hc0; c < hc1; ++c) {
                         float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
@@ -206,6 +213,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) big_fwd_kernel(const unsigned cha
                 fence_async_smem();
                 ew_sync();
                 if (tid == 0) mbar_arrive(zready);
+                if (t + 1 < T) compute_a(IC<0>{}, IC<4>{}, t + 1);          // pieces of the next step's inter layer, in the shadow of the MMAs
                 // ---- gating epilogue per pass
                 float yacc = 0.f;
                 for (int pass = 0; pass < NPASS; ++pass) {
@@ -214,7 +222,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) big_fwd_kernel(const unsigned cha
                     acc_use[buf]++;
                     tc_fence_after();
                     // the four threads of a row take 16 / 12 / 12 / 12 of the pass's 52 neurons, four neurons per iteration
-                    const int n0 = part == 0 ? 0 : 16 + 12 * (part - 1), nq = part == 0 ? 4 : 3;
+                    const int n0 = part == 0 ? 0 : 20 + 16 * (part - 1), nq = part == 0 ? 5 : 4;
 #ifdef NO_EPI
                     for (int q = 0; q < 0; ++q) {
 #else
@@ -241,10 +249,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) big_fwd_kernel(const unsigned cha
                     }
                     tc_fence_before();
                     mbar_arrive(&acc_empty[buf]);
+                    if (t + 1 < T) {
+                        if (pass == 0) compute_a(IC<4>{}, IC<7>{}, t + 1);
+                        else if (pass == 1) compute_a(IC<7>{}, IC<10>{}, t + 1);
+                        else if (pass == 2) compute_a(IC<10>{}, IC<13>{}, t + 1);
+                    }
                 }
                 if (part > 0) ys[(part - 1) * TM + row] = yacc;
                 ew_sync();
-                if (part == 0 && valid) y[(int64_t)t * B + b] = ((yacc + ys[row]) + (ys[TM + row] + ys[2 * TM + row])) + b_out;
+                if (part == 0 && valid) y[(int64_t)t * B + b] = (yacc + ys[row]) + ys[TM + row] + b_out;
                 ew_sync();          // h_t is visible to every thread of the tile before the next step reads it; ys is free again
             }
         }

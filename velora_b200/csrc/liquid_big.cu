@@ -4,13 +4,15 @@
 // Per sample and step the heads are a 517 x 816 contraction: one CTA owns a 128-sample tile and keeps z~ = [mish(W_in x) | h | 1]
 // as 66 bf16 operand planes in shared memory (132 KB); the 816 x 528 bf16 weight block (858 KB, pre-arranged in plane order by
 // big_pack_kernel) is streamed from L2 by one bulk-copy producer lane through a 3-stage ring; one lane issues the MMAs (four
-// passes of 52 neurons = 208 accumulator columns, double-buffered in TMEM); 16 element-wise warps (four threads per sample)
-// rebuild z~ at the start of a step and run the gating epilogue of pass p while the MMAs of pass p+1 execute.  h travels between
+// passes of 52 neurons = 208 accumulator columns, double-buffered in TMEM); 12 element-wise warps (three threads per sample)
+// run the gating epilogue of pass p while the MMAs of pass p+1 execute and, between the epilogues, compute the inter layer of
+// step t+1 into registers, so that the rebuild of z~ at the step boundary is only stores plus the conversion of h.  h travels between
 // steps through a two-slot scratch buffer in a tile-interleaved order ([tile][Nc/4][128 rows][4]) so that every warp access is
 // 512 contiguous bytes.  Measured (profiles/microbench/big_fwd_proto_r01.log): 0.82 G sample-steps/s = 690 TFLOP/s; the
 // MMA + streaming pipeline alone sustains 1.33 PFLOP/s, what is exposed is the rebuild of z~.
 // The backward of this class is not built: training this shape still runs on the generic fp32 kernels.
 #include <cuda_bf16.h>
+#include <type_traits>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -18,6 +20,7 @@
 namespace vb {
 namespace big {
 using namespace tcx;
+template <int V> using IC = std::integral_constant<int, V>;
 
 constexpr int I = 8, NI = 308, NC = 204;
 constexpr int A_CHUNKS = 39;                 // a: 308 features + 4 zeros
@@ -28,16 +31,16 @@ constexpr int NPASS = 4, PN = 52, PROWS = 4 * PN;     // 52 neurons = 208 accumu
 constexpr int STAGE_CHUNKS = 6, NSTAGE_PER_PASS = KC / STAGE_CHUNKS;      // 11 stages of K = 48
 constexpr int STAGE_BYTES = STAGE_CHUNKS * PROWS * 16;                    // 19968
 constexpr int RING = 3;
-constexpr int EW = 512;                      // element-wise threads: FOUR per sample (warps w, w+4, w+8, w+12 share TMEM lanes)
+constexpr int EW = 384;                      // element-wise threads: THREE per sample (warps w, w+4, w+8 share TMEM lanes)
 constexpr int NTHREADS = EW + 64;            // + producer warp + MMA warp
 
 constexpr int S_Z = 0;
 constexpr int S_STAGE = S_Z + KC * PLANE;
-constexpr int S_WIN = S_STAGE + RING * STAGE_BYTES;            // fp32 [I][312]
-constexpr int S_BIN = S_WIN + I * 312 * 4;                     // fp32 [312]
-constexpr int S_WOUT = S_BIN + 312 * 4;                        // fp32 [208]
+constexpr int S_WIN = S_STAGE + RING * STAGE_BYTES;            // fp32 [I][320]
+constexpr int S_BIN = S_WIN + I * 320 * 4;                     // fp32 [320]
+constexpr int S_WOUT = S_BIN + 320 * 4;                        // fp32 [208]
 constexpr int S_YS = S_WOUT + 208 * 4;                         // fp32 [128]
-constexpr int S_BAR = S_YS + 3 * 128 * 4;
+constexpr int S_BAR = S_YS + 2 * 128 * 4;
 constexpr int SMEM_BYTES = S_BAR + 128;
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -59,7 +62,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 __host__ __device__ __forceinline__ size_t h_index(int t, int64_t n_tiles, int64_t tile, int row, int j) {
     return ((((size_t)t * n_tiles + tile) * (NC / 4) + j / 4) * TM + row) * 4 + (j & 3);
 }
-__device__ __forceinline__ void ew_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+__device__ __forceinline__ void ew_sync() { asm volatile("bar.sync 1, 384;" ::: "memory"); }
 
 
 // weight block in plane order: [pass][stage][chunk (6)][row (208)][8 bf16]; row r = 4 jj + hs of neuron j = pass * 52 + jj,
@@ -102,8 +105,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) liquid_big_fwd_kernel(const unsig
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     constexpr LiquidLayout L(I, NI, NC, 1);
-    for (int e = tid; e < I * 312; e += NTHREADS) wins[e] = (e % 312) < NI ? __ldg(packed + L.win_t + (e / 312) * L.NIp + e % 312) : 0.f;
-    for (int e = tid; e < 312; e += NTHREADS) bins[e] = e < NI ? __ldg(packed + L.b_in + e) : 0.f;
+    for (int e = tid; e < I * 320; e += NTHREADS) wins[e] = (e % 320) < NI ? __ldg(packed + L.win_t + (e / 320) * L.NIp + e % 320) : 0.f;
+    for (int e = tid; e < 320; e += NTHREADS) bins[e] = e < NI ? __ldg(packed + L.b_in + e) : 0.f;
     for (int e = tid; e < 208; e += NTHREADS) wouts[e] = e < NC ? __ldg(packed + L.wout + e) : 0.f;
     const float b_out = __ldg(packed + L.b_out);
     const bool x_tm = flags & VB_FLAG_X_TIME_MAJOR, y_tm = flags & VB_FLAG_Y_TIME_MAJOR, h_tm = flags & VB_FLAG_H_TIME_MAJOR;
@@ -176,20 +179,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) liquid_big_fwd_kernel(const unsig
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int64_t b = tile * TM + row;
             const bool valid = b < B;
-            for (int t = 0; t < T; ++t, ++st) {
-                // ---- z~ = [mish(W_in x + b_in) | 0 | h_{t-1} | 1 | 0] as bf16 planes
+            uint4 areg[13];                       // this thread's 13 chunks of a = mish(W_in x + b_in), bf16
+            auto compute_a = [&](auto lo_c, auto hi_c, int t) {
+                constexpr int LO = decltype(lo_c)::value, HI = decltype(hi_c)::value;
                 float xr[I];
 #pragma unroll
                 for (int i = 0; i < I; ++i) xr[i] = valid ? __ldg(x + (x_tm ? (int64_t)t * B + b : b * T + t) * I + i) : 0.f;
-                const int c0 = 10 * part, c1 = part == 3 ? A_CHUNKS : 10 * part + 10;
-                for (int c = c0; c < c1; ++c) {
+#pragma unroll
+                for (int k = LO; k < HI; ++k) {
+                    const int c = 13 * part + k;
                     float u[8];
                     const float4 b0 = *reinterpret_cast<const float4*>(bins + 8 * c), b1 = *reinterpret_cast<const float4*>(bins + 8 * c + 4);
                     u[0] = b0.x; u[1] = b0.y; u[2] = b0.z; u[3] = b0.w; u[4] = b1.x; u[5] = b1.y; u[6] = b1.z; u[7] = b1.w;
 #pragma unroll
                     for (int i = 0; i < I; ++i) {
-                        const float4 w0 = *reinterpret_cast<const float4*>(wins + i * 312 + 8 * c);
-                        const float4 w1 = *reinterpret_cast<const float4*>(wins + i * 312 + 8 * c + 4);
+                        const float4 w0 = *reinterpret_cast<const float4*>(wins + i * 320 + 8 * c);
+                        const float4 w1 = *reinterpret_cast<const float4*>(wins + i * 320 + 8 * c + 4);
                         u[0] = fmaf(xr[i], w0.x, u[0]); u[1] = fmaf(xr[i], w0.y, u[1]); u[2] = fmaf(xr[i], w0.z, u[2]); u[3] = fmaf(xr[i], w0.w, u[3]);
                         u[4] = fmaf(xr[i], w1.x, u[4]); u[5] = fmaf(xr[i], w1.y, u[5]); u[6] = fmaf(xr[i], w1.z, u[6]); u[7] = fmaf(xr[i], w1.w, u[7]);
                     }
@@ -205,11 +210,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) liquid_big_fwd_kernel(const unsig
 #pragma unroll
                     for (int e = 0; e < 8; ++e)
                         if (8 * c + e >= NI) a[e] = 0.f;
-                    reinterpret_cast<uint4*>(zP)[c * TM + row] =
-                        make_uint4(pack_bf16(a[0], a[1]), pack_bf16(a[2], a[3]), pack_bf16(a[4], a[5]), pack_bf16(a[6], a[7]));
+                    areg[k] = make_uint4(pack_bf16(a[0], a[1]), pack_bf16(a[2], a[3]), pack_bf16(a[4], a[5]), pack_bf16(a[6], a[7]));
                 }
+            };
+            for (int t = 0; t < T; ++t, ++st) {
+                // ---- z~ = [mish(W_in x + b_in) | 0 | h_{t-1} | 1 | 0] as bf16 planes; the a-part was computed into registers during the
+                //      previous step's MMAs (or right here for the first step of a tile)
+                if (t == 0) compute_a(IC<0>{}, IC<13>{}, 0);
+#pragma unroll
+                for (int k = 0; k < 13; ++k) reinterpret_cast<uint4*>(zP)[(13 * part + k) * TM + row] = areg[k];
                 {
-                    const int hc0 = part < 2 ? 7 * part : 14 + 6 * (part - 2), hc1 = part < 2 ? hc0 + 7 : hc0 + 6;
+                    const int hc0 = 9 * part, hc1 = part == 2 ? H_CHUNKS : hc0 + 9;
                     for (int c = hc0; c < hc1; ++c) {
                         float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
                         if (t > 0) {
@@ -227,6 +238,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) liquid_big_fwd_kernel(const unsig
                 fence_async_smem();
                 ew_sync();
                 if (tid == 0) mbar_arrive(zready);
+                if (t + 1 < T) compute_a(IC<0>{}, IC<4>{}, t + 1);          // pieces of the next step's inter layer, in the shadow of the MMAs
                 // ---- gating epilogue per pass
                 float yacc = 0.f;
                 for (int pass = 0; pass < NPASS; ++pass) {
@@ -235,7 +247,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) liquid_big_fwd_kernel(const unsig
                     acc_use[buf]++;
                     tc_fence_after();
                     // the four threads of a row take 16 / 12 / 12 / 12 of the pass's 52 neurons, four neurons per iteration
-                    const int n0 = part == 0 ? 0 : 16 + 12 * (part - 1), nq = part == 0 ? 4 : 3;
+                    const int n0 = part == 0 ? 0 : 20 + 16 * (part - 1), nq = part == 0 ? 5 : 4;
 #pragma unroll 1
                     for (int q = 0; q < nq; ++q) {
                         float s16[16];
@@ -263,10 +275,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) liquid_big_fwd_kernel(const unsig
                     }
                     tc_fence_before();
                     mbar_arrive(&acc_empty[buf]);
+                    if (t + 1 < T) {
+                        if (pass == 0) compute_a(IC<4>{}, IC<7>{}, t + 1);
+                        else if (pass == 1) compute_a(IC<7>{}, IC<10>{}, t + 1);
+                        else if (pass == 2) compute_a(IC<10>{}, IC<13>{}, t + 1);
+                    }
                 }
                 if (part > 0) ys[(part - 1) * TM + row] = yacc;
                 ew_sync();
-                if (part == 0 && valid) y[y_tm ? (int64_t)t * B + b : b * T + t] = ((yacc + ys[row]) + (ys[TM + row] + ys[2 * TM + row])) + b_out;
+                if (part == 0 && valid) y[y_tm ? (int64_t)t * B + b : b * T + t] = (yacc + ys[row]) + ys[TM + row] + b_out;
                 ew_sync();          // h_t is visible to every thread of the tile before the next step reads it; ys is free again
             }
         }
