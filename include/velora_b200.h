@@ -47,7 +47,7 @@
 extern "C" {
 #endif
 
-#define VB_ABI_VERSION 1
+#define VB_ABI_VERSION 2      /* 2: layout flags, optimizer / policy-head / packed-gather / bf16-forward entry points added */
 
 /* argument errors */
 #define VB_ERR_NULL_POINTER (-1)
