@@ -207,7 +207,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(raw, name), name
     lib = _lib.lib()
-    assert lib.vb_query(0) == 1 and lib.vb_query(1) == 100          # ABI version, built for sm_100a
+    assert lib.vb_query(0) == 2 and lib.vb_query(1) == 100          # ABI version, built for sm_100a
     # pure host-side queries work without a device
     assert lib.vb_liquid_packed_floats(4, 12, 8, 2) == 752 + 48 + 640 + 32
     assert lib.vb_liquid_grad_floats(4, 12, 8, 2) == 752
