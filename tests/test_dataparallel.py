@@ -60,8 +60,21 @@ def _worker(rank, world, port, out):
     dp.configure(True, reduce="mean")
     t = torch.full((3,), float(rank + 1))
     dp.maybe_allreduce(t)
+    # policy noise: every rank draws the GLOBAL batch's noise and keeps its shard (functional.standard_normal_like)
+    from velora_b200 import functional as VF
+
+    torch.manual_seed(123)
+    local = VF.standard_normal_like(torch.zeros(5, 3))
+    shards = [torch.empty_like(local) for _ in range(world)]
+    dist.all_gather(shards, local)
+    torch.manual_seed(123)
+    dp.configure(False)
+    whole_noise = VF.standard_normal_like(torch.zeros(5 * world, 3))
+    dp.configure(True, reduce="mean")
+    noise_ok = bool(torch.equal(torch.cat(shards), whole_noise)) and dp.rank() == rank
     if rank == 0:
-        torch.save({"same_params": same_params, "err": err, "bounds": (lo_, hi_), "mean": t.tolist(), "world": dp.world_size()}, out)
+        torch.save({"same_params": same_params, "err": err, "bounds": (lo_, hi_), "mean": t.tolist(), "world": dp.world_size(),
+                    "noise_ok": noise_ok}, out)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -74,6 +87,7 @@ def test_two_rank_gloo(tmp_path):
     assert r["bounds"] == (0, 5)
     assert r["err"] < 1e-12          # sum of shard gradients == gradient of the whole batch
     assert r["mean"] == [1.5, 1.5, 1.5]
+    assert r["noise_ok"]             # the ranks' noise shards concatenate to the single-process draw of the global batch
 
 
 def test_shard_bounds_cover_batch():
