@@ -94,6 +94,41 @@ def liquid_seq_forward(params, x_seq: np.ndarray, h0: Optional[np.ndarray], dtyp
     return np.stack(ys, 1), np.stack(hs, 1), caches
 
 
+def bf16_round(a: np.ndarray) -> np.ndarray:
+    """float32 -> bfloat16 (round to nearest even) -> float32, the rounding `cvt.rn.bf16x2.f32` applies."""
+    u = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+    r = ((u >> 16) & 1) + np.uint32(0x7FFF)
+    return ((u + r) & np.uint32(0xFFFF0000)).view(np.float32)
+
+
+def liquid_seq_forward_bf16(params, x_seq: np.ndarray, h0: Optional[np.ndarray]):
+    """The arithmetic contract of vb_liquid_bf16_fwd (csrc/liquid_big.cu): the cell's five heads see bf16-rounded operands
+    (z = [mish(inter x) | h], the masked head weights with the two f heads summed in fp32 first, and their biases) and
+    accumulate without further rounding; everything else - inter layer, activations, the hidden state, the motor layer - is
+    float32 (evaluated here in float64).  Returns y[B,T,O], h_traj[B,T,Nc]."""
+    p = _cast(params, np.float64)
+    x_seq = np.asarray(x_seq, dtype=np.float64)
+    B, T, _ = x_seq.shape
+    nc = p["command.g_head.weight"].shape[0]
+    Wm = lambda k: (p[f"command.{k}.weight"] * p[f"command.{k}.mask"]).astype(np.float32)   # noqa: E731
+    wf = (Wm("f_head_to_g").astype(np.float32) + Wm("f_head_to_h").astype(np.float32)).astype(np.float32)
+    bf = (p["command.f_head_to_g.bias"].astype(np.float32) + p["command.f_head_to_h.bias"].astype(np.float32)).astype(np.float32)
+    W = {"g": bf16_round(Wm("g_head")), "h": bf16_round(Wm("h_head")), "f": bf16_round(wf), "p": bf16_round(Wm("proj"))}
+    b = {"g": bf16_round(p["command.g_head.bias"]), "h": bf16_round(p["command.h_head.bias"]), "f": bf16_round(bf),
+         "p": bf16_round(p["command.proj.bias"])}
+    h = np.zeros((B, nc)) if h0 is None else np.asarray(h0, dtype=np.float64)
+    ys, hs = [], []
+    for t in range(T):
+        a = mish(masked_linear(x_seq[:, t], p["inter.weight"], p["inter.mask"], p["inter.bias"]))
+        z = bf16_round(np.concatenate([a, h], axis=1)).astype(np.float64)
+        s = {k: z @ W[k].astype(np.float64).T + b[k].astype(np.float64) for k in W}
+        tg, th, gate = np.tanh(s["g"]), np.tanh(s["h"]), sigmoid(s["f"])
+        h = tg * (1.0 - gate) + gate * th
+        ys.append(masked_linear(mish(s["p"] + h), p["motor.weight"], p["motor.mask"], p["motor.bias"]))
+        hs.append(h)
+    return np.stack(ys, 1), np.stack(hs, 1)
+
+
 def liquid_seq_backward(params, caches, dy: np.ndarray, dh_traj: np.ndarray, dtype=np.float64):
     """Hand-derived BPTT.  dy[B,T,O] and dh_traj[B,T,Nc] are the loss gradients w.r.t. the two outputs.
 

@@ -200,3 +200,8 @@ def test_train_discrete_golden_regenerates(golden):
     assert set(fresh) == set(d.keys())
     for k, v in fresh.items():
         assert np.array_equal(np.asarray(v), d[k]), k
+
+
+def test_bf16_rounding_helper_matches_torch():
+    a = (np.random.default_rng(0).standard_normal(4096) * np.array([1e-3, 1.0, 300.0, 1e6]).repeat(1024)).astype(np.float32)
+    assert np.array_equal(lo.bf16_round(a), torch.tensor(a).to(torch.bfloat16).float().numpy())
