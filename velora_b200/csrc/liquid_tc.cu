@@ -1,11 +1,13 @@
 // Tensor-core (tcgen05 / TMEM) kernels for the 20-neuron class of LiquidNCPNetwork.
 //
 // Measured notes (profiles/r01): one tcgen05.mma costs the issuing CTA ~60-95 cycles of serial latency whatever its shape
-// (N = 16..96, M = 64/128, SS or TS operands) and ~47-50 cycles of SM time when two CTAs interleave, so the design
-// minimises the NUMBER of MMAs per step (12 heads + 12 dz + 8 dW) rather than their size; building the two 64-bit
-// descriptors at issue time is free (it hides inside that latency; a precomputed table was slower).
+// (N = 16..96, M = 64/128, SS or TS operands) and ~47-50 cycles of SM time when two CTAs interleave - it is bounded by the
+// fetch of the 4 KB A operand - so the design minimises the NUMBER of MMAs per step rather than their size: the forward
+// stacks parts along K and N (5 MMAs of N = 96), the backward issues 12 heads + 12 dz + 8 dW (its 128 TMEM columns per CTA
+// leave no room for the stacked forms); building the two 64-bit descriptors at issue time is free (it hides inside that
+// latency; a precomputed table was slower).
 // cudaOccupancyMaxActiveBlocksPerMultiprocessor reports 1 CTA/SM for any kernel that allocates TMEM; the real limits
-// (shared memory, registers, 512 TMEM columns) allow 4 (backward) and 8 (forward) here.
+// (shared memory, registers, 512 TMEM columns) allow 4 CTAs per SM for both kernels here.
 //
 // Why: the FFMA kernels (liquid_small.cu) spend ~2200 of their 4240 warp-instructions per step on three small
 // contractions (head pre-activations, dz = ds W, dW = ds^T z) plus ~850 uniform constant loads feeding them
