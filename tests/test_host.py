@@ -263,3 +263,19 @@ def test_dataparallel_helpers_single_process():
     t = torch.ones(3)
     dp.maybe_allreduce(t)                                  # disabled: no-op
     assert torch.equal(t, torch.ones(3))
+
+
+def test_fused_adam_argument_contract():
+    """FusedAdam is the plain Adam the reference constructs: other variants are refused at construction; the optimizer state
+    layout is torch's capturable one; without CUDA the step fails loudly instead of falling back."""
+    from velora_b200.optim import FusedAdam
+
+    p = torch.nn.Parameter(torch.ones(3))
+    for bad in (dict(weight_decay=0.1), dict(amsgrad=True), dict(maximize=True)):
+        with pytest.raises(ValueError):
+            FusedAdam([p], **bad)
+    opt = FusedAdam([p], lr=1e-3)
+    assert opt.defaults["capturable"] is True and opt.defaults["weight_decay"] == 0.0
+    p.grad = torch.ones(3)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        opt.step()
