@@ -279,3 +279,44 @@ def test_fused_adam_argument_contract():
     p.grad = torch.ones(3)
     with pytest.raises(RuntimeError, match="CUDA"):
         opt.step()
+
+
+def test_state_dicts_round_trip_with_the_reference_classes():
+    """Checkpoint compatibility: state dicts of the mirrored networks and SAC heads load into the
+    unmodified reference classes with strict=True and back, key for key and bit for bit."""
+    from oracle import ref_import
+
+    if not ref_import.reference_available():
+        pytest.skip("reference tree not present (GPU box)")
+    import velora_b200 as vb
+    from velora_b200.models.lnn import LiquidNCPNetwork, NCPNetwork
+    from velora_b200.models.sac import SACActor, SACActorDiscrete, SACCriticNCP, SACCriticNCPDiscrete
+
+    ref = ref_import.import_reference()
+    import velora.models.sac.continuous as rc
+    import velora.models.sac.discrete as rd
+
+    one, zero = torch.tensor([1.0]), torch.tensor([0.0])
+    pairs = [
+        (lambda: LiquidNCPNetwork(10, 20, 5), lambda: ref.LiquidNCPNetwork(10, 20, 5)),
+        (lambda: NCPNetwork(5, 128, 1), lambda: ref.NCPNetwork(5, 128, 1)),
+        (lambda: SACActor(4, 20, 1, one, zero), lambda: rc.SACActor(4, 20, 1, one, zero)),
+        (lambda: SACCriticNCP(4, 128, 1), lambda: rc.SACCriticNCP(4, 128, 1)),
+        (lambda: SACActorDiscrete(4, 20, 2), lambda: rd.SACActorDiscrete(4, 20, 2)),
+        (lambda: SACCriticNCPDiscrete(4, 128, 2), lambda: rd.SACCriticNCPDiscrete(4, 128, 2)),
+    ]
+    for make_ours, make_ref in pairs:
+        vb.set_seed(3)
+        ours = make_ours()
+        ref.set_seed(4)
+        theirs = make_ref()
+        sd_ours, sd_theirs = ours.state_dict(), theirs.state_dict()
+        assert list(sd_ours.keys()) == list(sd_theirs.keys())
+        theirs.load_state_dict(sd_ours, strict=True)          # ours -> reference
+        for k, v in theirs.state_dict().items():
+            assert torch.equal(v, sd_ours[k]), k
+        ref.set_seed(5)
+        other = make_ref()
+        ours.load_state_dict(other.state_dict(), strict=True)  # reference -> ours
+        for k, v in ours.state_dict().items():
+            assert torch.equal(v, other.state_dict()[k]), k
