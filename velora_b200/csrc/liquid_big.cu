@@ -31,6 +31,7 @@ constexpr int NPASS = 4, PN = 52, PROWS = 4 * PN;     // 52 neurons = 208 accumu
 constexpr int STAGE_CHUNKS = 6, NSTAGE_PER_PASS = KC / STAGE_CHUNKS;      // 11 stages of K = 48
 constexpr int STAGE_BYTES = STAGE_CHUNKS * PROWS * 16;                    // 19968
 constexpr int RING = 3;
+constexpr int A_STAGES = 6;                  // stages 0..5 (chunks 0..35) contract over the a-part of z~ only
 constexpr int EW = 384;                      // element-wise threads: THREE per sample (warps w, w+4, w+8 share TMEM lanes)
 constexpr int NTHREADS = EW + 64;            // + producer warp + MMA warp
 
@@ -100,8 +101,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) liquid_big_fwd_kernel(const unsig
     uint64_t* empty = full + RING;                                    // [RING]
     uint64_t* acc_full = empty + RING;                                // [2]
     uint64_t* acc_empty = acc_full + 2;                               // [2]
-    uint64_t* zready = acc_empty + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(zready + 1);
+    uint64_t* zready = acc_empty + 2;                                 // all of z~ (a-part and h-part) is in place
+    uint64_t* aready = zready + 1;                                    // the a-part planes of the coming step are in place
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aready + 1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     constexpr LiquidLayout L(I, NI, NC, 1);
@@ -119,6 +121,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) liquid_big_fwd_kernel(const unsig
         for (int s = 0; s < RING; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], EW); }
         mbar_init(zready, 1);
+        mbar_init(aready, EW);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     fence_async_smem();
@@ -150,13 +153,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) liquid_big_fwd_kernel(const unsig
             const uint32_t z_addr = smem_u32(zP), st_addr = smem_u32(smem + S_STAGE);
             uint32_t it = 0, acc_use[2] = {0, 0};
             for (int64_t st = 0; st < n_steps; ++st) {
-                mbar_wait(zready, st & 1);
+                // the a-part of z~ (chunks 0..38) is stored while the previous step's last epilogue still runs: the first six stages of
+                // pass 0 only contract over those chunks and start before the hidden state has been converted
+                mbar_wait(aready, st & 1);
                 tc_fence_after();
                 for (int pass = 0; pass < NPASS; ++pass) {
                     const int buf = pass & 1;
                     if (acc_use[buf] > 0) { mbar_wait(&acc_empty[buf], (acc_use[buf] - 1) & 1); tc_fence_after(); }
                     for (int s = 0; s < NSTAGE_PER_PASS; ++s, ++it) {
                         const int slot = it % RING;
+                        if (pass == 0 && s == A_STAGES) mbar_wait(zready, st & 1);
                         mbar_wait(&full[slot], (it / RING) & 1);
                         tc_fence_after();
 #pragma unroll
@@ -216,9 +222,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) liquid_big_fwd_kernel(const unsig
             for (int t = 0; t < T; ++t, ++st) {
                 // ---- z~ = [mish(W_in x + b_in) | 0 | h_{t-1} | 1 | 0] as bf16 planes; the a-part was computed into registers during the
                 //      previous step's MMAs (or right here for the first step of a tile)
-                if (t == 0) compute_a(IC<0>{}, IC<13>{}, 0);
+                if (t == 0) {
+                    compute_a(IC<0>{}, IC<13>{}, 0);
 #pragma unroll
-                for (int k = 0; k < 13; ++k) reinterpret_cast<uint4*>(zP)[(13 * part + k) * TM + row] = areg[k];
+                    for (int k = 0; k < 13; ++k) reinterpret_cast<uint4*>(zP)[(13 * part + k) * TM + row] = areg[k];
+                    fence_async_smem();
+                    mbar_arrive(aready);
+                }
                 {
                     const int hc0 = 9 * part, hc1 = part == 2 ? H_CHUNKS : hc0 + 9;
                     for (int c = hc0; c < hc1; ++c) {
@@ -246,6 +256,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) liquid_big_fwd_kernel(const unsig
                     mbar_wait(&acc_full[buf], acc_use[buf] & 1);
                     acc_use[buf]++;
                     tc_fence_after();
+                    if (pass == NPASS - 1 && t + 1 < T) {
+                        // every MMA of this step has completed: the a-planes are free, the next step's a-part goes in now
+#pragma unroll
+                        for (int k = 0; k < 13; ++k) reinterpret_cast<uint4*>(zP)[(13 * part + k) * TM + row] = areg[k];
+                        fence_async_smem();
+                        mbar_arrive(aready);
+                    }
                     // the four threads of a row take 16 / 12 / 12 / 12 of the pass's 52 neurons, four neurons per iteration
                     const int n0 = part == 0 ? 0 : 20 + 16 * (part - 1), nq = part == 0 ? 5 : 4;
 #pragma unroll 1
