@@ -320,3 +320,26 @@ def test_state_dicts_round_trip_with_the_reference_classes():
         ours.load_state_dict(other.state_dict(), strict=True)  # reference -> ours
         for k, v in ours.state_dict().items():
             assert torch.equal(v, other.state_dict()[k]), k
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the oracle's CPU port timed on the host cores) prints ONE JSON line with the keys the driver
+    reads; runs without a GPU."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                        "--batch", "256", "--seq", "4"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "liquid_cell_fwd_bwd_sample_steps_per_s" and d["unit"] == "sample-steps/s"
+    for key in ("value", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config",
+                "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
