@@ -12,11 +12,11 @@ from typing import Any, Dict, Literal
 
 import torch
 
-from velora_b200.buffer.experience import BatchExperience
+from velora_b200.buffer.experience import FIELD_NAMES, BatchExperience
 
 MetaDataKeys = Literal["capacity", "state_dim", "action_dim", "hidden_dim", "position", "size", "device"]
 BufferKeys = Literal["states", "actions", "rewards", "next_states", "dones", "hiddens"]
-FIELDS = ("states", "actions", "rewards", "next_states", "dones", "hiddens")
+FIELDS = FIELD_NAMES
 
 
 class BufferBase:
