@@ -93,8 +93,15 @@ def test_two_rank_gloo(tmp_path):
 def test_shard_bounds_cover_batch():
     from velora_b200 import dataparallel as dp
 
-    for n in (1, 7, 8, 1_048_576):
+    import pytest
+
+    for n in (8, 64, 1_048_576):
         for w in (1, 2, 4, 8):
             spans = [dp.shard_bounds(n, r, w) for r in range(w)]
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert len({b - a for a, b in spans}) == 1          # equal shards: the noise slicing and reduce='mean' rely on it
+    # uneven splits are refused instead of silently giving the last rank the wrong noise rows (B = 10 over 4 ranks)
+    for n, w in ((10, 4), (7, 2), (1, 8)):
+        with pytest.raises(ValueError, match="does not divide evenly"):
+            dp.shard_bounds(n, 0, w)

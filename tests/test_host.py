@@ -207,7 +207,8 @@ def test_library_loads_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(raw, name), name
     lib = _lib.lib()
-    assert lib.vb_query(0) == 2 and lib.vb_query(1) == 100          # ABI version, built for sm_100a
+    abi = int(re.search(r"#define\s+VB_ABI_VERSION\s+(\d+)", header).group(1))
+    assert lib.vb_query(0) == abi and lib.vb_query(1) == 100        # ABI version of the header, built for sm_100a
     # pure host-side queries work without a device
     assert lib.vb_liquid_packed_floats(4, 12, 8, 2) == 752 + 48 + 640 + 32
     assert lib.vb_liquid_grad_floats(4, 12, 8, 2) == 752
@@ -216,6 +217,15 @@ def test_library_loads_and_exports_every_declared_symbol():
     # argument errors are reported, not crashed on
     assert lib.vb_liquid_fwd(None, None, None, None, None, 1, 1, 4, 12, 8, 2, None, 0, 0, None) == -1
     assert b"null pointer" in lib.vb_last_error()
+
+
+def test_graft_entry_build_compiles_and_loads():
+    """`__graft_entry__.build()` (the driver's "does it build" check) compiles every CUDA source for sm_100a, loads the library
+    and checks its ABI version against the header."""
+    import __graft_entry__ as entry
+
+    entry.build()
+    assert os.path.isfile(_lib.LIB_PATH)
 
 
 def test_packed_row_layout_keeps_vector_alignment():
@@ -258,7 +268,7 @@ def test_dataparallel_helpers_single_process():
     from velora_b200 import dataparallel as dp
 
     assert dp.world_size() == 1 and dp.rank() == 0 and not dp.is_enabled()
-    assert dp.shard_bounds(10, rank=0, world=4) == (0, 3) and dp.shard_bounds(10, rank=3, world=4) == (9, 10)
+    assert dp.shard_bounds(12, rank=0, world=4) == (0, 3) and dp.shard_bounds(12, rank=3, world=4) == (9, 12)
     assert dp.shard_bounds(8, rank=1, world=2) == (4, 8)
     t = torch.ones(3)
     dp.maybe_allreduce(t)                                  # disabled: no-op

@@ -1,16 +1,19 @@
-"""BatchExperience: the struct-of-arrays minibatch `ReplayBuffer.sample` returns (role of velora/buffer/experience.py:6-27).
-
-One [batch, width] float32 tensor per stored quantity, in the order the buffer keeps them; `hiddens` is the actor's recurrent
-state at collection time.  The field list is the single source of truth shared with the buffer (`FIELD_NAMES`)."""
-from dataclasses import make_dataclass
+"""BatchExperience: the struct-of-arrays minibatch `ReplayBuffer.sample` returns (velora/buffer/experience.py:6-27)."""
+from dataclasses import dataclass, fields
 
 import torch
 
-FIELD_NAMES = ("states", "actions", "rewards", "next_states", "dones", "hiddens")
 
-BatchExperience = make_dataclass(
-    "BatchExperience",
-    [(name, torch.Tensor) for name in FIELD_NAMES],
-    namespace={"__doc__": "Six [batch, features] tensors: " + ", ".join(FIELD_NAMES) + "."},
-)
-BatchExperience.__module__ = __name__
+@dataclass
+class BatchExperience:
+    """One [batch, width] float32 tensor per stored quantity; `hiddens` is the actor's recurrent state at collection time."""
+
+    states: torch.Tensor
+    actions: torch.Tensor
+    rewards: torch.Tensor
+    next_states: torch.Tensor
+    dones: torch.Tensor
+    hiddens: torch.Tensor
+
+
+FIELD_NAMES = tuple(f.name for f in fields(BatchExperience))

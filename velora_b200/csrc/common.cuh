@@ -138,6 +138,17 @@ __device__ __forceinline__ float ex2_approx(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// min(x, c) that keeps a NaN in x (fminf returns the non-NaN operand, which would turn tanh(NaN) into 1 and sigmoid(NaN) into 0)
+__device__ __forceinline__ float min_keep_nan(float x, float c) {
+    float y;
+    asm("min.NaN.f32 %0, %1, %2;" : "=f"(y) : "f"(x), "f"(c));
+    return y;
+}
+__device__ __forceinline__ float max_keep_nan(float x, float c) {
+    float y;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(y) : "f"(x), "f"(c));
+    return y;
+}
 __device__ __forceinline__ float rcp_approx(float x) {
     float y;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -147,16 +158,16 @@ __device__ __forceinline__ float rcp_approx(float x) {
 // tanh(x) = 1 - 2 / (e^{2x} + 1).  One ex2 + one rcp; |abs err| ~ 1e-7 (the measure that matters: outputs are
 // compared in relative L2 norm).  tanh.approx (2^-11) is far too coarse for the 1e-5 contract.
 __device__ __forceinline__ float tanh_f(float x) {
-    float e = ex2_approx(fminf(x, 15.0f) * (2.0f * kLog2e));
+    float e = ex2_approx(min_keep_nan(x, 15.0f) * (2.0f * kLog2e));
     return 1.0f - 2.0f * rcp_approx(e + 1.0f);
 }
 __device__ __forceinline__ float sigmoid_f(float x) {
-    float e = ex2_approx(fminf(-x, 80.0f) * kLog2e);
+    float e = ex2_approx(min_keep_nan(-x, 80.0f) * kLog2e);
     return rcp_approx(1.0f + e);
 }
 // Mish(x) = x * tanh(softplus(x)) = x * w / (w + 2), w = e^x (e^x + 2).
 __device__ __forceinline__ float mish_f(float x) {
-    float n = ex2_approx(fminf(x, 20.0f) * kLog2e);
+    float n = ex2_approx(min_keep_nan(x, 20.0f) * kLog2e);
     float w = n * (n + 2.0f);
     return x * (w * rcp_approx(w + 2.0f));
 }
@@ -164,7 +175,7 @@ __device__ __forceinline__ float mish_f(float x) {
 //   dt/dx = (1 - t^2) sigmoid(x) = [4 (w + 1) / (w + 2)^2] [n / (n + 1)] = 4 n (n + 1) / (w + 2)^2     (w + 1 = (n + 1)^2)
 // so mish'(x) = t + 4 x n (n + 1) r^2 with r = 1 / (w + 2): one ex2, one rcp, 10 FP32 ops.
 __device__ __forceinline__ float mish_fwd_grad(float x, float& dmish) {
-    float n = ex2_approx(fminf(x, 20.0f) * kLog2e);
+    float n = ex2_approx(min_keep_nan(x, 20.0f) * kLog2e);
     float w = n * (n + 2.0f);
     float r = rcp_approx(w + 2.0f);
     float t = w * r;
@@ -178,9 +189,9 @@ __device__ __forceinline__ float mish_fwd_grad(float x, float& dmish) {
 // finite: e^18 * e^18 * e^30 < 2^128.
 // tanh(sg), tanh(sh), sigmoid(sf)
 __device__ __forceinline__ void tanh2_sigmoid(float sg, float sh, float sf, float& tg, float& th, float& gate) {
-    float a = ex2_approx(fminf(sg, 9.0f) * (2.0f * kLog2e)) + 1.0f;
-    float b = ex2_approx(fminf(sh, 9.0f) * (2.0f * kLog2e)) + 1.0f;
-    float c = ex2_approx(fminf(-sf, 30.0f) * kLog2e) + 1.0f;
+    float a = ex2_approx(min_keep_nan(sg, 9.0f) * (2.0f * kLog2e)) + 1.0f;
+    float b = ex2_approx(min_keep_nan(sh, 9.0f) * (2.0f * kLog2e)) + 1.0f;
+    float c = ex2_approx(min_keep_nan(-sf, 30.0f) * kLog2e) + 1.0f;
     float ab = a * b;
     float r = rcp_approx(ab * c);
     float rab = c * r;
@@ -190,7 +201,7 @@ __device__ __forceinline__ void tanh2_sigmoid(float sg, float sh, float sf, floa
 }
 // w = n (n + 2), n = e^min(x, 9): tanh(softplus x) = w / (w + 2) equals 1 to fp32 precision beyond x = 9
 __device__ __forceinline__ float mish_w(float x) {
-    float n = ex2_approx(fminf(x, 9.0f) * kLog2e);
+    float n = ex2_approx(min_keep_nan(x, 9.0f) * kLog2e);
     return n * (n + 2.0f);
 }
 __device__ __forceinline__ void mish2(float x0, float x1, float& y0, float& y1) {

@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(256) sac_head_fwd_kernel(const float* __restri
         float lp = 0.f;
         for (int j = 0; j < A; ++j) {
             const float mean = x[b * 2 * A + j];
-            const float ls = fminf(fmaxf(x[b * 2 * A + A + j], lo), hi);
+            const float ls = min_keep_nan(max_keep_nan(x[b * 2 * A + A + j], lo), hi)   /* torch.clamp keeps NaN */;
             const float sd = expf(ls);
             const float e = eps[b * A + j];
             const float xt = fmaf(sd, e, mean);

@@ -61,6 +61,9 @@ def shard_bounds(n: int, rank: Optional[int] = None, world: Optional[int] = None
         world = world_size()
     if rank is None:
         rank = dist.get_rank(_state["group"]) if world > 1 else 0
-    per = (n + world - 1) // world
-    lo = min(rank * per, n)
-    return lo, min(lo + per, n)
+    if n % world != 0:
+        # the noise slicing (functional.standard_normal_like), the shared index vector and reduce='mean' all assume equal shards:
+        # an uneven split would hand the last rank the wrong noise rows and bias the mean of shard means
+        raise ValueError(f"data-parallel batch of {n} rows does not divide evenly over {world} ranks")
+    per = n // world
+    return rank * per, (rank + 1) * per

@@ -132,10 +132,17 @@ class NeuroFlowCTCore:
 
         At batch 64 a train step is ~250 tiny launches, i.e. pure launch/dispatch latency (the reference spends 5.9 ms per
         step on the CPU for the same reason); replaying a graph removes the per-launch host cost.
-        Requires `capturable=True` at construction.  The returned losses are the graph's static output tensors.
+        Requires `capturable=True` at construction and a FULL buffer (the sampling range is a host integer that the capture
+        freezes).  The returned losses are the graph's static output tensors.
         """
         if self.device is None or torch.device(self.device).type != "cuda":
             raise RuntimeError("capture_train_step needs a CUDA device")
+        if self.buffer.size != self.buffer.capacity:
+            # `buffer.sample` draws torch.randint(0, size) and passes n_rows = size to the gather; both are HOST integers that a
+            # capture freezes, so a graph captured on a partly filled buffer would never see transitions added later
+            raise RuntimeError(
+                f"capture_train_step: the replay buffer holds {self.buffer.size} of {self.buffer.capacity} transitions; a captured "
+                "graph freezes the sampling range, so capture only once the buffer is full (or train eagerly until then)")
         cur = torch.cuda.current_stream(self.device)
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(cur)

@@ -200,4 +200,5 @@ class EntropyModuleDiscrete:
     def gradient_step(self, loss: torch.Tensor) -> None:
         self.optim.zero_grad()
         loss.backward()
+        _dp.maybe_allreduce(self.log_alpha.grad)      # data-parallel: entropy_mean is a mean over this rank's shard
         self.optim.step()
