@@ -10,8 +10,10 @@ Weak scaling: every rank owns 65536 batch rows.
 
 One JSON line on stdout (rank 0).  `value` is measured with inputs resident in HBM; `e2e` goes through the same
 public API with pinned HOST inputs, H2D/D2H copies inside the timed region; `roofline` is the dominant (backward)
-kernel against the measured HBM peak; `cpu_baseline` is the oracle's torch-CPU port of the reference timed on this
-box's host cores.  `--impl reference` times that port alone (the reference is Python and cannot travel here).
+kernel against the measured HBM peak; `cpu_baseline` is the UNMODIFIED reference (its package copied to the git-ignored
+baseline/_ref/ by baseline/install_ref.py, which gpurun ships) timed on this box's host cores - or, when that copy is absent, the
+oracle's torch-CPU port of it (kind "port").  `--impl reference` times that alone and, on a GPU box, also launches the
+same reference modules eagerly / jit-scripted on the GPU (`reference_on_this_gpu`: the incumbent a GPU user has today).
 """
 from __future__ import annotations
 
@@ -30,6 +32,12 @@ UNIT = "sample-steps/s"
 SHAPE = dict(I=4, N=20, O=2, Ni=12, Nc=8)
 ALGO_BYTES_FWD = 4 * (SHAPE["I"] + SHAPE["O"] + SHAPE["Nc"])            # read x_t, write y_t, write h_t
 ALGO_BYTES_BWD = 4 * (2 * SHAPE["I"] + SHAPE["O"] + SHAPE["Nc"])        # read x_t, h_{t-1}, dy_t; write dx_t
+
+
+def workload_config(B: int, T: int) -> dict:
+    """Identical on both arms (the driver compares the two `config` objects)."""
+    return {"workload": f"LiquidNCPNetwork(4,20,2) fwd+bwd, batch {B} x seq {T} per GPU, fp32 (BASELINE config 3)",
+            "batch_per_gpu": B, "seq_len": T}
 
 
 def algo_bytes_step(T: int) -> float:
@@ -126,11 +134,51 @@ def cpu_port_step_fn(B: int, T: int, threads: int):
     return step
 
 
-def time_cpu_port(B: int, T: int, steps: int, warmup: int):
+def reference_step_fn(B: int, T: int, threads: int, device=None, script: bool = False):
+    """The UNMODIFIED reference (baseline/_ref, loaded by oracle/ref_import.py): LiquidNCPNetwork(4,20,2) stepped T times the way
+    its callers do (`y, h = net(x_t, h)`, ncp.py:129-178), fwd + bwd of the config-3 loss.  None when no reference tree travelled."""
+    import torch
+
+    from oracle import ref_import
+
+    if not ref_import.reference_available():
+        return None
+    ref = ref_import.import_reference()
+    torch.set_num_threads(threads)
+    ref.set_seed(64)
+    net = ref.LiquidNCPNetwork(SHAPE["I"], SHAPE["N"], SHAPE["O"], device=device)
+    if device is not None:
+        net = net.to(device)
+    params = list(net.parameters())
+    if script:
+        net = torch.jit.script(net)      # what the reference's modules do with their networks (modules.py:388-392)
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(B, T, SHAPE["I"], generator=g).to(device)
+    ry = torch.randn(B, T, SHAPE["O"], generator=g).to(device)
+    rh = torch.randn(B, SHAPE["Nc"], generator=g).to(device)
+
+    def step():
+        for p in params:
+            p.grad = None
+        h, loss = None, None
+        for t in range(T):
+            y, h = net(x[:, t], h)
+            term = (y * ry[:, t]).sum()
+            loss = term if loss is None else loss + term
+        (loss + (h * rh).sum()).backward()
+
+    return step
+
+
+def time_cpu(B: int, T: int, steps: int, warmup: int):
+    """(times, threads, torch threads, kind): the unmodified reference when it is present, else the oracle's port of it."""
     import torch
 
     threads = os.cpu_count() or 1
-    step = cpu_port_step_fn(B, T, threads)
+    step = reference_step_fn(B, T, threads)
+    kind = "reference"
+    if step is None:
+        step, kind = cpu_port_step_fn(B, T, threads), "port"
     for _ in range(warmup):
         step()
     times = []
@@ -138,7 +186,47 @@ def time_cpu_port(B: int, T: int, steps: int, warmup: int):
         t0 = time.perf_counter()
         step()
         times.append(time.perf_counter() - t0)
-    return times, threads, torch.get_num_threads()
+    return times, threads, torch.get_num_threads(), kind
+
+
+def cpu_sample_text(kind: str, B: int, T: int, what: str, used: int) -> str:
+    if kind == "reference":
+        from oracle import ref_import
+
+        src = f"unmodified reference modules from {os.path.relpath(ref_import.REFERENCE_ROOT, ROOT)} (LiquidNCPNetwork stepped T times, eager)"
+    else:
+        src = "oracle torch-CPU port of the reference ops"
+    return f"{src}, batch {B} x seq {T}, {what}, {used} threads"
+
+
+def time_reference_on_gpu(B: int, T: int, iters: int = 3):
+    """The incumbent a GPU user of the reference has today: the same unmodified modules launched eagerly (and jit-scripted) on
+    this GPU.  Reported beside the CPU arm; not the driver's ratio."""
+    import torch
+
+    if not torch.cuda.is_available():
+        return None
+    out = {}
+    for name, script in (("eager", False), ("jit_script", True)):
+        try:
+            step = reference_step_fn(B, T, os.cpu_count() or 1, device=torch.device("cuda", 0), script=script)
+            if step is None:
+                return None
+            for _ in range(3 if script else 1):
+                step()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(iters):
+                step()
+            b.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b) / iters
+            out[name] = {"value": B * T / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms}
+        except Exception as e:      # the incumbent is informational: never fail the arm on it
+            out[name] = {"error": repr(e)[:200]}
+    out["sample"] = f"unmodified reference LiquidNCPNetwork(4,20,2) on cuda:0, batch {B} x seq {T}, fwd+bwd, {iters} steps"
+    return out
 
 
 def run_reference(args) -> None:
@@ -146,11 +234,11 @@ def run_reference(args) -> None:
     if rank != 0:
         return
     B, T = args.batch, args.seq
-    # bounded sample: full batch is ~0.5-1 s per step on 16 cores; shrink it when the requested run would take minutes
+    # bounded sample: full batch is ~0.2-1 s per step on the host cores; shrink it when the requested run would take minutes
     sample_B = B
     if (args.steps + args.warmup) > 60:
         sample_B = max(4096, B // 4)
-    times, threads, used = time_cpu_port(sample_B, T, args.steps, max(args.warmup, 1))
+    times, threads, used, kind = time_cpu(sample_B, T, args.steps, max(args.warmup, 1))
     total = sum(times)
     value = sample_B * T * len(times) / total
     line = {
@@ -158,13 +246,16 @@ def run_reference(args) -> None:
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"LiquidNCPNetwork(4,20,2) fwd+bwd, batch {B} x seq {T}, fp32 (BASELINE config 3)",
-                   "batch_per_gpu": B, "seq_len": T},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"oracle torch-CPU port of the reference ops, batch {sample_B} x seq {T}, {len(times)} steps, {used} threads"},
+        "config": workload_config(B, T),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
+                         "sample": cpu_sample_text(kind, sample_B, T, f"{len(times)} steps", used)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if kind == "reference" and not args.no_gpu_incumbent:
+        inc = time_reference_on_gpu(B, T)
+        if inc is not None:
+            line["reference_on_this_gpu"] = inc
     print(json.dumps(line), flush=True)
 
 
@@ -502,24 +593,24 @@ def run_ours(args) -> None:
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        times, threads, used = time_cpu_port(B, T, 3, 1)
+        times, threads, used, kind = time_cpu(B, T, 3, 1)
         best = min(times)
-        cpu = {"value": B * T / best, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"oracle torch-CPU port of the reference ops, full batch {B} x seq {T}, best of 3 steps, {used} threads"}
+        cpu = {"value": B * T / best, "unit": UNIT, "cores": threads, "kind": kind,
+               "sample": cpu_sample_text(kind, B, T, "full size, best of 3 steps", used)}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"LiquidNCPNetwork(4,20,2) fwd+bwd, batch {B} x seq {T} per GPU, fp32 (BASELINE config 3)",
-                       "batch_per_gpu": B, "global_batch": B * world, "seq_len": T,
-                       "parallelism": f"dp{world}" if world > 1 else "single",
-                       "l2": f"{R} rotating input sets ({R * 4 * (B * T * (SHAPE['I'] + SHAPE['O']) + B * SHAPE['Nc']) // 2**20} MiB) + ~170 MB touched per step > 126 MB L2",
-                       "e2e_inputs": "x from pinned host memory every step; loss weights r_y, r_h fixed on the device (config 3); loss + gradients read back",
-                       "layout": "time-major storage [T,B,F] viewed as [B,T,F]" if tm else "batch-major [B,T,F]",
-                       "launch": f"{R} CUDA graphs (one per input set) replayed round-robin" if graphs is not None else "eager",
-                       "eager_ms_per_step": eager_ms / K, "extra_untimed_graph_replays": extra_warm},
+            "config": workload_config(B, T),
+            "details": {"global_batch": B * world,
+                        "parallelism": f"dp{world}" if world > 1 else "single",
+                        "l2": f"{R} rotating input sets ({R * 4 * (B * T * (SHAPE['I'] + SHAPE['O']) + B * SHAPE['Nc']) // 2**20} MiB) + ~170 MB touched per step > 126 MB L2",
+                        "e2e_inputs": "x from pinned host memory every step; loss weights r_y, r_h fixed on the device (config 3); loss + gradients read back",
+                        "layout": "time-major storage [T,B,F] viewed as [B,T,F]" if tm else "batch-major [B,T,F]",
+                        "launch": f"{R} CUDA graphs (one per input set) replayed round-robin" if graphs is not None else "eager",
+                        "eager_ms_per_step": eager_ms / K, "extra_untimed_graph_replays": extra_warm},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / K},
             "gpu_launches": gpu_launches,
@@ -557,6 +648,7 @@ def main() -> None:
     ap.add_argument("--batch", type=int, default=65536, help="batch rows per GPU")
     ap.add_argument("--seq", type=int, default=32)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-gpu-incumbent", action="store_true", help="reference arm: skip timing the reference modules on the GPU")
     ap.add_argument("--no-graph", action="store_true", help="time the eager Python loop instead of CUDA-graph replays")
     ap.add_argument("--batch-major", action="store_true", help="store the sequence tensors [B,T,F] instead of time-major")
     args = ap.parse_args()

@@ -1,4 +1,5 @@
-"""Import the UNMODIFIED reference hot path from /root/reference (test infrastructure, build container only).
+"""Import the UNMODIFIED reference hot path from /root/reference (build container) or from its copy under baseline/_ref/
+(git-ignored, shipped to the GPU box; written by baseline/install_ref.py).  Test and benchmark infrastructure only.
 
 The reference package cannot be imported normally here: `velora/models/__init__.py:2`,
 `velora/utils/__init__.py:1` and `velora/buffer/__init__.py:3` pull in gymnasium / sqlmodel, which are not
@@ -7,9 +8,9 @@ packages and minimal stubs for `gymnasium`, `sqlmodel`, `sqlalchemy`, so that th
 `velora/wiring.py`, `velora/models/lnn/*.py`, `velora/models/weight.py`, `velora/buffer/*.py`,
 `velora/utils/{core,torch}.py` are the code that runs.
 
-Only `oracle/make_golden.py` and the `-m "not gpu"` tests that are skipped when /root/reference is absent may use
-this.  Nothing in the product (`velora_b200/`), `bench.py` or the `-m gpu` tests imports it: /root/reference does
-not exist on the GPU box.
+Users: `oracle/make_golden.py`, tests that skip when no reference tree is present, `bench.py --impl reference` (the
+reference arm) and tests/test_dropin_gpu.py (the reference's own agent code driving the B200 kernels).  Nothing in the
+product (`velora_b200/`) imports it.  /root/reference does not exist on the GPU box; baseline/_ref/ does.
 """
 from __future__ import annotations
 
@@ -17,7 +18,18 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("VELORA_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_root() -> str:
+    cands = [os.environ.get("VELORA_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")]
+    for c in cands:
+        if c and os.path.isfile(os.path.join(c, "velora", "wiring.py")):
+            return c
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def reference_available() -> bool:

@@ -351,5 +351,5 @@ def test_bench_reference_arm_prints_the_contract_line():
                 "cpu_baseline", "e2e"):
         assert key in d, key
     assert d["value"] > 0 and d["higher_is_better"] is True and d["vs_baseline"] is None
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
