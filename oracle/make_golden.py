@@ -169,6 +169,42 @@ def gen_liquid(ref) -> dict:
     return out
 
 
+def gen_liquid_big(ref) -> dict:
+    """BASELINE config 4's network, LiquidNCPNetwork(8,512,1) (Ni=308, Nc=204), at B=8, T=4: parameters, fp32 outputs / data
+    gradients, and the fp64 deep copy's outputs and all 14 parameter gradients (the arbiter; the reference's own fp32 distance
+    from it is stored per tensor as `e32_*` instead of a second 2 MB gradient set)."""
+    out = {}
+    name, i, n, o, sp, seed, B, T = "big", 8, 512, 1, 0.5, 64, 8, 4
+    ref.set_seed(seed)
+    net = ref.LiquidNCPNetwork(i, n, o, sparsity_level=sp)
+    out[f"{name}_meta"] = np.array([i, n, o, sp, seed, B, T, 1], dtype=np.float64)
+    for k, v in net.state_dict().items():
+        out[f"{name}_sd_{k}"] = t2n(v)
+    nc = net.hidden_size
+    g = torch.Generator().manual_seed(123)
+    x = torch.randn(B, T, i, generator=g)
+    h0 = 0.5 * torch.randn(B, nc, generator=g)
+    ry = torch.randn(B, T, o, generator=g)
+    rh = torch.randn(B, T, nc, generator=g) / 8
+    for k, v in (("x", x), ("h0", h0), ("ry", ry), ("rh", rh)):
+        out[f"{name}_{k}"] = t2n(v)
+    res = {}
+    for dtype, tag in ((torch.float32, "f32"), (torch.float64, "f64")):
+        m = copy.deepcopy(net).to(dtype)
+        xx = x.detach().clone().to(dtype).requires_grad_(True)
+        hh = h0.detach().clone().to(dtype).requires_grad_(True)
+        y, htraj = liquid_seq_ref(m, xx, hh, compose=(dtype == torch.float64))
+        ((y * ry.to(dtype)).sum() + (htraj * rh.to(dtype)).sum()).backward()
+        res[tag] = {"y": y, "htraj": htraj, "dx": xx.grad, "dh0": hh.grad, **{f"grad_{k}": p.grad for k, p in m.named_parameters()}}
+    for k, v in res["f64"].items():
+        out[f"{name}_f64_{k}"] = t2n(v)
+        a, b = res["f32"][k].double(), v.double()
+        out[f"{name}_e32_{k}"] = np.array([float((a - b).norm() / b.norm())])
+    for k in ("y", "htraj", "dx", "dh0"):
+        out[f"{name}_f32_{k}"] = t2n(res["f32"][k])
+    return out
+
+
 # ----------------------------------------------------------------------------------------------- cell
 def gen_cell(ref) -> dict:
     """NCPLiquidCell on the style of hand-written mask the reference tests use (an in x hidden {-1,0,1} matrix)."""
@@ -454,13 +490,16 @@ def main() -> None:
     torch.set_num_threads(1)
     ref = ref_import.import_reference()
     os.makedirs(OUT, exist_ok=True)
-    for name, fn in (("wiring", gen_wiring), ("liquid", gen_liquid), ("cell", gen_cell), ("ncp", gen_ncp), ("buffer", gen_buffer),
-                     ("train", gen_train), ("train_discrete", gen_train_discrete)):
+    only = sys.argv[sys.argv.index("--only") + 1].split(",") if "--only" in sys.argv else None
+    for name, fn in (("wiring", gen_wiring), ("liquid", gen_liquid), ("liquid_big", gen_liquid_big), ("cell", gen_cell), ("ncp", gen_ncp),
+                     ("buffer", gen_buffer), ("train", gen_train), ("train_discrete", gen_train_discrete)):
+        if only is not None and name not in only:
+            continue
         data = fn(ref)
         path = os.path.join(OUT, f"{name}.npz")
         np.savez_compressed(path, **data)
         print(f"{path}: {len(data)} arrays, {os.path.getsize(path) / 1024:.1f} KiB")
-    with open(os.path.join(OUT, "PROVENANCE.txt"), "w") as f:
+    with open(os.path.join(OUT, "PROVENANCE.txt"), "w" if only is None else "a") as f:
         f.write(
             "Generated by oracle/make_golden.py from the unmodified reference at /root/reference (velora v0.2.0)\n"
             f"torch {torch.__version__}, numpy {np.__version__}, CPU.\n"

@@ -271,3 +271,109 @@ def test_bf16_tensor_core_forward_of_the_512_neuron_class(B, T, with_h0):
     assert torch.equal(y2, y) and torch.equal(h2, h_last)
     with pytest.raises(RuntimeError):
         LiquidNCPNetwork(4, 20, 2, device=dev).forward_seq_bf16(torch.zeros(2, 3, 4, device=dev))
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE config 4's network vs the reference
+def _big(golden):
+    import velora_b200 as vb
+    from velora_b200.models.lnn import LiquidNCPNetwork
+
+    d = golden("liquid_big")
+    vb.set_seed(64)
+    net = LiquidNCPNetwork(8, 512, 1, device=torch.device("cuda"))
+    net.load_state_dict({k: torch.tensor(v) for k, v in liquid_case_params(d, "big").items()})
+    return d, net
+
+
+def _close_to_f64(ours, d, key, what, rtol=FP32_RTOL):
+    """The big golden keeps the fp64 arbiter and the reference's own fp32 distance from it (e32_*): within rtol of the arbiter and
+    no further from it than 4x the fp32 reference."""
+    e = rel_err(ours, d[f"big_f64_{key}"])
+    assert e <= max(4.0 * float(d[f"big_e32_{key}"][0]), rtol / 4) and e <= rtol, f"{what}: {e:.3e} (reference fp32: {float(d[f'big_e32_{key}'][0]):.3e})"
+
+
+def test_512_neuron_network_fp32_path_vs_reference(golden):
+    """LiquidNCPNetwork(8,512,1) - the network BASELINE config 4 trains - on the fp32 tile kernels (fp32 atomics for the 526 k-float
+    gradient block) against the reference's golden at that shape: outputs, data gradients and all 14 parameter gradients."""
+    d, net = _big(golden)
+    dev = torch.device("cuda")
+    x = torch.tensor(d["big_x"], device=dev, requires_grad=True)
+    h0 = torch.tensor(d["big_h0"], device=dev, requires_grad=True)
+    y, ht = net.forward_seq(x, h0)
+    assert_close_to_reference(y.detach().cpu().numpy(), d["big_f32_y"], d["big_f64_y"], "y")
+    assert_close_to_reference(ht.detach().cpu().numpy(), d["big_f32_htraj"], d["big_f64_htraj"], "h_traj")
+    ((y * torch.tensor(d["big_ry"], device=dev)).sum() + (ht * torch.tensor(d["big_rh"], device=dev)).sum()).backward()
+    assert_close_to_reference(x.grad.cpu().numpy(), d["big_f32_dx"], d["big_f64_dx"], "dx")
+    assert_close_to_reference(h0.grad.cpu().numpy(), d["big_f32_dh0"], d["big_f64_dh0"], "dh0")
+    for k, p in net.named_parameters():
+        g = p.grad.cpu().numpy()
+        _close_to_f64(g, d, f"grad_{k}", f"grad {k}")
+        if k.endswith("weight"):
+            mask = net.state_dict()[k.replace("weight", "mask")].cpu().numpy()
+            assert np.all(g[mask == 0] == 0.0), k
+
+
+def test_512_neuron_bf16_forward_vs_fp64_reference(golden):
+    """forward_seq_bf16 (tcgen05, bf16 operands) against the fp64 deep copy of the REFERENCE at (8,512,1): BASELINE's 2e-2."""
+    d, net = _big(golden)
+    dev = torch.device("cuda")
+    x, h0 = torch.tensor(d["big_x"], device=dev), torch.tensor(d["big_h0"], device=dev)
+    y, h_last, ht = net.forward_seq_bf16(x, h0, return_traj=True)
+    assert rel_err(y.cpu().numpy(), d["big_f64_y"]) < 2e-2
+    assert rel_err(ht.cpu().numpy(), d["big_f64_htraj"]) < 2e-2
+    assert rel_err(h_last.cpu().numpy(), d["big_f64_htraj"][:, -1]) < 2e-2
+
+
+# ------------------------------------------------------------------------------------------------ the benchmarked configuration itself
+@pytest.mark.parametrize("layout", ["time_major", "batch_major"])
+def test_benchmarked_configuration_vs_fp64_oracle(layout):
+    """bench.py's workload as bench.py runs it - LiquidNCPNetwork(4,20,2), 65536 x 32, h0 = None, loss sum(y r_y) + sum(h_T r_h),
+    sequence tensors time-major - compared with the fp64 oracle on the first 4096 rows: outputs and dx
+    row for row; the parameter gradients of the full batch against a second full-size run whose upstream gradient is zero outside
+    those rows (so the kernels run at the benchmarked size and the oracle only has to cover 4096 rows)."""
+    import velora_b200 as vb
+    from velora_b200.models.lnn import LiquidNCPNetwork
+
+    dev = torch.device("cuda")
+    vb.set_seed(64)
+    net = LiquidNCPNetwork(4, 20, 2, device=dev)
+    B, T, R = 65536, 32, 4096
+    g = torch.Generator(device=dev).manual_seed(1234)
+
+    def seq(F):
+        if layout == "time_major":
+            return torch.randn(T, B, F, device=dev, generator=g).permute(1, 0, 2)
+        return torch.randn(B, T, F, device=dev, generator=g)
+
+    x = seq(4).requires_grad_(True)
+    ry = seq(2)
+    rh = torch.randn(B, 8, device=dev, generator=g)
+    keep = torch.zeros(B, 1, 1, device=dev)
+    keep[:R] = 1.0
+    ry_m = ry * keep                                   # same storage order as ry
+    rh_m = rh * keep[:, 0]
+    y, ht, hl = net.forward_seq(x, None, return_last=True)
+    torch.autograd.backward([y, hl], [ry_m, rh_m])
+    p = {k: v.detach().cpu().numpy() for k, v in net.state_dict().items()}
+    xo = x[:R].detach().cpu().numpy()
+    yo, hto, caches = lo.liquid_seq_forward(p, xo, None, np.float64)
+    dh = np.zeros_like(hto)
+    dh[:, -1] = rh[:R].cpu().numpy()
+    dxo, _, go = lo.liquid_seq_backward(p, caches, ry[:R].cpu().numpy(), dh, np.float64)
+    assert rel_err(y[:R].detach().cpu().numpy(), yo) < FP32_RTOL
+    assert rel_err(ht[:R].detach().cpu().numpy(), hto) < FP32_RTOL
+    assert rel_err(x.grad[:R].cpu().numpy(), dxo) < FP32_RTOL
+    assert torch.count_nonzero(x.grad[R:]) == 0
+    for k, pr in net.named_parameters():
+        assert rel_err(pr.grad.cpu().numpy(), go[k]) < FP32_RTOL, k
+    # the unmasked full-batch run (what the bench times) is the masked run plus the rest: additivity over disjoint row sets
+    g_first = torch.cat([pr.grad.flatten() for pr in net.parameters()]).clone()
+    net.zero_grad()
+    y2, _, hl2 = net.forward_seq(x.detach(), None, return_last=True)
+    torch.autograd.backward([y2, hl2], [ry - ry_m, rh - rh_m])
+    g_rest = torch.cat([pr.grad.flatten() for pr in net.parameters()]).clone()
+    net.zero_grad()
+    y3, _, hl3 = net.forward_seq(x.detach(), None, return_last=True)
+    torch.autograd.backward([y3, hl3], [ry, rh])
+    g_all = torch.cat([pr.grad.flatten() for pr in net.parameters()])
+    assert torch.equal(y3, y) and rel_err(g_all.cpu().numpy(), (g_first + g_rest).cpu().numpy()) < 5e-6

@@ -205,3 +205,23 @@ def test_train_discrete_golden_regenerates(golden):
 def test_bf16_rounding_helper_matches_torch():
     a = (np.random.default_rng(0).standard_normal(4096) * np.array([1e-3, 1.0, 300.0, 1e6]).repeat(1024)).astype(np.float32)
     assert np.array_equal(lo.bf16_round(a), torch.tensor(a).to(torch.bfloat16).float().numpy())
+
+
+def test_bf16_contract_oracle_against_the_fp64_oracle_and_the_reference(golden):
+    """`liquid_seq_forward_bf16` (the arithmetic contract of the tcgen05 bf16 forward: bf16-rounded head operands, exact
+    accumulation) stays within BASELINE's 2e-2 of the fp64 oracle and of the REFERENCE's fp64 deep copy at (8,512,1); the fp64
+    oracle itself reproduces the reference at that shape to 1e-12."""
+    from vb_testutil import liquid_case_params, rel_err
+
+    d = golden("liquid_big")
+    p = liquid_case_params(d, "big")
+    x, h0 = d["big_x"], d["big_h0"]
+    y64, h64, caches = lo.liquid_seq_forward(p, x, h0, np.float64)
+    assert rel_err(y64, d["big_f64_y"]) < 1e-12 and rel_err(h64, d["big_f64_htraj"]) < 1e-12
+    dx, dh0, grads = lo.liquid_seq_backward(p, caches, d["big_ry"], d["big_rh"], np.float64)
+    assert rel_err(dx, d["big_f64_dx"]) < 1e-11 and rel_err(dh0, d["big_f64_dh0"]) < 1e-11
+    for k, g in grads.items():
+        assert rel_err(g, d[f"big_f64_grad_{k}"]) < 1e-11, k
+    yb, hb = lo.liquid_seq_forward_bf16(p, x, h0)
+    assert rel_err(yb, y64) < 2e-2 and rel_err(hb, h64) < 2e-2
+    assert rel_err(yb, d["big_f64_y"]) < 2e-2 and rel_err(hb, d["big_f64_htraj"]) < 2e-2

@@ -12,7 +12,8 @@ from typing import Optional, Sequence
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libvelora_b200.so")
+# VELORA_B200_LIB selects another build of the same ABI (the clock64-instrumented copy used by profiles/microbench/trace_run.py)
+LIB_PATH = os.environ.get("VELORA_B200_LIB") or os.path.join(_HERE, "lib", "libvelora_b200.so")
 
 VB_MASK_I32, VB_MASK_F32 = 0, 1
 VB_FLAG_FORCE_GENERIC = 1

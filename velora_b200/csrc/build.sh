@@ -2,7 +2,7 @@
 # Builds libvelora_b200.so in-tree for sm_100a (cross-compiles without a GPU).  Used by __graft_entry__.build().
 set -e
 cd "$(dirname "$0")"
-OUT=../lib
+OUT=${VB_OUT:-../lib}       # VB_OUT=../lib_trace VB_TRACE_BUILD=1 builds the instrumented copy next to the product library
 mkdir -p "$OUT"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr -Xptxas -v"
@@ -18,5 +18,5 @@ for s in $SRCS; do
   fi
   OBJS="$OBJS $o"
 done
-$NVCC -shared -o "$OUT/libvelora_b200.so" $OBJS -lcudart
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT/libvelora_b200.so" $OBJS -lcudart
 echo "built $OUT/libvelora_b200.so"
