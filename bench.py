@@ -451,10 +451,10 @@ def run_ours(args) -> None:
         saved = []
         for i in range(R):
             y, _, h_last = net.forward_seq(xs[i], None, return_last=True)
-            x_s, _, h_traj, packed = y.grad_fn.saved_tensors
-            saved.append((x_s, h_traj, packed, torch.empty_like(y), torch.empty_like(h_traj), torch.empty_like(x_s)))
+            x_s, _, h_traj, packed, gates = y.grad_fn.saved_tensors
+            saved.append((x_s, h_traj, packed, torch.empty_like(y), torch.empty_like(h_traj), torch.empty_like(x_s), gates))
         dpacked = torch.empty(L.vb_liquid_grad_floats(I, Ni, Nc, O), dtype=torch.float32, device=dev)
-        ws = torch.empty(L.vb_liquid_bwd_workspace_bytes(I, Ni, Nc, O, B, T), dtype=torch.uint8, device=dev)
+        ws = torch.empty(L.vb_liquid_bwd_workspace_bytes(I, Ni, Nc, O, B, T, 1), dtype=torch.uint8, device=dev)
         tm_out = not saved[0][1].is_contiguous()
         lay_f = (VF.X_TM if tm else 0) | ((VF.Y_TM | VF.H_TM) if tm_out else 0)
         lay_b = (VF.X_TM | VF.DX_TM | VF.Y_TM if tm else 0) | (VF.H_TM if tm_out else 0)
@@ -462,13 +462,14 @@ def run_ours(args) -> None:
         out = []
         for which in ("fwd", "bwd"):
             def call(i):
-                x_s, h_traj, packed, y2, h2, dx = saved[i % R]
-                if which == "fwd":
+                x_s, h_traj, packed, y2, h2, dx, gates = saved[i % R]
+                if which == "fwd":          # the training forward: it also writes the saved gate factors
                     _lib.check(L.vb_liquid_fwd(_lib.ptr(packed), _lib.ptr(x_s), None, _lib.ptr(y2), _lib.ptr(h2), B, T, I, Ni, Nc, O,
-                                               None, 0, lay_f, st), "vb_liquid_fwd")
+                                               _lib.ptr(gates), gates.numel(), lay_f, st), "vb_liquid_fwd")
                 else:
                     _lib.check(L.vb_liquid_bwd(_lib.ptr(packed), _lib.ptr(x_s), None, _lib.ptr(h_traj), _lib.ptr(rys[i % R]), None,
-                                               _lib.ptr(rhs[i % R]), _lib.ptr(dx), None, _lib.ptr(dpacked), B, T, I, Ni, Nc, O,
+                                               _lib.ptr(rhs[i % R]), _lib.ptr(gates), gates.numel(), _lib.ptr(dx), None, _lib.ptr(dpacked),
+                                               B, T, I, Ni, Nc, O,
                                                _lib.ptr(ws), ws.numel(), lay_b, st), "vb_liquid_bwd")
             for i in range(3):
                 call(i)

@@ -20,7 +20,9 @@
  *   - return value: 0 = ok; negative = argument error (VB_ERR_*); positive = cudaError_t.
  *     vb_last_error() returns a thread-local description of the last failure on the calling thread.
  *   - re-entrant: may be called concurrently from several host threads (autograd's backward runs on its own
- *     thread) and on several streams.
+ *     thread) and on several streams; the tensor-core and tile kernels keep no process-global device state (weights are
+ *     staged per CTA in shared memory).  Exception: the VB_FLAG_FORCE_FFMA tier keeps its weights in a __constant__ bank and
+ *     serialises its launches on one mutex + event per device.
  *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with a cudaError_t.
  *
  * Packed parameter block ("packed", float32).  The seven SparseLinear layers of a LiquidNCPNetwork stay the
@@ -47,7 +49,8 @@
 extern "C" {
 #endif
 
-#define VB_ABI_VERSION 2      /* 2: layout flags, optimizer / policy-head / packed-gather / bf16-forward entry points added */
+#define VB_ABI_VERSION 3      /* 3: the liquid forward saves gate factors for the backward (vb_liquid_saved_bytes, `saved` arguments);
+                               *    2: layout flags, optimizer / policy-head / packed-gather / bf16-forward entry points added */
 
 /* argument errors */
 #define VB_ERR_NULL_POINTER (-1)
@@ -105,22 +108,28 @@ int vb_liquid_pack(const float* w_in, const float* b_in, const void* m_in, int m
                    const float* w_out, const float* b_out, const void* m_out, int m_out_type,
                    int I, int Ni, int Nc, int O, float* packed, void* stream);
 
-int64_t vb_liquid_fwd_workspace_bytes(int I, int Ni, int Nc, int O, int64_t B, int T);
-int64_t vb_liquid_bwd_workspace_bytes(int I, int Ni, int Nc, int O, int64_t B, int T);
+/* Activations saved for the backward ("save, don't recompute": the path is far from HBM-bound).  On the tensor-core path the forward
+ * writes, per sample and step, the four gate factors of every command neuron and mish(c) - 160 B - into a caller-owned block of
+ * vb_liquid_saved_bytes() bytes (16-byte aligned; 0 = this path saves nothing and `saved` is ignored); the backward reads it back instead
+ * of re-running the five heads.  A backward called with saved = NULL re-runs the forward into its workspace first
+ * (vb_liquid_bwd_workspace_bytes(..., have_saved = 0) includes that room). */
+int64_t vb_liquid_saved_bytes(int I, int Ni, int Nc, int O, int64_t B, int T, int flags);
+int64_t vb_liquid_bwd_workspace_bytes(int I, int Ni, int Nc, int O, int64_t B, int T, int have_saved);
 
 /* T-fold LiquidNCPNetwork.forward (ncp.py:129-178) with the time loop on chip.
  *   x [B,T,I]; h0 [B,Nc] or NULL (= zeros, ncp.py:162-166); y [B,T,O]; h_traj [B,T,Nc] (h_traj[:,t] is the h'
  *   returned by step t).  T = 1 is exactly one reference forward call. */
 int vb_liquid_fwd(const float* packed, const float* x, const float* h0, float* y, float* h_traj,
                   int64_t B, int T, int I, int Ni, int Nc, int O,
-                  void* workspace, int64_t workspace_bytes, int flags, void* stream);
+                  void* saved, int64_t saved_bytes, int flags, void* stream);      /* saved: NULL for inference */
 
-/* Backward of the above (what autograd does over the reference's op graph), gates recomputed from x and h_traj.
+/* Backward of the above (what autograd does over the reference's op graph); gates from `saved` or recomputed from x and h_traj.
  *   dy [B,T,O]; dh_traj [B,T,Nc] or NULL; dh_last [B,Nc] or NULL (extra gradient on h_traj[:,T-1]);
  *   dx [B,T,I] or NULL; dh0 [B,Nc] or NULL; dpacked: F-section layout, overwritten with the parameter gradients
  *   of the PACKED (pre-masked) weights — vb_liquid_unpack_grads() maps them back to the seven layers. */
 int vb_liquid_bwd(const float* packed, const float* x, const float* h0, const float* h_traj,
                   const float* dy, const float* dh_traj, const float* dh_last,
+                  const void* saved, int64_t saved_bytes,
                   float* dx, float* dh0, float* dpacked,
                   int64_t B, int T, int I, int Ni, int Nc, int O,
                   void* workspace, int64_t workspace_bytes, int flags, void* stream);

@@ -377,3 +377,93 @@ def test_benchmarked_configuration_vs_fp64_oracle(layout):
     torch.autograd.backward([y3, hl3], [ry, rh])
     g_all = torch.cat([pr.grad.flatten() for pr in net.parameters()])
     assert torch.equal(y3, y) and rel_err(g_all.cpu().numpy(), (g_first + g_rest).cpu().numpy()) < 5e-6
+
+
+# ------------------------------------------------------------------------------------------------ re-entrancy and the saved block
+def test_two_networks_on_two_streams_and_two_graphs_do_not_interfere(golden):
+    """The tensor-core kernels keep no process-global device state (round 1 staged the inter / motor weights in a __constant__
+    bank): two DIFFERENT networks run concurrently on two streams - eagerly and as two CUDA graphs replayed at the same time -
+    and each reproduces what it computes alone."""
+    import velora_b200 as vb
+    from velora_b200.models.lnn import LiquidNCPNetwork
+
+    dev = torch.device("cuda")
+    nets, xs, want = [], [], []
+    for seed in (64, 65):
+        vb.set_seed(seed)
+        net = LiquidNCPNetwork(4, 20, 2, device=dev)
+        g = torch.Generator(device=dev).manual_seed(seed)
+        x = torch.randn(4096, 16, 4, device=dev, generator=g)
+        nets.append(net)
+        xs.append(x)
+
+    def run(k):
+        net, x = nets[k], xs[k]
+        net.zero_grad()
+        y, ht, hl = net.forward_seq(x, None, return_last=True)
+        (y.sum() + hl.sum()).backward()
+        return y.detach().clone(), torch.cat([p.grad.flatten() for p in net.parameters()]).clone()
+
+    for k in range(2):
+        want.append(run(k))
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+    for rep in range(5):                                   # eager, interleaved launches on two streams
+        got = [None, None]
+        for k in range(2):
+            streams[k].wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(streams[k]):
+                got[k] = run(k)
+        torch.cuda.synchronize()
+        for k in range(2):
+            assert torch.equal(got[k][0], want[k][0]) and torch.equal(got[k][1], want[k][1]), (rep, k)
+    graphs, outs = [], []
+    for k in range(2):                                     # one graph per network, replayed concurrently
+        with torch.cuda.stream(streams[k]):
+            run(k)
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=streams[k]):
+            outs.append(run(k))
+        graphs.append(gr)
+    for rep in range(5):
+        for k in range(2):
+            with torch.cuda.stream(streams[k]):
+                graphs[k].replay()
+        torch.cuda.synchronize()
+        for k in range(2):
+            assert torch.equal(outs[k][0], want[k][0]) and torch.equal(outs[k][1], want[k][1]), ("graph", rep, k)
+
+
+def test_backward_without_a_saved_block_reruns_the_forward(golden):
+    """C ABI: vb_liquid_bwd(saved = NULL) re-runs the forward into its workspace and gives bit-identical gradients to the call
+    that is handed the block the forward wrote."""
+    from velora_b200 import _lib
+
+    d = golden("liquid")
+    net = _build(d, "actor_seq")
+    dev = torch.device("cuda")
+    x = torch.tensor(d["actor_seq_x"], device=dev, requires_grad=True)
+    h0 = torch.tensor(d["actor_seq_h0"], device=dev)
+    y, ht = net.forward_seq(x, h0)
+    x_s, h0_s, h_traj, packed, gates = y.grad_fn.saved_tensors
+    assert gates.numel() > 0
+    L = _lib.lib()
+    B, T = x.shape[0], x.shape[1]
+    dy = torch.tensor(d["actor_seq_ry"], device=dev).permute(1, 0, 2).contiguous().permute(1, 0, 2)
+    lay = 32 | 64        # dy and h_traj time-major (how LiquidSeqFn allocates them); x batch-major
+    outs = []
+    for have in (1, 0):
+        ws = torch.empty(L.vb_liquid_bwd_workspace_bytes(4, 12, 8, 2, B, T, have), dtype=torch.uint8, device=dev)
+        dx = torch.empty_like(x_s)
+        dp = torch.empty(L.vb_liquid_grad_floats(4, 12, 8, 2), device=dev)
+        _lib.check(L.vb_liquid_bwd(_lib.ptr(packed), _lib.ptr(x_s), _lib.ptr(h0_s), _lib.ptr(h_traj), _lib.ptr(dy), None, None,
+                                   _lib.ptr(gates) if have else None, gates.numel() if have else 0, _lib.ptr(dx), None, _lib.ptr(dp),
+                                   B, T, 4, 12, 8, 2, _lib.ptr(ws), ws.numel(), lay, None), "vb_liquid_bwd")
+        torch.cuda.synchronize()
+        outs.append((dx, dp))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    small = torch.empty(1024, dtype=torch.uint8, device=dev)
+    rc = L.vb_liquid_bwd(_lib.ptr(packed), _lib.ptr(x_s), _lib.ptr(h0_s), _lib.ptr(h_traj), _lib.ptr(dy), None, None, None, 0,
+                         None, None, _lib.ptr(outs[0][1]), B, T, 4, 12, 8, 2, _lib.ptr(small), small.numel(), lay, None)
+    assert rc == -3 and b"workspace too small" in L.vb_last_error()

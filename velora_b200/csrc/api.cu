@@ -48,10 +48,11 @@ int64_t bwd_workspace_bytes(int, int, int, int, int64_t);
 }  // namespace small
 namespace tc {
 bool has_tc_path(int I, int Ni, int Nc, int O);
-int fwd(const float*, const float*, const float*, float*, float*, int64_t, int, int, int, int, int, int, cudaStream_t);
-int bwd(const float*, const float*, const float*, const float*, const float*, const float*, const float*, float*, float*, float*,
-        int64_t, int, int, int, int, int, int, void*, int64_t, cudaStream_t);
-int64_t bwd_workspace_bytes(int, int, int, int);
+int fwd(const float*, const float*, const float*, float*, float*, void*, int64_t, int64_t, int, int, int, int, int, int, cudaStream_t);
+int bwd(const float*, const float*, const float*, const float*, const float*, const float*, const float*, const void*, int64_t, float*, float*,
+        float*, int64_t, int, int, int, int, int, int, void*, int64_t, cudaStream_t);
+int64_t saved_bytes(int, int, int, int, int64_t, int);
+int64_t bwd_workspace_bytes(int, int, int, int, int64_t, int, bool);
 }  // namespace tc
 // the tensor-core critic kernels take over once the batch fills a few 128-sample tiles per SM
 static constexpr int64_t kNcpTcMinBatch = 4096;
@@ -107,20 +108,19 @@ extern "C" int vb_liquid_has_fast_path(int I, int Ni, int Nc, int O) {
 
 static inline int64_t max64(int64_t a, int64_t b) { return a > b ? a : b; }
 
-extern "C" int64_t vb_liquid_fwd_workspace_bytes(int I, int Ni, int Nc, int O, int64_t B, int T) {
-    (void)B; (void)T;
-    if (!dims_ok(I, Ni, Nc, O)) return VB_ERR_BAD_DIMS;
-    return 16;
+extern "C" int64_t vb_liquid_saved_bytes(int I, int Ni, int Nc, int O, int64_t B, int T, int flags) {
+    if (!dims_ok(I, Ni, Nc, O) || B < 0 || T < 1) return VB_ERR_BAD_DIMS;
+    if ((flags & (VB_FLAG_FORCE_GENERIC | VB_FLAG_FORCE_FFMA)) || !tc::has_tc_path(I, Ni, Nc, O)) return 0;
+    return tc::saved_bytes(I, Ni, Nc, O, B, T);
 }
 extern "C" int vb_liquid_time_major_ok(int I, int Ni, int Nc, int O, int flags) {
     return !(flags & (VB_FLAG_FORCE_GENERIC | VB_FLAG_FORCE_FFMA)) && tc::has_tc_path(I, Ni, Nc, O);
 }
-extern "C" int64_t vb_liquid_bwd_workspace_bytes(int I, int Ni, int Nc, int O, int64_t B, int T) {
-    (void)T;
-    if (!dims_ok(I, Ni, Nc, O)) return VB_ERR_BAD_DIMS;
+extern "C" int64_t vb_liquid_bwd_workspace_bytes(int I, int Ni, int Nc, int O, int64_t B, int T, int have_saved) {
+    if (!dims_ok(I, Ni, Nc, O) || B < 0 || T < 1) return VB_ERR_BAD_DIMS;
     int64_t g = generic::liquid_bwd_workspace_bytes(I, Ni, Nc, O);
     int64_t s = small::has_fast_path(I, Ni, Nc, O) ? small::bwd_workspace_bytes(I, Ni, Nc, O, B) : 0;
-    int64_t t = tc::has_tc_path(I, Ni, Nc, O) ? tc::bwd_workspace_bytes(I, Ni, Nc, O) : 0;
+    int64_t t = tc::has_tc_path(I, Ni, Nc, O) ? tc::bwd_workspace_bytes(I, Ni, Nc, O, B, T, !have_saved) : 0;
     return max64(max64(g, s), t);
 }
 extern "C" int64_t vb_ncp_bwd_workspace_bytes(int I, int Ni, int Nc, int O, int64_t B) {
@@ -131,13 +131,12 @@ extern "C" int64_t vb_ncp_bwd_workspace_bytes(int I, int Ni, int Nc, int O, int6
 
 extern "C" int vb_liquid_fwd(const float* packed, const float* x, const float* h0, float* y, float* h_traj,
                              int64_t B, int T, int I, int Ni, int Nc, int O,
-                             void* workspace, int64_t workspace_bytes, int flags, void* stream) {
-    (void)workspace; (void)workspace_bytes;
+                             void* saved, int64_t saved_bytes, int flags, void* stream) {
     VB_CHECK_ARG(dims_ok(I, Ni, Nc, O) && B >= 0 && T >= 1, VB_ERR_BAD_DIMS, "vb_liquid_fwd: bad dims B=%lld T=%d (%d,%d,%d,%d)", (long long)B, T, I, Ni, Nc, O);
     if (B == 0) return 0;      // empty batch: nothing to launch (tensors of zero rows have no storage to point at)
     VB_CHECK_ARG(packed && x && y && h_traj, VB_ERR_NULL_POINTER, "vb_liquid_fwd: null pointer");
     if (!(flags & (VB_FLAG_FORCE_GENERIC | VB_FLAG_FORCE_FFMA)) && tc::has_tc_path(I, Ni, Nc, O))
-        return tc::fwd(packed, x, h0, y, h_traj, B, T, I, Ni, Nc, O, flags & VB_FLAG_LAYOUT_MASK, (cudaStream_t)stream);
+        return tc::fwd(packed, x, h0, y, h_traj, saved, saved_bytes, B, T, I, Ni, Nc, O, flags & VB_FLAG_LAYOUT_MASK, (cudaStream_t)stream);
     VB_CHECK_ARG(!(flags & VB_FLAG_LAYOUT_MASK) || T == 1, VB_ERR_LAYOUT,
                  "vb_liquid_fwd: time-major tensors are only supported by the tensor-core kernels (vb_liquid_time_major_ok)");
     if (!(flags & VB_FLAG_FORCE_GENERIC) && small::has_fast_path(I, Ni, Nc, O))
@@ -147,6 +146,7 @@ extern "C" int vb_liquid_fwd(const float* packed, const float* x, const float* h
 
 extern "C" int vb_liquid_bwd(const float* packed, const float* x, const float* h0, const float* h_traj,
                              const float* dy, const float* dh_traj, const float* dh_last,
+                             const void* saved, int64_t saved_bytes,
                              float* dx, float* dh0, float* dpacked,
                              int64_t B, int T, int I, int Ni, int Nc, int O,
                              void* workspace, int64_t workspace_bytes, int flags, void* stream) {
@@ -157,8 +157,8 @@ extern "C" int vb_liquid_bwd(const float* packed, const float* x, const float* h
         return 0;
     }
     if (!(flags & (VB_FLAG_FORCE_GENERIC | VB_FLAG_FORCE_FFMA)) && tc::has_tc_path(I, Ni, Nc, O))
-        return tc::bwd(packed, x, h0, h_traj, dy, dh_traj, dh_last, dx, dh0, dpacked, B, T, I, Ni, Nc, O, flags & VB_FLAG_LAYOUT_MASK,
-                       workspace, workspace_bytes, (cudaStream_t)stream);
+        return tc::bwd(packed, x, h0, h_traj, dy, dh_traj, dh_last, saved, saved_bytes, dx, dh0, dpacked, B, T, I, Ni, Nc, O,
+                       flags & VB_FLAG_LAYOUT_MASK, workspace, workspace_bytes, (cudaStream_t)stream);
     VB_CHECK_ARG(!(flags & VB_FLAG_LAYOUT_MASK) || T == 1, VB_ERR_LAYOUT,
                  "vb_liquid_bwd: time-major tensors are only supported by the tensor-core kernels (vb_liquid_time_major_ok)");
     if (!(flags & VB_FLAG_FORCE_GENERIC) && small::has_fast_path(I, Ni, Nc, O))

@@ -140,10 +140,17 @@ class LiquidSeqFn(torch.autograd.Function):
                 y = torch.empty((B, T, O), dtype=torch.float32, device=dev)
                 h_traj = torch.empty((B, T, Nc), dtype=torch.float32, device=dev)
             lay = (X_TM if x_tm else 0) | ((Y_TM | H_TM) if tm_ok else 0)
+            # the gate factors the backward would otherwise recompute (tensor-core path: 160 B per sample-step); only when a
+            # gradient can be asked for
+            saved = None
+            if any(ctx.needs_input_grad):
+                n_saved = L.vb_liquid_saved_bytes(I, Ni, Nc, O, B, T, flags)
+                if n_saved > 0:
+                    saved = torch.empty(n_saved, dtype=torch.uint8, device=dev)
             with _timed("liquid_fwd", 1):
                 _lib.check(
                     L.vb_liquid_fwd(_lib.ptr(packed), _lib.ptr(x), _lib.ptr(h0c), _lib.ptr(y), _lib.ptr(h_traj),
-                                    B, T, I, Ni, Nc, O, None, 0, flags | lay, st),
+                                    B, T, I, Ni, Nc, O, _lib.ptr(saved), 0 if saved is None else saved.numel(), flags | lay, st),
                     "vb_liquid_fwd",
                 )
         h_last = h_traj[:, T - 1].clone()
@@ -151,20 +158,23 @@ class LiquidSeqFn(torch.autograd.Function):
         ctx.heads_type = heads_type
         ctx.has_h0 = h0 is not None
         ctx.layout = (tm_ok, x_tm)
-        ctx.save_for_backward(x, h0c if h0c is not None else x.new_empty(0), h_traj, packed)
+        ctx.has_saved = saved is not None
+        ctx.save_for_backward(x, h0c if h0c is not None else x.new_empty(0), h_traj, packed,
+                              saved if saved is not None else x.new_empty(0))
         ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable()
         return y, h_traj, h_last
 
     @staticmethod
     def backward(ctx, dy, dh_traj, dh_last):
-        x, h0, h_traj, packed = ctx.saved_tensors
+        x, h0, h_traj, packed, saved = ctx.saved_tensors
         I, Ni, Nc, O = ctx.dims
         masks = ctx.masks
         L = _lib.lib()
         dev = x.device
         B, T, _ = x.shape
         h0p = h0 if ctx.has_h0 else None
+        saved = saved if ctx.has_saved else None
         tm_ok, x_tm = ctx.layout
         dy, dy_tm = _seq(dy, tm_ok) if dy is not None else (torch.zeros((B, T, O), dtype=torch.float32, device=dev), False)
         dh_traj, dh_tm = _seq(dh_traj, tm_ok)
@@ -178,11 +188,12 @@ class LiquidSeqFn(torch.autograd.Function):
             dh0 = torch.empty((B, Nc), dtype=torch.float32, device=dev) if need_h0 else None
             n_grad = L.vb_liquid_grad_floats(I, Ni, Nc, O)
             dpacked = torch.empty(n_grad, dtype=torch.float32, device=dev)
-            ws = _workspace(dev, L.vb_liquid_bwd_workspace_bytes(I, Ni, Nc, O, B, T))
+            ws = _workspace(dev, L.vb_liquid_bwd_workspace_bytes(I, Ni, Nc, O, B, T, 1 if saved is not None or ctx.flags & 3 else 0))
             with _timed("liquid_bwd", 2):
                 _lib.check(
                     L.vb_liquid_bwd(_lib.ptr(packed), _lib.ptr(x), _lib.ptr(h0p), _lib.ptr(h_traj), _lib.ptr(dy),
-                                    _lib.ptr(dh_traj), _lib.ptr(dh_last), _lib.ptr(dx), _lib.ptr(dh0), _lib.ptr(dpacked),
+                                    _lib.ptr(dh_traj), _lib.ptr(dh_last), _lib.ptr(saved), 0 if saved is None else saved.numel(),
+                                    _lib.ptr(dx), _lib.ptr(dh0), _lib.ptr(dpacked),
                                     B, T, I, Ni, Nc, O, _lib.ptr(ws), ws.numel(), ctx.flags | lay, st),
                     "vb_liquid_bwd",
                 )
