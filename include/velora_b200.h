@@ -142,15 +142,26 @@ int vb_liquid_unpack_grads(const float* dpacked, const void* m_in, int m_in_type
                            float* g_w_out, float* g_b_out,
                            int I, int Ni, int Nc, int O, int accumulate, void* stream);
 
-/* Forward of the 512-neuron class (BASELINE config 4: LiquidNCPNetwork(8,512,1)) with the heads on tcgen05 in bf16 (bf16 operands,
- * fp32 accumulation, fp32 hidden state; 2e-2 relative contract) - opt-in, inference only: the fp32 contract of vb_liquid_fwd and the
- * backward of this class stay on the tile kernels.  x [B,T,I], y [B,T,O] (batch- or time-major: VB_FLAG_X/Y_TIME_MAJOR), h0 [B,Nc] or
- * NULL, h_last [B,Nc] or NULL, h_traj [B,T,Nc] or NULL (VB_FLAG_H_TIME_MAJOR).  The workspace must be 128-byte aligned. */
+/* The 512-neuron class (BASELINE config 4: LiquidNCPNetwork(8,512,1)) with the heads on tcgen05 in bf16 (bf16 operands, fp32 accumulation,
+ * fp32 hidden state; 2e-2 relative contract) - opt-in; the fp32 contract of vb_liquid_fwd / vb_liquid_bwd stays on the tile kernels.
+ * Forward: x [B,T,I], y [B,T,O] (batch- or time-major: VB_FLAG_X/Y_TIME_MAJOR), h0 [B,Nc] or NULL, h_last [B,Nc] or NULL, h_traj [B,T,Nc]
+ * or NULL (VB_FLAG_H_TIME_MAJOR).  With a `saved` block (vb_liquid_bf16_saved_bytes() bytes, 128-byte aligned; NULL for inference) the
+ * forward also writes what the backward needs: the gate factors, mish(c) and z~ in bf16, 3096 B per sample-step.
+ * Backward: dy [B,T,O] (VB_FLAG_Y_TIME_MAJOR), dh_last [B,Nc] or NULL (gradient on the last hidden state) -> dx [B,T,I] or NULL
+ * (VB_FLAG_DX_TIME_MAJOR), dh0 [B,Nc] or NULL, dpacked (F layout, overwritten; vb_liquid_unpack_grads maps it to the layers).  The
+ * recurrence runs on a hand-written tcgen05 kernel; three dense GEMMs over all sample-steps (dz_a, dW_in, dW_heads) are cuBLAS calls on
+ * `stream` (the library links libcublas; this entry point cannot be captured in a CUDA graph).  Workspaces must be 128-byte aligned. */
 int vb_liquid_bf16_ok(int I, int Ni, int Nc, int O);
 int64_t vb_liquid_bf16_fwd_workspace_bytes(int I, int Ni, int Nc, int O, int64_t B, int T);
+int64_t vb_liquid_bf16_saved_bytes(int I, int Ni, int Nc, int O, int64_t B, int T);
 int vb_liquid_bf16_fwd(const float* packed, const float* x, const float* h0, float* y, float* h_last, float* h_traj,
+                       void* saved, int64_t saved_bytes,
                        int64_t B, int T, int I, int Ni, int Nc, int O, void* workspace, int64_t workspace_bytes, int flags,
                        void* stream);
+int64_t vb_liquid_bf16_bwd_workspace_bytes(int I, int Ni, int Nc, int O, int64_t B, int T);
+int vb_liquid_bf16_bwd(const float* packed, const float* x, const float* dy, const float* dh_last, const void* saved, int64_t saved_bytes,
+                       float* dx, float* dh0, float* dpacked, int64_t B, int T, int I, int Ni, int Nc, int O,
+                       void* workspace, int64_t workspace_bytes, int flags, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ NCP network (critic) */
 int64_t vb_ncp_packed_floats(int I, int Ni, int Nc, int O);

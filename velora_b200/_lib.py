@@ -39,7 +39,10 @@ SIGNATURES = {
     "vb_liquid_unpack_grads": (_i, [_p, _p, _i, _pp, _i, _p, _i, _p, _p, _pp, _pp, _p, _p, _i, _i, _i, _i, _i, _p]),
     "vb_liquid_bf16_ok": (_i, [_i, _i, _i, _i]),
     "vb_liquid_bf16_fwd_workspace_bytes": (_i64, [_i, _i, _i, _i, _i64, _i]),
-    "vb_liquid_bf16_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _p, _i64, _i, _p]),
+    "vb_liquid_bf16_saved_bytes": (_i64, [_i, _i, _i, _i, _i64, _i]),
+    "vb_liquid_bf16_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i, _i, _i, _i, _i, _p, _i64, _i, _p]),
+    "vb_liquid_bf16_bwd_workspace_bytes": (_i64, [_i, _i, _i, _i, _i64, _i]),
+    "vb_liquid_bf16_bwd": (_i, [_p, _p, _p, _p, _p, _i64, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _p, _i64, _i, _p]),
     "vb_ncp_packed_floats": (_i64, [_i, _i, _i, _i]),
     "vb_ncp_grad_floats": (_i64, [_i, _i, _i, _i]),
     "vb_ncp_pack": (_i, [_pp, _pp, _pp, _i, _i, _i, _i, _i, _p, _p]),

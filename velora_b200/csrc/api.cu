@@ -65,7 +65,11 @@ int64_t bwd_workspace_bytes(int, int, int, int);
 namespace big {
 bool has_path(int I, int Ni, int Nc, int O);
 int64_t fwd_workspace_bytes(int64_t B);
-int fwd(const float*, const float*, const float*, float*, float*, float*, int64_t, int, int, void*, int64_t, cudaStream_t);
+int64_t saved_bytes(int64_t B, int T);
+int fwd(const float*, const float*, const float*, float*, float*, float*, void*, int64_t, int64_t, int, int, void*, int64_t, cudaStream_t);
+int64_t bwd_workspace_bytes(int64_t B, int T);
+int bwd(const float*, const float*, const float*, const float*, const void*, int64_t, float*, float*, float*, int64_t, int, int, void*, int64_t,
+        cudaStream_t);
 }  // namespace big
 namespace generic {
 int liquid_fwd(const float*, const float*, const float*, float*, float*, int64_t, int, int, int, int, int, cudaStream_t);
@@ -198,12 +202,36 @@ extern "C" int64_t vb_liquid_bf16_fwd_workspace_bytes(int I, int Ni, int Nc, int
     return big::fwd_workspace_bytes(B);
 }
 
+extern "C" int64_t vb_liquid_bf16_saved_bytes(int I, int Ni, int Nc, int O, int64_t B, int T) {
+    if (!big::has_path(I, Ni, Nc, O) || B < 0 || T < 1) return VB_ERR_BAD_DIMS;
+    return big::saved_bytes(B, T);
+}
+
+extern "C" int64_t vb_liquid_bf16_bwd_workspace_bytes(int I, int Ni, int Nc, int O, int64_t B, int T) {
+    if (!big::has_path(I, Ni, Nc, O) || B < 0 || T < 1) return VB_ERR_BAD_DIMS;
+    return big::bwd_workspace_bytes(B, T);
+}
+
+extern "C" int vb_liquid_bf16_bwd(const float* packed, const float* x, const float* dy, const float* dh_last, const void* saved,
+                                  int64_t saved_bytes, float* dx, float* dh0, float* dpacked, int64_t B, int T, int I, int Ni, int Nc, int O,
+                                  void* workspace, int64_t workspace_bytes, int flags, void* stream) {
+    VB_CHECK_ARG(B >= 0 && T >= 1, VB_ERR_BAD_DIMS, "vb_liquid_bf16_bwd: bad dims B=%lld T=%d", (long long)B, T);
+    VB_CHECK_ARG(big::has_path(I, Ni, Nc, O), VB_ERR_BAD_DIMS, "vb_liquid_bf16_bwd: no bf16 tensor-core kernel for (%d,%d,%d,%d)", I, Ni, Nc, O);
+    VB_CHECK_ARG(dpacked && (B == 0 || (packed && x && dy && saved)), VB_ERR_NULL_POINTER, "vb_liquid_bf16_bwd: null pointer");
+    if (B == 0) {
+        VB_CUDA(cudaMemsetAsync(dpacked, 0, (size_t)LiquidLayout(I, Ni, Nc, O).f_total * 4, (cudaStream_t)stream));
+        return 0;
+    }
+    return big::bwd(packed, x, dy, dh_last, saved, saved_bytes, dx, dh0, dpacked, B, T, flags, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
 extern "C" int vb_liquid_bf16_fwd(const float* packed, const float* x, const float* h0, float* y, float* h_last, float* h_traj,
+                                  void* saved, int64_t saved_bytes,
                                   int64_t B, int T, int I, int Ni, int Nc, int O, void* workspace, int64_t workspace_bytes, int flags,
                                   void* stream) {
     VB_CHECK_ARG(B >= 0 && T >= 1, VB_ERR_BAD_DIMS, "vb_liquid_bf16_fwd: bad dims B=%lld T=%d", (long long)B, T);
     VB_CHECK_ARG(big::has_path(I, Ni, Nc, O), VB_ERR_BAD_DIMS, "vb_liquid_bf16_fwd: no bf16 tensor-core kernel for (%d,%d,%d,%d)", I, Ni, Nc, O);
     if (B == 0) return 0;
     VB_CHECK_ARG(packed && x && y, VB_ERR_NULL_POINTER, "vb_liquid_bf16_fwd: null pointer");
-    return big::fwd(packed, x, h0, y, h_last, h_traj, B, T, flags, workspace, workspace_bytes, (cudaStream_t)stream);
+    return big::fwd(packed, x, h0, y, h_last, h_traj, saved, saved_bytes, B, T, flags, workspace, workspace_bytes, (cudaStream_t)stream);
 }

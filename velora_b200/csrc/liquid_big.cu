@@ -10,61 +10,11 @@
 // steps through a two-slot scratch buffer in a tile-interleaved order ([tile][Nc/4][128 rows][4]) so that every warp access is
 // 512 contiguous bytes.  Measured (profiles/microbench/big_fwd_proto_r01.log): 0.82 G sample-steps/s = 690 TFLOP/s; the
 // MMA + streaming pipeline alone sustains 1.33 PFLOP/s, what is exposed is the rebuild of z~.
-// The backward of this class is not built: training this shape still runs on the generic fp32 kernels.
-#include <cuda_bf16.h>
-#include <type_traits>
-
-#include "common.cuh"
-#include "tc_common.cuh"
+// With a saved block (training) the kernel also writes the gate factors, mish(c) and z~ for the backward (liquid_big_bwd.cu).
+#include "big_common.cuh"
 
 namespace vb {
 namespace big {
-using namespace tcx;
-template <int V> using IC = std::integral_constant<int, V>;
-
-constexpr int I = 8, NI = 308, NC = 204;
-constexpr int A_CHUNKS = 39;                 // a: 308 features + 4 zeros
-constexpr int H_CHUNK0 = 39;                 // h starts at feature 312
-constexpr int H_CHUNKS = 26;                 // 204 h + the constant-1 feature + 3 zeros
-constexpr int KC = 66;                       // 528 features, 33 K-steps
-constexpr int NPASS = 4, PN = 52, PROWS = 4 * PN;     // 52 neurons = 208 accumulator columns per pass
-constexpr int STAGE_CHUNKS = 6, NSTAGE_PER_PASS = KC / STAGE_CHUNKS;      // 11 stages of K = 48
-constexpr int STAGE_BYTES = STAGE_CHUNKS * PROWS * 16;                    // 19968
-constexpr int RING = 3;
-constexpr int A_STAGES = 6;                  // stages 0..5 (chunks 0..35) contract over the a-part of z~ only
-constexpr int EW = 384;                      // element-wise threads: THREE per sample (warps w, w+4, w+8 share TMEM lanes)
-constexpr int NTHREADS = EW + 64;            // + producer warp + MMA warp
-
-constexpr int S_Z = 0;
-constexpr int S_STAGE = S_Z + KC * PLANE;
-constexpr int S_WIN = S_STAGE + RING * STAGE_BYTES;            // fp32 [I][320]
-constexpr int S_BIN = S_WIN + I * 320 * 4;                     // fp32 [320]
-constexpr int S_WOUT = S_BIN + 320 * 4;                        // fp32 [208]
-constexpr int S_YS = S_WOUT + 208 * 4;                         // fp32 [128]
-constexpr int S_BAR = S_YS + 2 * 128 * 4;
-constexpr int SMEM_BYTES = S_BAR + 128;
-
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-    uint32_t r;
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-    return r;
-}
-// h_traj in the kernel's own tile-interleaved order: [T][tile][NC / 4][128 rows][4 floats]: a warp reads / writes 512 contiguous bytes
-__host__ __device__ __forceinline__ size_t h_index(int t, int64_t n_tiles, int64_t tile, int row, int j) {
-    return ((((size_t)t * n_tiles + tile) * (NC / 4) + j / 4) * TM + row) * 4 + (j & 3);
-}
-__device__ __forceinline__ void ew_sync() { asm volatile("bar.sync 1, 384;" ::: "memory"); }
-
 
 // weight block in plane order: [pass][stage][chunk (6)][row (208)][8 bf16]; row r = 4 jj + hs of neuron j = pass * 52 + jj,
 // hs in (g, h, f, proj); feature k: a at [0,308), zeros, h at [312,516), the bias (constant-1 feature) at 516, zeros to 528
@@ -86,11 +36,13 @@ __global__ void __launch_bounds__(256) big_pack_kernel(const float* __restrict__
     }
 }
 
+// TRAIN: also write the activations the backward needs (big_common.cuh: G, M, Z) into `saved`.
+template <bool TRAIN>
 __global__ void __launch_bounds__(NTHREADS, 1) liquid_big_fwd_kernel(const unsigned char* __restrict__ wpack, const float* __restrict__ packed,
                                                                      const float* __restrict__ x, const float* __restrict__ h0,
                                                                      float* __restrict__ y, float* __restrict__ h_last,
                                                                      float* __restrict__ h_out, float* __restrict__ hbuf,
-                                                                     int64_t B, int T, int flags) {
+                                                                     unsigned char* __restrict__ saved, int64_t B, int T, int flags) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* zP = smem + S_Z;
     float* wins = reinterpret_cast<float*>(smem + S_WIN);
@@ -130,6 +82,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) liquid_big_fwd_kernel(const unsig
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const int64_t n_tiles = (B + TM - 1) / TM;
+    const int64_t R = saved_rows(B, T);
+    uint4* const sG = reinterpret_cast<uint4*>(saved + saved_g_off(R));
+    uint2* const sM = reinterpret_cast<uint2*>(saved + saved_m_off(R));
+    unsigned char* const sZ = saved + saved_z_off(R);
     const int64_t my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
     const int64_t n_steps = my_tiles * T;                   // steps this CTA walks (tiles are processed one after the other)
 
@@ -226,6 +182,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) liquid_big_fwd_kernel(const unsig
                     compute_a(IC<0>{}, IC<13>{}, 0);
 #pragma unroll
                     for (int k = 0; k < 13; ++k) reinterpret_cast<uint4*>(zP)[(13 * part + k) * TM + row] = areg[k];
+                    if (TRAIN) {
+                        uint4* zr = reinterpret_cast<uint4*>(sZ + (size_t)(tile * TM + row) * Z_ROW_BYTES);      // r = (0 * n_tiles + tile) * 128 + row
+#pragma unroll
+                        for (int k = 0; k < 13; ++k) zr[13 * part + k] = areg[k];
+                    }
                     fence_async_smem();
                     mbar_arrive(aready);
                 }
@@ -241,9 +202,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) liquid_big_fwd_kernel(const unsig
                             if (8 * c + 4 < NC) v1 = __ldg(reinterpret_cast<const float4*>(h0 + b * NC + 8 * c + 4));
                         }
                         if (8 * c + 4 == NC) v1.x = 1.0f;        // the constant-1 (bias) feature follows the last h
-                        reinterpret_cast<uint4*>(zP)[(H_CHUNK0 + c) * TM + row] =
-                            make_uint4(pack_bf16(v0.x, v0.y), pack_bf16(v0.z, v0.w), pack_bf16(v1.x, v1.y), pack_bf16(v1.z, v1.w));
+                        const uint4 hz = make_uint4(pack_bf16(v0.x, v0.y), pack_bf16(v0.z, v0.w), pack_bf16(v1.x, v1.y), pack_bf16(v1.z, v1.w));
+                        reinterpret_cast<uint4*>(zP)[(H_CHUNK0 + c) * TM + row] = hz;
+                        if (TRAIN) reinterpret_cast<uint4*>(sZ + (size_t)(((int64_t)t * n_tiles + tile) * TM + row) * Z_ROW_BYTES)[H_CHUNK0 + c] = hz;
                     }
+                    if (TRAIN && part == 0)     // chunk 65 (features 520..527) is the all-zero plane
+                        reinterpret_cast<uint4*>(sZ + (size_t)(((int64_t)t * n_tiles + tile) * TM + row) * Z_ROW_BYTES)[KC - 1] = make_uint4(0, 0, 0, 0);
                 }
                 fence_async_smem();
                 ew_sync();
@@ -262,6 +226,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) liquid_big_fwd_kernel(const unsig
                         for (int k = 0; k < 13; ++k) reinterpret_cast<uint4*>(zP)[(13 * part + k) * TM + row] = areg[k];
                         fence_async_smem();
                         mbar_arrive(aready);
+                        if (TRAIN) {
+                            uint4* zr = reinterpret_cast<uint4*>(sZ + (size_t)(((int64_t)(t + 1) * n_tiles + tile) * TM + row) * Z_ROW_BYTES);
+#pragma unroll
+                            for (int k = 0; k < 13; ++k) zr[13 * part + k] = areg[k];
+                        }
                     }
                     // the four threads of a row take 16 / 12 / 12 / 12 of the pass's 52 neurons, four neurons per iteration
                     const int n0 = part == 0 ? 0 : 20 + 16 * (part - 1), nq = part == 0 ? 5 : 4;
@@ -270,15 +239,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) liquid_big_fwd_kernel(const unsig
                         float s16[16];
                         tmem_ld16(taddr + buf * PROWS + 4 * n0 + 16 * q, s16);
                         float hn[4], cc[4], m[4];
+                        float fa[4], fb[4], fc[4], fd[4];       // TRAIN: the gate factors of big_common.cuh
 #pragma unroll
                         for (int jj = 0; jj < 4; ++jj) {
                             float tg, th, gate;
                             tanh2_sigmoid(s16[4 * jj + 0], s16[4 * jj + 1], s16[4 * jj + 2], tg, th, gate);
-                            hn[jj] = fmaf(gate, th - tg, tg);
+                            const float d = th - tg;
+                            hn[jj] = fmaf(gate, d, tg);
                             cc[jj] = s16[4 * jj + 3] + hn[jj];
+                            if (TRAIN) {
+                                const float omg = 1.0f - gate;
+                                fa[jj] = omg * fmaf(-tg, tg, 1.0f);
+                                fb[jj] = gate * fmaf(-th, th, 1.0f);
+                                fc[jj] = d * gate * omg;
+                            }
                         }
-                        mish4(cc, m);
+                        if (TRAIN) {
+                            mish2_grad(cc[0], cc[1], m[0], m[1], fd[0], fd[1]);
+                            mish2_grad(cc[2], cc[3], m[2], m[3], fd[2], fd[3]);
+                        } else {
+                            mish4(cc, m);
+                        }
                         const int j = pass * PN + n0 + 4 * q;
+                        if (TRAIN && j < NC) {
+                            const size_t slot = ((size_t)((int64_t)t * n_tiles + tile) * NQUAD + j / 4) * TM + row;
+                            sG[2 * slot] = make_uint4(pack_bf16(fa[0], fb[0]), pack_bf16(fc[0], fd[0]), pack_bf16(fa[1], fb[1]), pack_bf16(fc[1], fd[1]));
+                            sG[2 * slot + 1] = make_uint4(pack_bf16(fa[2], fb[2]), pack_bf16(fc[2], fd[2]), pack_bf16(fa[3], fb[3]), pack_bf16(fc[3], fd[3]));
+                            sM[slot] = make_uint2(pack_bf16(m[0], m[1]), pack_bf16(m[2], m[3]));
+                        }
                         if (j < NC) {
                             const float4 w4 = *reinterpret_cast<const float4*>(wouts + j);
                             yacc = fmaf(m[0], w4.x, fmaf(m[1], w4.y, fmaf(m[2], w4.z, fmaf(m[3], w4.w, yacc))));
@@ -320,8 +308,15 @@ int64_t fwd_workspace_bytes(int64_t B) {
     return (int64_t)kWpackBytes + 2 * n_tiles * TM * NC * (int64_t)sizeof(float);
 }
 
-int fwd(const float* packed, const float* x, const float* h0, float* y, float* h_last, float* h_traj, int64_t B, int T, int flags,
-        void* ws, int64_t ws_bytes, cudaStream_t stream) {
+int64_t saved_bytes(int64_t B, int T) { return (int64_t)saved_total_bytes(saved_rows(B, T)); }
+
+int fwd(const float* packed, const float* x, const float* h0, float* y, float* h_last, float* h_traj, void* saved, int64_t saved_bytes_, int64_t B,
+        int T, int flags, void* ws, int64_t ws_bytes, cudaStream_t stream) {
+    if (saved) {
+        VB_CHECK_ARG(saved_bytes_ >= saved_bytes(B, T), VB_ERR_WORKSPACE, "vb_liquid_bf16_fwd: saved block too small (%lld bytes, need %lld)",
+                     (long long)saved_bytes_, (long long)saved_bytes(B, T));
+        VB_CHECK_ARG((reinterpret_cast<uintptr_t>(saved) & 127) == 0, VB_ERR_ALIGNMENT, "vb_liquid_bf16_fwd: the saved block must be 128-byte aligned");
+    }
     VB_CHECK_ARG(ws && ws_bytes >= fwd_workspace_bytes(B), VB_ERR_WORKSPACE, "vb_liquid_bf16_fwd: workspace too small (%lld bytes, need %lld)",
                  (long long)ws_bytes, (long long)fwd_workspace_bytes(B));
     VB_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 127) == 0 && (!h0 || (reinterpret_cast<uintptr_t>(h0) & 15) == 0) &&
@@ -332,13 +327,14 @@ int fwd(const float* packed, const float* x, const float* h0, float* y, float* h
     big_pack_kernel<<<296, 256, 0, stream>>>(packed, wpack);
     VB_LAUNCH_CHECK();
     LaunchCfg cfg;
-    int rc = cached_launch_cfg(liquid_big_fwd_kernel, NTHREADS, SMEM_BYTES, &cfg);
+    auto kern = saved ? liquid_big_fwd_kernel<true> : liquid_big_fwd_kernel<false>;
+    int rc = cached_launch_cfg(kern, NTHREADS, SMEM_BYTES, &cfg);
     if (rc) return rc;
     const int64_t n_tiles = (B + TM - 1) / TM;
     const int sms = device_sms() > 0 ? device_sms() : 148;
     const int grid = (int)(n_tiles < sms ? n_tiles : sms);
-    liquid_big_fwd_kernel<<<grid, NTHREADS, SMEM_BYTES, stream>>>(reinterpret_cast<const unsigned char*>(wpack), packed, x, h0, y, h_last, h_traj, hbuf,
-                                                                  B, T, flags);
+    kern<<<grid, NTHREADS, SMEM_BYTES, stream>>>(reinterpret_cast<const unsigned char*>(wpack), packed, x, h0, y, h_last, h_traj, hbuf,
+                                                 reinterpret_cast<unsigned char*>(saved), B, T, flags);
     VB_LAUNCH_CHECK();
     return 0;
 }

@@ -164,22 +164,6 @@ __device__ __forceinline__ void inter_layer(const float* sw, const float (&x)[C:
         }
 }
 
-// Mish and Mish' of two values sharing one reciprocal (common.cuh: mish_fwd_grad): n = e^x, w = n (n + 2), t = w / (w + 2),
-// mish' = t + 4 x n (n + 1) / (w + 2)^2.  Clamped at 20: (w + 2)^2 stays finite for the pair product.
-__device__ __forceinline__ void mish2_grad(float x0, float x1, float& y0, float& y1, float& g0, float& g1) {
-    float n0 = ex2_approx(min_keep_nan(x0, 20.0f) * kLog2e), n1 = ex2_approx(min_keep_nan(x1, 20.0f) * kLog2e);
-    float w0 = n0 * (n0 + 2.0f), w1 = n1 * (n1 + 2.0f);
-    float d0 = w0 + 2.0f, d1 = w1 + 2.0f;
-    float r = rcp_approx(d0 * d1);
-    float r0 = d1 * r, r1 = d0 * r;
-    float t0 = w0 * r0, t1 = w1 * r1;
-    float p0 = fmaf(n0, n0, n0) * r0, p1 = fmaf(n1, n1, n1) * r1;
-    g0 = fmaf(4.0f * x0, p0 * r0, t0);
-    g1 = fmaf(4.0f * x1, p1 * r1, t1);
-    y0 = x0 * t0;
-    y1 = x1 * t1;
-}
-
 // z~ = [a (NI), h (NC), 1, 0..] -> chunks 0..2 of the three part planes (forward: one thread owns the whole row)
 template <class C>
 __device__ __forceinline__ void store_z(unsigned char* zP, int row, const float (&a)[C::NI], const float (&h)[C::NC]) {

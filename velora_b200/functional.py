@@ -430,9 +430,33 @@ class SacHeadFn(torch.autograd.Function):
         return dx, None, None, None, None, None
 
 
-def liquid_bf16_forward(x: torch.Tensor, h0: Optional[torch.Tensor], dims, masks, params, want_traj: bool = False):
-    """Inference forward of the 512-neuron class on tcgen05 in bf16 (vb_liquid_bf16_fwd): x [B,T,I] -> y [B,T,O], h_T [B,Nc]
-    (+ h_traj [B,T,Nc] when asked for).  No autograd graph: the backward of this class runs on the fp32 tile kernels."""
+def _pack_liquid(L, dims, masks, params, dev, st):
+    """vb_liquid_pack of the seven layers -> (packed block, masks as passed, heads mask type code)."""
+    I, Ni, Nc, O = dims
+    params = [_f32c(p.detach()) for p in params]
+    masks = tuple(_lib.mask_arg(m, dev) for m in masks)
+    heads_type = _lib.common_mask_type(masks[1:6])
+    if heads_type is None:
+        masks = (masks[0], *[m.contiguous() for m in masks[1:6]], masks[6])
+        heads_type = _lib.mask_type(masks[1])
+    packed = torch.empty(L.vb_liquid_packed_floats(I, Ni, Nc, O), dtype=torch.float32, device=dev)
+    _count(1)
+    _lib.check(
+        L.vb_liquid_pack(
+            _lib.ptr(params[0]), _lib.ptr(params[1]), _lib.ptr(masks[0]), _lib.mask_type(masks[0]),
+            _lib.ptr_array([params[2 + 2 * k] for k in range(5)]), _lib.ptr_array([params[3 + 2 * k] for k in range(5)]),
+            _lib.ptr_array(list(masks[1:6])), heads_type,
+            _lib.ptr(params[12]), _lib.ptr(params[13]), _lib.ptr(masks[6]), _lib.mask_type(masks[6]),
+            I, Ni, Nc, O, _lib.ptr(packed), st,
+        ),
+        "vb_liquid_pack",
+    )
+    return packed, masks, heads_type
+
+
+def liquid_bf16_forward(x: torch.Tensor, h0: Optional[torch.Tensor], dims, masks, params, want_traj: bool = False, train: bool = False):
+    """Forward of the 512-neuron class on tcgen05 in bf16 (vb_liquid_bf16_fwd): x [B,T,I] -> y [B,T,O], h_T [B,Nc] (+ h_traj [B,T,Nc] when
+    asked for).  `train`: also returns (x as the kernels read it, x time-major?, packed, masks, heads type, saved block) for the backward."""
     I, Ni, Nc, O = dims
     L = _lib.lib()
     _lib.require_cuda(x, "LiquidNCPNetwork.forward_seq_bf16")
@@ -442,36 +466,89 @@ def liquid_bf16_forward(x: torch.Tensor, h0: Optional[torch.Tensor], dims, masks
     B, T, _ = x.shape
     x, x_tm = _seq(x, T > 1)
     h0c = _f32c(h0)
-    params = [_f32c(p.detach()) for p in params]
-    masks = tuple(_lib.mask_arg(m, dev) for m in masks)
-    heads_type = _lib.common_mask_type(masks[1:6])
-    if heads_type is None:
-        masks = (masks[0], *[m.contiguous() for m in masks[1:6]], masks[6])
-        heads_type = _lib.mask_type(masks[1])
     with torch.cuda.device(dev):
         st = _lib.stream_ptr(dev)
-        packed = torch.empty(L.vb_liquid_packed_floats(I, Ni, Nc, O), dtype=torch.float32, device=dev)
-        _count(1)
-        _lib.check(
-            L.vb_liquid_pack(
-                _lib.ptr(params[0]), _lib.ptr(params[1]), _lib.ptr(masks[0]), _lib.mask_type(masks[0]),
-                _lib.ptr_array([params[2 + 2 * k] for k in range(5)]), _lib.ptr_array([params[3 + 2 * k] for k in range(5)]),
-                _lib.ptr_array(list(masks[1:6])), heads_type,
-                _lib.ptr(params[12]), _lib.ptr(params[13]), _lib.ptr(masks[6]), _lib.mask_type(masks[6]),
-                I, Ni, Nc, O, _lib.ptr(packed), st,
-            ),
-            "vb_liquid_pack",
-        )
+        packed, masks, heads_type = _pack_liquid(L, dims, masks, params, dev, st)
         y = torch.empty((T, B, O), dtype=torch.float32, device=dev).permute(1, 0, 2)
         h_last = torch.empty((B, Nc), dtype=torch.float32, device=dev)
         h_traj = torch.empty((T, B, Nc), dtype=torch.float32, device=dev).permute(1, 0, 2) if want_traj else None
+        saved = torch.empty(L.vb_liquid_bf16_saved_bytes(I, Ni, Nc, O, B, T), dtype=torch.uint8, device=dev) if train and B > 0 else None
         ws = _workspace(dev, L.vb_liquid_bf16_fwd_workspace_bytes(I, Ni, Nc, O, B, T))
         flags = (X_TM if x_tm else 0) | Y_TM | H_TM
         _count(2)
         with _timed("liquid_bf16_fwd", 0):
             _lib.check(
                 L.vb_liquid_bf16_fwd(_lib.ptr(packed), _lib.ptr(x), _lib.ptr(h0c), _lib.ptr(y), _lib.ptr(h_last), _lib.ptr(h_traj),
+                                     _lib.ptr(saved), 0 if saved is None else saved.numel(),
                                      B, T, I, Ni, Nc, O, _lib.ptr(ws), ws.numel(), flags, st),
                 "vb_liquid_bf16_fwd",
             )
+    if train:
+        return y, h_last, (x, x_tm, packed, masks, heads_type, saved)
     return (y, h_last, h_traj) if want_traj else (y, h_last)
+
+
+class LiquidBf16SeqFn(torch.autograd.Function):
+    """y [B,T,O], h_T [B,Nc] = liquid(x [B,T,I], h0 | None) for the 512-neuron class with bf16 tensor-core operands, TRAINABLE:
+    forward vb_liquid_bf16_fwd (saving the gate factors, mish(c) and z~), backward vb_liquid_bf16_bwd.  2e-2 relative contract."""
+
+    @staticmethod
+    def forward(ctx, x, h0, dims, masks, *params):
+        y, h_last, (xk, x_tm, packed, masks, heads_type, saved) = liquid_bf16_forward(x, h0, dims, masks, params, train=True)
+        ctx.dims, ctx.masks, ctx.heads_type, ctx.x_tm = dims, masks, heads_type, x_tm
+        ctx.has_h0 = h0 is not None
+        ctx.has_saved = saved is not None
+        ctx.save_for_backward(xk, packed, saved if saved is not None else xk.new_empty(0))
+        ctx.set_materialize_grads(False)
+        return y, h_last
+
+    @staticmethod
+    def backward(ctx, dy, dh_last):
+        x, packed, saved = ctx.saved_tensors
+        I, Ni, Nc, O = ctx.dims
+        masks = ctx.masks
+        L = _lib.lib()
+        dev = x.device
+        B, T, _ = x.shape
+        dy_tm = False
+        if dy is None:
+            dy = torch.zeros((B, T, O), dtype=torch.float32, device=dev)
+        else:
+            dy, dy_tm = _seq(dy, T > 1)
+        dh_last = _f32c(dh_last)
+        need_x = ctx.needs_input_grad[0]
+        need_h0 = ctx.has_h0 and ctx.needs_input_grad[1]
+        with torch.cuda.device(dev):
+            st = _lib.stream_ptr(dev)
+            dx = torch.empty_like(x) if need_x else None
+            dh0 = torch.empty((B, Nc), dtype=torch.float32, device=dev) if need_h0 else None
+            dpacked = torch.empty(L.vb_liquid_grad_floats(I, Ni, Nc, O), dtype=torch.float32, device=dev)
+            ws = _workspace(dev, L.vb_liquid_bf16_bwd_workspace_bytes(I, Ni, Nc, O, B, T)) if B > 0 else None
+            flags = (X_TM | DX_TM if ctx.x_tm else 0) | (Y_TM if dy_tm else 0)
+            with _timed("liquid_bf16_bwd", 6):
+                _lib.check(
+                    L.vb_liquid_bf16_bwd(_lib.ptr(packed), _lib.ptr(x), _lib.ptr(dy), _lib.ptr(dh_last),
+                                         _lib.ptr(saved) if ctx.has_saved else None, saved.numel() if ctx.has_saved else 0,
+                                         _lib.ptr(dx), _lib.ptr(dh0), _lib.ptr(dpacked), B, T, I, Ni, Nc, O,
+                                         _lib.ptr(ws), 0 if ws is None else ws.numel(), flags, st),
+                    "vb_liquid_bf16_bwd",
+                )
+            _dp.maybe_allreduce(dpacked)       # data-parallel: ONE collective over the flat block (526 k floats for this class)
+            need = ctx.needs_input_grad[4:]
+            shapes = [(Ni, I), (Ni,)] + [(Nc, Ni + Nc), (Nc,)] * 5 + [(O, Nc), (O,)]
+            grads: List[Optional[torch.Tensor]] = [
+                torch.empty(s, dtype=torch.float32, device=dev) if need[k] else None for k, s in enumerate(shapes)
+            ]
+            m_in, m_h, m_out = masks[0], list(masks[1:6]), masks[6]
+            _count(1)
+            _lib.check(
+                L.vb_liquid_unpack_grads(
+                    _lib.ptr(dpacked), _lib.ptr(m_in), _lib.mask_type(m_in), _lib.ptr_array(m_h), ctx.heads_type,
+                    _lib.ptr(m_out), _lib.mask_type(m_out),
+                    _lib.ptr(grads[0]), _lib.ptr(grads[1]),
+                    _lib.ptr_array([grads[2 + 2 * k] for k in range(5)]), _lib.ptr_array([grads[3 + 2 * k] for k in range(5)]),
+                    _lib.ptr(grads[12]), _lib.ptr(grads[13]), I, Ni, Nc, O, 0, st,
+                ),
+                "vb_liquid_unpack_grads",
+            )
+        return (dx, dh0, None, None, *grads)

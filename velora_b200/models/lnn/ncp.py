@@ -121,9 +121,10 @@ class LiquidNCPNetwork(nn.Module):
 
     @torch.jit.ignore
     def forward_seq_bf16(self, x: torch.Tensor, h0: Optional[torch.Tensor] = None, return_traj: bool = False):
-        """Inference-only `forward_seq` with the cell's heads on the tensor cores in bf16 (bf16 operands, fp32 accumulation and
-        hidden state; agrees with `forward_seq` to ~1e-2 relative).  Available for the 512-neuron class (BASELINE config 4);
-        returns (y [B,T,out], h_T [B,Nc]) and the hidden trajectory when `return_traj`."""
+        """`forward_seq` with the cell's heads on the tensor cores in bf16 (bf16 operands, fp32 accumulation and hidden state; agrees
+        with `forward_seq` to ~1e-2 relative, BASELINE's bf16 contract is 2e-2).  Available for the 512-neuron class (BASELINE config 4).
+        Returns (y [B,T,out], h_T [B,Nc]), differentiable w.r.t. x, h0 and the fourteen parameters (backward on tcgen05 as well:
+        vb_liquid_bf16_bwd); with `return_traj` the hidden trajectory is returned too and the call is inference-only."""
         if x.dim() != 3:
             raise ValueError(f"Unsupported dimensionality: '{x.shape}'. Should be 3 dimensional with: '(batch_size, steps, features)'.")
         dev = self._target_device()
@@ -138,6 +139,9 @@ class LiquidNCPNetwork(nn.Module):
             params += [h.weight, h.bias]
         params += [self.motor.weight, self.motor.bias]
         dims = (self.in_features, int(self.inter.out_features), int(cmd.n_hidden), int(self.motor.out_features))
+        needs_grad = torch.is_grad_enabled() and (x.requires_grad or (h0 is not None and h0.requires_grad) or any(p.requires_grad for p in params))
+        if needs_grad and not return_traj:
+            return VF.LiquidBf16SeqFn.apply(x, h0, dims, masks, *params)
         with torch.no_grad():
             return VF.liquid_bf16_forward(x, h0, dims, masks, params, want_traj=return_traj)
 
