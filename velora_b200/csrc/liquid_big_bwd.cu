@@ -55,9 +55,12 @@ constexpr int A_RING = 6;                                  // ds operand stages 
 constexpr int A_STAGE_BYTES = STAGE_CHUNKS * PLANE;        // 48 features x 128 rows x 2 B
 constexpr int R_S_A = 0;
 constexpr int R_S_B = R_S_A + A_RING * A_STAGE_BYTES;
-constexpr int R_S_WOUT = R_S_B + RING * STAGE_BYTES;       // fp32 [208]
+constexpr int G_RING = 4;                                  // saved-factor stages in flight: 4 x 12 KB per SM covers the DRAM round trip
+constexpr int G_STAGE_BYTES = 3 * TM * 32;                 // the three quads of a stage x 128 rows x 16 bf16: contiguous in the saved block
+constexpr int R_S_G = R_S_B + RING * STAGE_BYTES;
+constexpr int R_S_WOUT = R_S_G + G_RING * G_STAGE_BYTES;   // fp32 [208]
 constexpr int R_S_BAR = R_S_WOUT + 208 * 4;
-constexpr int R_SMEM_BYTES = R_S_BAR + 256;
+constexpr int R_SMEM_BYTES = R_S_BAR + 512;
 
 __global__ void __launch_bounds__(NTHREADS, 1) liquid_big_rec_kernel(const unsigned char* __restrict__ whp, const float* __restrict__ packed,
                                                                      const unsigned char* __restrict__ saved, const float* __restrict__ dy,
@@ -72,7 +75,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) liquid_big_rec_kernel(const unsig
     uint64_t* a_empty = a_full + A_RING;                              // [A_RING]  its MMAs completed
     uint64_t* acc_full = a_empty + A_RING;                            // [2]       dh of a step complete
     uint64_t* acc_empty = acc_full + 2;                               // [2]       everybody has read that dh
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    uint64_t* g_full = acc_empty + 2;                                 // [G_RING]  saved-factor stage landed
+    uint64_t* g_empty = g_full + G_RING;                              // [G_RING]  every element-wise thread has read it
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(g_empty + G_RING);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     constexpr LiquidLayout L(I, NI, NC, 1);
@@ -86,6 +91,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) liquid_big_rec_kernel(const unsig
         for (int s = 0; s < RING; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
         for (int s = 0; s < A_RING; ++s) { mbar_init(&a_full[s], EW); mbar_init(&a_empty[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], EW); }
+        for (int s = 0; s < G_RING; ++s) { mbar_init(&g_full[s], 1); mbar_init(&g_empty[s], EW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     fence_async_smem();
@@ -97,18 +103,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) liquid_big_rec_kernel(const unsig
     const int64_t my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
     const int64_t n_steps = my_tiles * T;
     const int64_t R = saved_rows(B, T);
+    const unsigned char* sGb = saved + saved_g_off(R);
 
     if (warp == EW / 32) {
-        // ---------------------------------------------------------------- producer: the same 17 weight stages every step
+        // ---------------------------------------------------------------- producer: per stage one W_h block (the same 17 every step, from
+        // L2) and the tile-step's saved gate factors of the stage's three quads (12 KB, contiguous, from HBM).  With the factors loaded
+        // by the element-wise threads themselves (two LDG.128 each, even two stages ahead) the kernel had ~24 KB in flight per SM and
+        // spent 1 ms of its 2.15 ms waiting for them (profiles/r02); the bulk ring keeps 48 KB in flight and costs no registers.
         if (lane == 0) {
             uint32_t it = 0;
-            for (int64_t st = 0; st < n_steps; ++st)
-                for (int s = 0; s < R_STAGES; ++s, ++it) {
-                    const int slot = it % RING;
-                    const uint32_t use = it / RING;
-                    if (use > 0) mbar_wait(&empty_b[slot], (use - 1) & 1);
-                    mbar_expect_tx(&full_b[slot], STAGE_BYTES);
-                    bulk_g2s(smem + R_S_B + slot * STAGE_BYTES, whp + (size_t)s * STAGE_BYTES, STAGE_BYTES, &full_b[slot]);
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+                for (int t = T - 1; t >= 0; --t) {
+                    const size_t ts = (size_t)((int64_t)t * n_tiles + tile);
+                    for (int s = 0; s < R_STAGES; ++s, ++it) {
+                        {
+                            const int slot = it % G_RING;
+                            const uint32_t use = it / G_RING;
+                            if (use > 0) mbar_wait(&g_empty[slot], (use - 1) & 1);
+                            mbar_expect_tx(&g_full[slot], G_STAGE_BYTES);
+                            bulk_g2s(smem + R_S_G + slot * G_STAGE_BYTES, sGb + (ts * NQUAD + 3 * s) * (size_t)(TM * 32), G_STAGE_BYTES, &g_full[slot]);
+                        }
+                        const int slot = it % RING;
+                        const uint32_t use = it / RING;
+                        if (use > 0) mbar_wait(&empty_b[slot], (use - 1) & 1);
+                        mbar_expect_tx(&full_b[slot], STAGE_BYTES);
+                        bulk_g2s(smem + R_S_B + slot * STAGE_BYTES, whp + (size_t)s * STAGE_BYTES, STAGE_BYTES, &full_b[slot]);
+                    }
                 }
         }
     } else if (warp == EW / 32 + 1) {
@@ -145,7 +165,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) liquid_big_rec_kernel(const unsig
         // ---------------------------------------------------------------- element-wise warps: three threads per sample
         const int row = tid & (TM - 1), part = tid >> 7;          // part 0..2: quad 3 s + part of stage s
         const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-        const uint4* sG = reinterpret_cast<const uint4*>(saved + saved_g_off(R));
         uint32_t ait = 0;
         int64_t st = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -162,11 +181,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) liquid_big_rec_kernel(const unsig
                     tc_fence_after();
                 }
 #pragma unroll 1
-                for (int s = 0; s < R_STAGES; ++s, ++ait) {
+                for (int s = 0; s < R_STAGES; ++s) {
                     const int q = 3 * s + part;
-                    // requests first: the saved factors (HBM) and the carried dh' (TMEM, or dh_last for the sequence's last step)
-                    const size_t slot = (ts * NQUAD + q) * TM + row;
-                    const uint4 g0 = __ldg(sG + 2 * slot), g1 = __ldg(sG + 2 * slot + 1);
+                    uint4 g0, g1;
+                    {
+                        const int gs = ait % G_RING;
+                        mbar_wait(&g_full[gs], (ait / G_RING) & 1);
+                        const uint4* gp = reinterpret_cast<const uint4*>(smem + R_S_G + gs * G_STAGE_BYTES) + (part * TM + row) * 2;
+                        g0 = gp[0];
+                        g1 = gp[1];
+                        mbar_arrive(&g_empty[gs]);
+                    }
                     float dhc[4];
                     if (first) {
                         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -200,6 +225,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) liquid_big_rec_kernel(const unsig
                     mbar_arrive(&a_full[sa]);
                     reinterpret_cast<uint4*>(ds_row)[2 * q] = c0;
                     reinterpret_cast<uint4*>(ds_row)[2 * q + 1] = c1;
+                    ++ait;
                 }
                 tc_fence_before();
                 mbar_arrive(&acc_empty[prev]);
