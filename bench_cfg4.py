@@ -8,7 +8,7 @@ One step = zero the gradients, `forward_seq_bf16` (vb_liquid_bf16_fwd, training 
 sum(y r_y) + sum(h_T r_h) (vb_liquid_bf16_bwd: tcgen05 recurrence + three cuBLAS GEMMs + the small kernels, then - for N > 1 - ONE NCCL
 all-reduce of the 526 k-float gradient block, then vb_liquid_unpack_grads).  Timed with CUDA events, barrier + synchronize on both
 sides, max over ranks.  One JSON line (rank 0): sample-steps/s and the fraction of the measured sustained bf16 tensor peak at SURVEY.md
-8(d)'s algorithmic 3.149 MFLOP per sample-step (forward + dgrad + wgrad, dense).  The working set (6.5 GB of saved activations per step)
+8(d)'s algorithmic 3.149 MFLOP per sample-step (forward + dgrad + wgrad, dense).  The working set (7.8 GB of saved activations per step)
 is far larger than L2.
 """
 from __future__ import annotations
@@ -103,7 +103,7 @@ def main() -> None:
                          "peak_kind": "measured sustained bf16 (MEASURED_PEAKS.json)" if os.path.isfile(peak_path) else "fallback",
                          "algorithmic_flops_per_sample_step": FLOPS_PER_SAMPLE_STEP, "per": "GPU"},
             "fwd_ms": avg("liquid_bf16_fwd"), "bwd_ms": avg("liquid_bf16_bwd"),
-            "saved_activation_bytes_per_step": 3096 * B * T,
+            "saved_activation_bytes_per_step": int(__import__("velora_b200")._lib.lib().vb_liquid_bf16_saved_bytes(8, 308, 204, 1, B, T)),
         }
         print(json.dumps(line), flush=True)
     if world > 1:

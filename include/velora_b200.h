@@ -146,7 +146,7 @@ int vb_liquid_unpack_grads(const float* dpacked, const void* m_in, int m_in_type
  * fp32 hidden state; 2e-2 relative contract) - opt-in; the fp32 contract of vb_liquid_fwd / vb_liquid_bwd stays on the tile kernels.
  * Forward: x [B,T,I], y [B,T,O] (batch- or time-major: VB_FLAG_X/Y_TIME_MAJOR), h0 [B,Nc] or NULL, h_last [B,Nc] or NULL, h_traj [B,T,Nc]
  * or NULL (VB_FLAG_H_TIME_MAJOR).  With a `saved` block (vb_liquid_bf16_saved_bytes() bytes, 128-byte aligned; NULL for inference) the
- * forward also writes what the backward needs: the gate factors, mish(c) and z~ in bf16, 3096 B per sample-step.
+ * forward also writes what the backward needs: the gate factors, mish(c), z~ and mish'(u) in bf16, 3720 B per sample-step.
  * Backward: dy [B,T,O] (VB_FLAG_Y_TIME_MAJOR), dh_last [B,Nc] or NULL (gradient on the last hidden state) -> dx [B,T,I] or NULL
  * (VB_FLAG_DX_TIME_MAJOR), dh0 [B,Nc] or NULL, dpacked (F layout, overwritten; vb_liquid_unpack_grads maps it to the layers).  The
  * recurrence runs on a hand-written tcgen05 kernel; three dense GEMMs over all sample-steps (dz_a, dW_in, dW_heads) are cuBLAS calls on

@@ -61,16 +61,18 @@ __device__ __forceinline__ void ew_sync() { asm volatile("bar.sync 1, 384;" ::: 
 //   G  [t][tile][quad (51)][row][16 bf16]  per command neuron (A, Bc, Cc, mish'(c)): ds = dh' * (A, Bc, Cc), dc = dm * mish'(c)
 //   M  [t][tile][quad (51)][row][4 bf16]   m = mish(c) (for dW_out)
 //   Z  [r][528 bf16] row-major             z~ = [a (308) | 0 (4) | h_{t-1} (204) | 1 | 0 (11)]: the wgrad GEMM's second operand
+//   U  [r][312 bf16] row-major             mish'(W_in x + b_in) (zero padded): du = dz_a * U is then one streaming pass
 constexpr int NQUAD = NC / 4;                         // 51
 constexpr int ZW = KC * 8;                            // 528
 constexpr int DSW = 4 * NC;                           // 816 = ds features per row, feature 4 j + hs
 constexpr int AW = A_CHUNKS * 8;                      // 312 = padded a-part
-constexpr size_t G_ROW_BYTES = (size_t)NQUAD * 32, M_ROW_BYTES = (size_t)NQUAD * 8, Z_ROW_BYTES = (size_t)ZW * 2;
+constexpr size_t G_ROW_BYTES = (size_t)NQUAD * 32, M_ROW_BYTES = (size_t)NQUAD * 8, Z_ROW_BYTES = (size_t)ZW * 2, U_ROW_BYTES = (size_t)AW * 2;
 __host__ __device__ inline int64_t saved_rows(int64_t B, int T) { return (int64_t)T * ((B + TM - 1) / TM) * TM; }
 __host__ __device__ inline size_t saved_g_off(int64_t) { return 0; }
 __host__ __device__ inline size_t saved_m_off(int64_t R) { return (size_t)R * G_ROW_BYTES; }
 __host__ __device__ inline size_t saved_z_off(int64_t R) { return (size_t)R * (G_ROW_BYTES + M_ROW_BYTES); }
-__host__ __device__ inline size_t saved_total_bytes(int64_t R) { return (size_t)R * (G_ROW_BYTES + M_ROW_BYTES + Z_ROW_BYTES); }
+__host__ __device__ inline size_t saved_u_off(int64_t R) { return (size_t)R * (G_ROW_BYTES + M_ROW_BYTES + Z_ROW_BYTES); }
+__host__ __device__ inline size_t saved_total_bytes(int64_t R) { return (size_t)R * (G_ROW_BYTES + M_ROW_BYTES + Z_ROW_BYTES + U_ROW_BYTES); }
 
 }  // namespace big
 }  // namespace vb

@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) liquid_big_fwd_kernel(const unsig
     uint4* const sG = reinterpret_cast<uint4*>(saved + saved_g_off(R));
     uint2* const sM = reinterpret_cast<uint2*>(saved + saved_m_off(R));
     unsigned char* const sZ = saved + saved_z_off(R);
+    unsigned char* const sU = saved + saved_u_off(R);
     const int64_t my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
     const int64_t n_steps = my_tiles * T;                   // steps this CTA walks (tiles are processed one after the other)
 
@@ -161,7 +162,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) liquid_big_fwd_kernel(const unsig
                         u[4] = fmaf(xr[i], w1.x, u[4]); u[5] = fmaf(xr[i], w1.y, u[5]); u[6] = fmaf(xr[i], w1.z, u[6]); u[7] = fmaf(xr[i], w1.w, u[7]);
                     }
                     float a[8];
-                    {
+                    if (TRAIN) {
+                        float g[8];
+#pragma unroll
+                        for (int e = 0; e < 8; e += 2) mish2_grad(u[e], u[e + 1], a[e], a[e + 1], g[e], g[e + 1]);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e)
+                            if (8 * c + e >= NI) g[e] = 0.f;
+                        reinterpret_cast<uint4*>(sU + (size_t)(((int64_t)t * n_tiles + tile) * TM + row) * U_ROW_BYTES)[c] =
+                            make_uint4(pack_bf16(g[0], g[1]), pack_bf16(g[2], g[3]), pack_bf16(g[4], g[5]), pack_bf16(g[6], g[7]));
+                    } else {
                         float u4[4] = {u[0], u[1], u[2], u[3]}, a4[4];
                         mish4(u4, a4);
                         a[0] = a4[0]; a[1] = a4[1]; a[2] = a4[2]; a[3] = a4[3];
