@@ -21,8 +21,19 @@ constexpr int STAGE_CHUNKS = 6, NSTAGE_PER_PASS = KC / STAGE_CHUNKS;      // 11 
 constexpr int STAGE_BYTES = STAGE_CHUNKS * PROWS * 16;                    // 19968
 constexpr int RING = 3;
 constexpr int A_STAGES = 6;                  // stages 0..5 (chunks 0..35) contract over the a-part of z~ only
-constexpr int EW = 384;                      // element-wise threads: THREE per sample (warps w, w+4, w+8 share TMEM lanes)
+// Element-wise threads per sample: warps w, w + 4, w + 8, ... address the same TMEM lanes and split a row's features.  Measured in round 2
+// (profiles/r02/README.md): six threads per sample (24 warps, 72 registers) execute 27 % more instructions (per-thread overheads) at 50 %
+// instead of 45 % issue utilisation - 4.52 ms against 4.41 ms for the training forward - so three it stays.
+#ifndef VB_BIG_EWT
+#define VB_BIG_EWT 3
+#endif
+constexpr int EWT = VB_BIG_EWT;
+constexpr int EW = TM * EWT;
 constexpr int NTHREADS = EW + 64;            // + producer warp + MMA warp
+// contiguous split of `total` items over `parts` owners
+__host__ __device__ constexpr int part_cnt(int total, int parts, int p) { return total / parts + (p < total % parts ? 1 : 0); }
+__host__ __device__ constexpr int part_off(int total, int parts, int p) { return p * (total / parts) + (p < total % parts ? p : total % parts); }
+constexpr int AMAX = (A_CHUNKS + EWT - 1) / EWT;      // a-chunks held in registers per thread
 
 constexpr int S_Z = 0;
 constexpr int S_STAGE = S_Z + KC * PLANE;
@@ -30,7 +41,7 @@ constexpr int S_WIN = S_STAGE + RING * STAGE_BYTES;            // fp32 [I][320]
 constexpr int S_BIN = S_WIN + I * 320 * 4;                     // fp32 [320]
 constexpr int S_WOUT = S_BIN + 320 * 4;                        // fp32 [208]
 constexpr int S_YS = S_WOUT + 208 * 4;                         // fp32 [128]
-constexpr int S_BAR = S_YS + 2 * 128 * 4;
+constexpr int S_BAR = S_YS + (EWT - 1) * 128 * 4;
 constexpr int SMEM_BYTES = S_BAR + 128;
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -52,7 +63,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 __host__ __device__ __forceinline__ size_t h_index(int t, int64_t n_tiles, int64_t tile, int row, int j) {
     return ((((size_t)t * n_tiles + tile) * (NC / 4) + j / 4) * TM + row) * 4 + (j & 3);
 }
-__device__ __forceinline__ void ew_sync() { asm volatile("bar.sync 1, 384;" ::: "memory"); }
+__device__ __forceinline__ void ew_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EW) : "memory"); }
 
 
 

@@ -134,15 +134,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) liquid_big_fwd_kernel(const unsig
             }
         }
     } else {
-        // ---------------------------------------------------------------- element-wise warps: two threads per sample
-        const int row = tid & (TM - 1), part = tid >> 7;          // part 0..3
+        // ---------------------------------------------------------------- element-wise warps: EWT threads per sample
+        const int row = tid & (TM - 1), part = tid >> 7;          // part 0 .. EWT - 1
+        const int a_off = part_off(A_CHUNKS, EWT, part), a_cnt = part_cnt(A_CHUNKS, EWT, part);
         const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         uint32_t acc_use[2] = {0, 0};
         int64_t st = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int64_t b = tile * TM + row;
             const bool valid = b < B;
-            uint4 areg[13];                       // this thread's 13 chunks of a = mish(W_in x + b_in), bf16
+            uint4 areg[AMAX];                     // this thread's chunks of a = mish(W_in x + b_in), bf16
             auto compute_a = [&](auto lo_c, auto hi_c, int t) {
                 constexpr int LO = decltype(lo_c)::value, HI = decltype(hi_c)::value;
                 float xr[I];
@@ -150,7 +151,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) liquid_big_fwd_kernel(const unsig
                 for (int i = 0; i < I; ++i) xr[i] = valid ? __ldg(x + (x_tm ? (int64_t)t * B + b : b * T + t) * I + i) : 0.f;
 #pragma unroll
                 for (int k = LO; k < HI; ++k) {
-                    const int c = 13 * part + k;
+                    if (k >= a_cnt) break;
+                    const int c = a_off + k;
                     float u[8];
                     const float4 b0 = *reinterpret_cast<const float4*>(bins + 8 * c), b1 = *reinterpret_cast<const float4*>(bins + 8 * c + 4);
                     u[0] = b0.x; u[1] = b0.y; u[2] = b0.z; u[3] = b0.w; u[4] = b1.x; u[5] = b1.y; u[6] = b1.z; u[7] = b1.w;
@@ -189,19 +191,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) liquid_big_fwd_kernel(const unsig
                 // ---- z~ = [mish(W_in x + b_in) | 0 | h_{t-1} | 1 | 0] as bf16 planes; the a-part was computed into registers during the
                 //      previous step's MMAs (or right here for the first step of a tile)
                 if (t == 0) {
-                    compute_a(IC<0>{}, IC<13>{}, 0);
+                    compute_a(IC<0>{}, IC<AMAX>{}, 0);
 #pragma unroll
-                    for (int k = 0; k < 13; ++k) reinterpret_cast<uint4*>(zP)[(13 * part + k) * TM + row] = areg[k];
+                    for (int k = 0; k < AMAX; ++k)
+                        if (k < a_cnt) reinterpret_cast<uint4*>(zP)[(a_off + k) * TM + row] = areg[k];
                     if (TRAIN) {
                         uint4* zr = reinterpret_cast<uint4*>(sZ + (size_t)(tile * TM + row) * Z_ROW_BYTES);      // r = (0 * n_tiles + tile) * 128 + row
 #pragma unroll
-                        for (int k = 0; k < 13; ++k) zr[13 * part + k] = areg[k];
+                        for (int k = 0; k < AMAX; ++k)
+                            if (k < a_cnt) zr[a_off + k] = areg[k];
                     }
                     fence_async_smem();
                     mbar_arrive(aready);
                 }
                 {
-                    const int hc0 = 9 * part, hc1 = part == 2 ? H_CHUNKS : hc0 + 9;
+                    const int hc0 = part_off(H_CHUNKS, EWT, part), hc1 = hc0 + part_cnt(H_CHUNKS, EWT, part);
                     for (int c = hc0; c < hc1; ++c) {
                         float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
                         if (t > 0) {
@@ -222,7 +226,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) liquid_big_fwd_kernel(const unsig
                 fence_async_smem();
                 ew_sync();
                 if (tid == 0) mbar_arrive(zready);
-                if (t + 1 < T) compute_a(IC<0>{}, IC<4>{}, t + 1);          // pieces of the next step's inter layer, in the shadow of the MMAs
+                constexpr int AQ = (AMAX + 3) / 4;      // the next step's inter layer in four pieces, in the shadow of the MMAs
+                constexpr int A1 = AQ < AMAX ? AQ : AMAX, A2 = 2 * AQ < AMAX ? 2 * AQ : AMAX, A3 = 3 * AQ < AMAX ? 3 * AQ : AMAX;
+                if (t + 1 < T) compute_a(IC<0>{}, IC<A1>{}, t + 1);
                 // ---- gating epilogue per pass
                 float yacc = 0.f;
                 for (int pass = 0; pass < NPASS; ++pass) {
@@ -233,17 +239,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) liquid_big_fwd_kernel(const unsig
                     if (pass == NPASS - 1 && t + 1 < T) {
                         // every MMA of this step has completed: the a-planes are free, the next step's a-part goes in now
 #pragma unroll
-                        for (int k = 0; k < 13; ++k) reinterpret_cast<uint4*>(zP)[(13 * part + k) * TM + row] = areg[k];
+                        for (int k = 0; k < AMAX; ++k)
+                            if (k < a_cnt) reinterpret_cast<uint4*>(zP)[(a_off + k) * TM + row] = areg[k];
                         fence_async_smem();
                         mbar_arrive(aready);
                         if (TRAIN) {
                             uint4* zr = reinterpret_cast<uint4*>(sZ + (size_t)(((int64_t)(t + 1) * n_tiles + tile) * TM + row) * Z_ROW_BYTES);
 #pragma unroll
-                            for (int k = 0; k < 13; ++k) zr[13 * part + k] = areg[k];
+                            for (int k = 0; k < AMAX; ++k)
+                                if (k < a_cnt) zr[a_off + k] = areg[k];
                         }
                     }
-                    // the four threads of a row take 16 / 12 / 12 / 12 of the pass's 52 neurons, four neurons per iteration
-                    const int n0 = part == 0 ? 0 : 20 + 16 * (part - 1), nq = part == 0 ? 5 : 4;
+                    // the EWT threads of a row split the pass's 13 neuron quads, four neurons per iteration
+                    const int n0 = 4 * part_off(PN / 4, EWT, part), nq = part_cnt(PN / 4, EWT, part);
 #pragma unroll 1
                     for (int q = 0; q < nq; ++q) {
                         float s16[16];
@@ -291,14 +299,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) liquid_big_fwd_kernel(const unsig
                     tc_fence_before();
                     mbar_arrive(&acc_empty[buf]);
                     if (t + 1 < T) {
-                        if (pass == 0) compute_a(IC<4>{}, IC<7>{}, t + 1);
-                        else if (pass == 1) compute_a(IC<7>{}, IC<10>{}, t + 1);
-                        else if (pass == 2) compute_a(IC<10>{}, IC<13>{}, t + 1);
+                        if (pass == 0) compute_a(IC<A1>{}, IC<A2>{}, t + 1);
+                        else if (pass == 1) compute_a(IC<A2>{}, IC<A3>{}, t + 1);
+                        else if (pass == 2) compute_a(IC<A3>{}, IC<AMAX>{}, t + 1);
                     }
                 }
                 if (part > 0) ys[(part - 1) * TM + row] = yacc;
                 ew_sync();
-                if (part == 0 && valid) y[y_tm ? (int64_t)t * B + b : b * T + t] = (yacc + ys[row]) + ys[TM + row] + b_out;
+                if (part == 0 && valid) {
+                    float ysum = yacc;
+#pragma unroll
+                    for (int k = 0; k < EWT - 1; ++k) ysum += ys[k * TM + row];
+                    y[y_tm ? (int64_t)t * B + b : b * T + t] = ysum + b_out;
+                }
                 ew_sync();          // h_t is visible to every thread of the tile before the next step reads it; ys is free again
             }
         }

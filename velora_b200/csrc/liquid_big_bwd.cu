@@ -51,6 +51,8 @@ __global__ void __launch_bounds__(256) big_bwd_pack_kernel(const float* __restri
 }
 
 // ------------------------------------------------------------------------------------------------ 1. the recurrence
+constexpr int R_EW = 3 * TM;                               // element-wise threads: three per sample, one neuron quad per thread and stage
+constexpr int R_NTHREADS = R_EW + 64;                      // + producer warp + MMA warp
 constexpr int A_RING = 6;                                  // ds operand stages in flight (6 x 12 KB)
 constexpr int A_STAGE_BYTES = STAGE_CHUNKS * PLANE;        // 48 features x 128 rows x 2 B
 constexpr int R_S_A = 0;
@@ -62,7 +64,7 @@ constexpr int R_S_WOUT = R_S_G + G_RING * G_STAGE_BYTES;   // fp32 [208]
 constexpr int R_S_BAR = R_S_WOUT + 208 * 4;
 constexpr int R_SMEM_BYTES = R_S_BAR + 512;
 
-__global__ void __launch_bounds__(NTHREADS, 1) liquid_big_rec_kernel(const unsigned char* __restrict__ whp, const float* __restrict__ packed,
+__global__ void __launch_bounds__(R_NTHREADS, 1) liquid_big_rec_kernel(const unsigned char* __restrict__ whp, const float* __restrict__ packed,
                                                                      const unsigned char* __restrict__ saved, const float* __restrict__ dy,
                                                                      const float* __restrict__ dh_last, unsigned char* __restrict__ ds_out,
                                                                      float* __restrict__ dh0, int64_t B, int T, int flags) {
@@ -81,7 +83,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) liquid_big_rec_kernel(const unsig
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     constexpr LiquidLayout L(I, NI, NC, 1);
-    for (int e = tid; e < 208; e += NTHREADS) wouts[e] = e < NC ? __ldg(packed + L.wout + e) : 0.f;
+    for (int e = tid; e < 208; e += R_NTHREADS) wouts[e] = e < NC ? __ldg(packed + L.wout + e) : 0.f;
     const bool y_tm = flags & VB_FLAG_Y_TIME_MAJOR;
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
@@ -89,9 +91,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) liquid_big_rec_kernel(const unsig
     }
     if (tid == 0) {
         for (int s = 0; s < RING; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
-        for (int s = 0; s < A_RING; ++s) { mbar_init(&a_full[s], EW); mbar_init(&a_empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], EW); }
-        for (int s = 0; s < G_RING; ++s) { mbar_init(&g_full[s], 1); mbar_init(&g_empty[s], EW); }
+        for (int s = 0; s < A_RING; ++s) { mbar_init(&a_full[s], R_EW); mbar_init(&a_empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], R_EW); }
+        for (int s = 0; s < G_RING; ++s) { mbar_init(&g_full[s], 1); mbar_init(&g_empty[s], R_EW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     fence_async_smem();
@@ -105,7 +107,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) liquid_big_rec_kernel(const unsig
     const int64_t R = saved_rows(B, T);
     const unsigned char* sGb = saved + saved_g_off(R);
 
-    if (warp == EW / 32) {
+    if (warp == R_EW / 32) {
         // ---------------------------------------------------------------- producer: per stage one W_h block (the same 17 every step, from
         // L2) and the tile-step's saved gate factors of the stage's three quads (12 KB, contiguous, from HBM).  With the factors loaded
         // by the element-wise threads themselves (two LDG.128 each, even two stages ahead) the kernel had ~24 KB in flight per SM and
@@ -131,7 +133,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) liquid_big_rec_kernel(const unsig
                     }
                 }
         }
-    } else if (warp == EW / 32 + 1) {
+    } else if (warp == R_EW / 32 + 1) {
         // ---------------------------------------------------------------- MMA issuer
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc(128, PROWS, 0, 0);
@@ -535,10 +537,10 @@ int bwd(const float* packed, const float* x, const float* dy, const float* dh_la
     // 1. recurrence
     {
         LaunchCfg cfg;
-        int rc = cached_launch_cfg(liquid_big_rec_kernel, NTHREADS, R_SMEM_BYTES, &cfg);
+        int rc = cached_launch_cfg(liquid_big_rec_kernel, R_NTHREADS, R_SMEM_BYTES, &cfg);
         if (rc) return rc;
         const int grid = (int)(n_tiles < sms ? n_tiles : sms);
-        liquid_big_rec_kernel<<<grid, NTHREADS, R_SMEM_BYTES, stream>>>(reinterpret_cast<const unsigned char*>(whp), packed, sv, dy, dh_last,
+        liquid_big_rec_kernel<<<grid, R_NTHREADS, R_SMEM_BYTES, stream>>>(reinterpret_cast<const unsigned char*>(whp), packed, sv, dy, dh_last,
                                                                         reinterpret_cast<unsigned char*>(ds), dh0, B, T, flags);
         VB_LAUNCH_CHECK();
     }
