@@ -107,6 +107,26 @@ class ClockSampler(threading.Thread):
         }
 
 
+def bind_to_gpu_numa_node(index: int):
+    """Pin this rank's host threads to the CPUs NVML reports as local to its GPU, BEFORE the pinned staging buffers are allocated
+    (first touch then places them on that NUMA node).  Round 1's end-to-end leg scaled 4.1x at 8 GPUs: eight ranks pulled 33.5 MB per
+    step through whatever socket their pages happened to be on.  Returns the CPU list (None when NVML gives no answer)."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = [64 * w + b for w, mask in enumerate(words) for b in range(64) if (mask >> b) & 1 and 64 * w + b < n_cpu]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return cpus
+    except Exception:
+        pass
+    return None
+
+
 def cpu_port_step_fn(B: int, T: int, threads: int):
     """The oracle's torch-CPU port of the reference (op for op the reference's ATen sequence), fwd + bwd."""
     import torch
@@ -274,9 +294,10 @@ def run_ours(args) -> None:
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-        vb.dataparallel.configure(True, reduce="sum")
+        vb.dataparallel.configure(True, reduce="sum", oneshot=False if args.nccl_allreduce else None)
     B, T = args.batch, args.seq
     K, W = args.steps, max(args.warmup, 3)
 
@@ -611,7 +632,10 @@ def run_ours(args) -> None:
                         "e2e_inputs": "x from pinned host memory every step; loss weights r_y, r_h fixed on the device (config 3); loss + gradients read back",
                         "layout": "time-major storage [T,B,F] viewed as [B,T,F]" if tm else "batch-major [B,T,F]",
                         "launch": f"{R} CUDA graphs (one per input set) replayed round-robin" if graphs is not None else "eager",
-                        "eager_ms_per_step": eager_ms / K, "extra_untimed_graph_replays": extra_warm},
+                        "eager_ms_per_step": eager_ms / K, "extra_untimed_graph_replays": extra_warm,
+                        "gradient_exchange": ("one-shot NVLink kernel (vb_allreduce_oneshot)" if vb.dataparallel._state["oneshot"] is not None
+                                              else "NCCL all-reduce") if world > 1 else None,
+                        "host_cpus_bound_to_gpu_numa_node": len(numa) if numa else None},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / K},
             "gpu_launches": gpu_launches,
@@ -650,6 +674,7 @@ def main() -> None:
     ap.add_argument("--seq", type=int, default=32)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-gpu-incumbent", action="store_true", help="reference arm: skip timing the reference modules on the GPU")
+    ap.add_argument("--nccl-allreduce", action="store_true", help="exchange the gradient block with NCCL instead of the one-shot NVLink kernel")
     ap.add_argument("--no-graph", action="store_true", help="time the eager Python loop instead of CUDA-graph replays")
     ap.add_argument("--batch-major", action="store_true", help="store the sequence tensors [B,T,F] instead of time-major")
     args = ap.parse_args()

@@ -218,6 +218,17 @@ int vb_sac_head_fwd(const float* x, const float* eps, const float* scale, const 
 int vb_sac_head_bwd(const float* x, const float* eps, const float* scale, float log_std_min, float log_std_max, int64_t B, int A,
                     const float* a_norm, const float* std_in, const float* d_actions, const float* d_log_prob, float* dx, void* stream);
 
+/* ------------------------------------------------------------------------------------------------ data-parallel exchange */
+/* One-shot all-reduce (sum, then * scale) of a small fp32 block over NVLink peer memory: the ONE exchange of the data-parallel path, the
+ * parameter-gradient block of a backward.  peer_buffers: host array of `world` device pointers, entry r = rank r's
+ * symmetric buffer of vb_allreduce_oneshot_buffer_bytes(cap_floats) bytes, zero-initialised once, mapped into this process (the host
+ * framework allocates and exchanges them: torch.distributed._symmetric_memory); counter: a device uint32, zero-initialised, private to
+ * this rank.  Every rank must make the same sequence of calls.  In place on `data`; one single-CTA kernel; graph-capturable (the call
+ * number lives in `counter`).  A rank that waits ~2 s for a peer traps the kernel instead of spinning forever. */
+int64_t vb_allreduce_oneshot_buffer_bytes(int64_t cap_floats);
+int vb_allreduce_oneshot(float* data, int64_t n, void* const* peer_buffers, int rank, int world, int64_t cap_floats, float scale,
+                         void* counter, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -54,11 +54,24 @@ def _worker(rank, world, port, out):
             (q * up[0][lo_:hi_].to(dev)).sum().backward()
         return torch.cat([p.grad.flatten() for p in net.parameters()])
 
-    dp.configure(True, reduce="sum")
+    dp.configure(True, reduce="sum", oneshot=False)                   # NCCL
     lo_, hi_ = dp.shard_bounds(B)
-    calls0 = dp._state["calls"]
+    g_nccl = grads(LiquidNCPNetwork, (4, 20, 2), lo_, hi_, (x, h0), (ry, rh))
+    dp.configure(True, reduce="sum")                                  # this library's one-shot NVLink kernel when peer memory is available
+    res["oneshot_available"] = dp._state["oneshot"] is not None
+    calls0, one0 = dp._state["calls"], dp._state["oneshot_calls"]
     g_dp = grads(LiquidNCPNetwork, (4, 20, 2), lo_, hi_, (x, h0), (ry, rh))
     res["liquid_allreduces"] = dp._state["calls"] - calls0            # ONE collective per backward
+    res["oneshot_used"] = dp._state["oneshot_calls"] - one0
+    res["oneshot_vs_nccl"] = float((g_dp - g_nccl).abs().max())
+    if res["oneshot_available"]:                                      # many calls back to back: the two-slot protocol holds
+        t = torch.full((918,), float(rank + 1), device=dev)
+        acc = torch.zeros(918, device=dev)
+        for k in range(200):
+            u = t * (k + 1)
+            dp.maybe_allreduce(u)
+            acc += u
+        res["oneshot_stress"] = float((acc - 3.0 * sum(range(1, 201))).abs().max())
     xq, rq = torch.randn(B, 5, generator=g), torch.randn(B, 1, generator=g)
     q_dp = grads(NCPNetwork, (5, 128, 1), lo_, hi_, (xq,), (rq,))
     dp.configure(False)
@@ -116,6 +129,9 @@ def test_two_rank_nccl_gradients_equal_single_process(tmp_path):
     mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
     r = torch.load(out)
     assert r["liquid_allreduces"] == 1
+    if r["oneshot_available"]:
+        assert r["oneshot_used"] == 1 and r["oneshot_stress"] == 0.0, r
+    assert r["oneshot_vs_nccl"] < 1e-6 * 50, r
     assert r["liquid_rel"] < 2e-6 and r["critic_rel"] < 2e-6, r       # fp32 summation order differs between 1 and 2 shards
     assert r["replicas_equal"]
     for kind in ("ct", "discrete"):
