@@ -83,9 +83,10 @@ def _worker(rank, world, port, out):
     dist.all_gather(both, g_dp)
     res["replicas_equal"] = bool(torch.equal(both[0], both[1]))
 
-    # ---- whole agents: two train steps data-parallel == single process on the whole batch (same indices, same noise)
-    def agent_params(kind, parallel):
-        dp.configure(parallel, reduce="mean")
+    # ---- whole agents: two train steps data-parallel == single process on the whole batch (same indices, same noise), with NCCL and
+    #      with the one-shot NVLink kernel as the gradient exchange
+    def agent_params(kind, parallel, oneshot):
+        dp.configure(parallel, reduce="mean", oneshot=oneshot)
         if kind == "ct":
             a = NeuroFlowCTCore(4, 1, 20, 128, torch.tensor([3.0]), torch.tensor([0.0]), buffer_size=2048, seed=64, device=dev)
         else:
@@ -110,12 +111,13 @@ def _worker(rank, world, port, out):
         return torch.cat([flat, a.entropy.log_alpha.detach().reshape(1)])
 
     for kind in ("ct", "discrete"):
-        p_dp = agent_params(kind, True)
-        p_one = agent_params(kind, False)
-        res[f"{kind}_max_abs"] = float((p_dp - p_one).abs().max())
-        pair = [torch.empty_like(p_dp) for _ in range(world)]
-        dist.all_gather(pair, p_dp)
-        res[f"{kind}_replicas_equal"] = bool(torch.equal(pair[0], pair[1]))      # includes log_alpha (the discrete module all-reduces it too)
+        p_one = agent_params(kind, False, None)
+        for name, oneshot in (("nccl", False), ("oneshot", None)):
+            p_dp = agent_params(kind, True, oneshot)
+            res[f"{kind}_{name}_max_abs"] = float((p_dp - p_one).abs().max())
+            pair = [torch.empty_like(p_dp) for _ in range(world)]
+            dist.all_gather(pair, p_dp)
+            res[f"{kind}_{name}_replicas_equal"] = bool(torch.equal(pair[0], pair[1]))      # includes log_alpha (discrete: all-reduced too)
     if rank == 0:
         torch.save(res, out)
     dist.barrier()
@@ -135,5 +137,6 @@ def test_two_rank_nccl_gradients_equal_single_process(tmp_path):
     assert r["liquid_rel"] < 2e-6 and r["critic_rel"] < 2e-6, r       # fp32 summation order differs between 1 and 2 shards
     assert r["replicas_equal"]
     for kind in ("ct", "discrete"):
-        assert r[f"{kind}_max_abs"] < 1e-6, r                          # two Adam steps of 3e-4
-        assert r[f"{kind}_replicas_equal"], r
+        for name in ("nccl", "oneshot"):
+            assert r[f"{kind}_{name}_max_abs"] < 1e-6, r               # two Adam steps of 3e-4
+            assert r[f"{kind}_{name}_replicas_equal"], r
