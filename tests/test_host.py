@@ -212,7 +212,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     # pure host-side queries work without a device
     assert lib.vb_liquid_packed_floats(4, 12, 8, 2) == 752 + 48 + 640 + 32
     assert lib.vb_liquid_grad_floats(4, 12, 8, 2) == 752
-    assert lib.vb_liquid_has_fast_path(4, 12, 8, 2) == 2 and lib.vb_liquid_has_fast_path(10, 12, 8, 5) == 1 and lib.vb_liquid_has_fast_path(5, 77, 51, 1) == 0
+    assert lib.vb_liquid_has_fast_path(4, 12, 8, 2) == 2 and lib.vb_liquid_has_fast_path(10, 12, 8, 5) == 2 and lib.vb_liquid_has_fast_path(6, 12, 8, 2) == 0 and lib.vb_liquid_has_fast_path(5, 77, 51, 1) == 0
     assert lib.vb_liquid_packed_floats(0, 1, 1, 1) < 0
     # argument errors are reported, not crashed on
     assert lib.vb_liquid_fwd(None, None, None, None, None, 1, 1, 4, 12, 8, 2, None, 0, 0, None) == -1

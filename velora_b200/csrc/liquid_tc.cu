@@ -410,7 +410,7 @@ struct BwdSmem {
 };
 
 template <class C, bool VEC, int LAY>
-__global__ void __launch_bounds__(BT, 4) liquid_bwd_tc_kernel(
+__global__ void __launch_bounds__(BT, (BwdSmem<C>::BYTES + 1024 > 58368 ? 3 : 4)) liquid_bwd_tc_kernel(
     const float* __restrict__ packed, const float* __restrict__ x, const float* __restrict__ h0, const float* __restrict__ h_traj,
     const float* __restrict__ dy, const float* __restrict__ dh_traj, const float* __restrict__ dh_last, const float4* __restrict__ saved,
     float* __restrict__ dx, float* __restrict__ dh0, float* __restrict__ partials, float* __restrict__ d3buf,
@@ -546,7 +546,8 @@ __global__ void __launch_bounds__(BT, 4) liquid_bwd_tc_kernel(
                 float u[C::NI];
                 inter_layer<C>(sw, xr, u);
                 // Mish'(u) and x_t wait in this thread's TMEM lane (16 spare columns) for the dz MMA; a goes to the z~ planes
-                static_assert(C::NI == 12 && C::I <= 4, "parking area: 8 + 8 TMEM columns = Mish'(u[0..8)) | Mish'(u[8..12)), x");
+                // (x_t rides along when it fits the four spare columns; wider inputs are re-read from global memory after the MMA)
+                static_assert(C::NI == 12, "parking area: 8 + 8 TMEM columns = Mish'(u[0..8)) | Mish'(u[8..12)), x (I <= 4)");
                 {
                     float a8[8], g8[8];
 #pragma unroll
@@ -665,8 +666,14 @@ __global__ void __launch_bounds__(BT, 4) liquid_bwd_tc_kernel(
                     for (int j = 0; j < 8; ++j) du[j] = dz8[j] * dmu[j];
 #pragma unroll
                     for (int j = 8; j < C::NI; ++j) du[j] = dz4[j - 8] * dmu[j];
+                    if constexpr (C::I <= 4) {
 #pragma unroll
-                    for (int i = 0; i < C::I; ++i) xr2[i] = dmu[C::NI + i];
+                        for (int i = 0; i < C::I; ++i) xr2[i] = dmu[C::NI + i];
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < C::I; ++i) xr2[i] = 0.f;
+                        if (valid) ldg_row<C::I>(xr2, x + rx(b, t) * C::I, vx);
+                    }
                 }
                 tc_fence_before();
                 if (dx) {
@@ -914,7 +921,9 @@ static int launch_bwd(const float* packed, const float* x, const float* h0, cons
     return 0;
 }
 
-#define VB_TC_SHAPES(X) X(4, 12, 8, 2) X(3, 12, 8, 2)
+// (4,20,2) / (3,20,2): the SAC actors of BASELINE configs 1-3; (10,20,5): the reference's own fixture (tests/models/test_lnn.py:280-309);
+// (8,20,2): an 8-observation actor.  The wide shapes run three CTAs per SM (their dW_in transposition buffer is larger).
+#define VB_TC_SHAPES(X) X(4, 12, 8, 2) X(3, 12, 8, 2) X(10, 12, 8, 5) X(8, 12, 8, 2)
 
 bool has_tc_path(int I, int Ni, int Nc, int O) {
 #define X(a, b, c, d) if (I == a && Ni == b && Nc == c && O == d) return true;
