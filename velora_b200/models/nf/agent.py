@@ -76,6 +76,24 @@ class NeuroFlowCTCore:
         self.critic.update_targets()
         return {"critic": critic_loss.detach(), "actor": actor_loss.detach(), "entropy": entropy_loss.detach()}
 
+    def state_dict(self):
+        """{"modules": ..., "optimizers": ...} (velora/models/base.py:296-312)."""
+        from velora_b200.utils.restore import _agent_state
+
+        return _agent_state(self)
+
+    def save(self, dirpath, *, buffer: bool = False, force: bool = False) -> None:
+        """Writes model / optimizer (/ buffer) state in the reference's checkpoint format (velora/utils/restore.py:107-196)."""
+        from velora_b200.utils.restore import save_model
+
+        save_model(self, dirpath, buffer=buffer, force=force)
+
+    def load_state(self, dirpath, *, buffer: bool = False):
+        """Restores a checkpoint written by `save` or by the reference's `save_model` into this agent."""
+        from velora_b200.utils.restore import load_state
+
+        return load_state(self, dirpath, buffer=buffer)
+
     def predict(self, state: torch.Tensor, hidden: torch.Tensor | None = None, *, train_mode: bool = False):
         """Action for the given state (agent.py:356-388): deterministic `tanh(mean)` when `train_mode` is False, a sampled
         action otherwise; returns (action, new hidden)."""

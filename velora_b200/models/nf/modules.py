@@ -38,6 +38,14 @@ class ActorModule:
     def forward(self, obs: torch.Tensor, hidden: torch.Tensor | None = None):
         return self.network(obs, hidden)
 
+    def state_dict(self):
+        """modules.py:165-169"""
+        return {"actor": self.network.state_dict(), "actor_optim": self.optim.state_dict()}
+
+    def load_state_dict(self, state_dict) -> None:
+        self.network.load_state_dict(state_dict["actor"])
+        self.optim.load_state_dict(state_dict["actor_optim"])
+
     def eval_mode(self) -> None:
         """modules.py:157-159"""
         self.network.eval()
@@ -85,6 +93,19 @@ class CriticModule:
         c2_loss.backward()
         self.optim2.step()
 
+    def state_dict(self):
+        """modules.py:452-460"""
+        return {"critic": self.network1.state_dict(), "critic2": self.network2.state_dict(), "critic_target": self.target1.state_dict(),
+                "critic2_target": self.target2.state_dict(), "critic_optim": self.optim1.state_dict(), "critic2_optim": self.optim2.state_dict()}
+
+    def load_state_dict(self, state_dict) -> None:
+        self.network1.load_state_dict(state_dict["critic"])
+        self.network2.load_state_dict(state_dict["critic2"])
+        self.target1.load_state_dict(state_dict["critic_target"])
+        self.target2.load_state_dict(state_dict["critic2_target"])
+        self.optim1.load_state_dict(state_dict["critic_optim"])
+        self.optim2.load_state_dict(state_dict["critic2_optim"])
+
     def predict(self, obs: torch.Tensor, actions: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         return self.network1(obs, actions), self.network2(obs, actions)
 
@@ -108,6 +129,13 @@ class EntropyModule:
     def compute_loss(self, log_probs: torch.Tensor) -> torch.Tensor:
         entropy = (log_probs + self.target).detach()
         return -(self.log_alpha * entropy).mean()
+
+    def state_dict(self):
+        """modules.py:732-739: the reference stores the entropy optimizer only (log_alpha itself is not in the checkpoint)."""
+        return {"entropy_optim": self.optim.state_dict()}
+
+    def load_state_dict(self, state_dict) -> None:
+        self.optim.load_state_dict(state_dict["entropy_optim"])
 
     def gradient_step(self, loss: torch.Tensor) -> None:
         self.optim.zero_grad()
@@ -140,6 +168,14 @@ class ActorModuleDiscrete:
     def forward(self, obs: torch.Tensor, hidden: torch.Tensor | None = None):
         return self.network(obs, hidden)
 
+    def state_dict(self):
+        """modules.py:165-169"""
+        return {"actor": self.network.state_dict(), "actor_optim": self.optim.state_dict()}
+
+    def load_state_dict(self, state_dict) -> None:
+        self.network.load_state_dict(state_dict["actor"])
+        self.optim.load_state_dict(state_dict["actor_optim"])
+
     def eval_mode(self) -> None:
         self.network.eval()
 
@@ -171,6 +207,8 @@ class CriticModuleDiscrete:
 
     update_targets = CriticModule.update_targets
     gradient_step = CriticModule.gradient_step
+    state_dict = CriticModule.state_dict
+    load_state_dict = CriticModule.load_state_dict
 
     def predict(self, obs: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         return self.network1(obs), self.network2(obs)
@@ -196,6 +234,13 @@ class EntropyModuleDiscrete:
         with torch.no_grad():
             entropy_mean = -torch.sum(probs * log_probs, dim=1).mean()
         return self.log_alpha * (entropy_mean - self.target)
+
+    def state_dict(self):
+        """modules.py:732-739: the reference stores the entropy optimizer only (log_alpha itself is not in the checkpoint)."""
+        return {"entropy_optim": self.optim.state_dict()}
+
+    def load_state_dict(self, state_dict) -> None:
+        self.optim.load_state_dict(state_dict["entropy_optim"])
 
     def gradient_step(self, loss: torch.Tensor) -> None:
         self.optim.zero_grad()

@@ -1,4 +1,4 @@
-from velora_b200.models.sac.continuous import SACActor, SACCriticNCP
-from velora_b200.models.sac.discrete import SACActorDiscrete, SACCriticNCPDiscrete
+from velora_b200.models.sac.continuous import SACActor, SACCritic, SACCriticNCP
+from velora_b200.models.sac.discrete import SACActorDiscrete, SACCriticDiscrete, SACCriticNCPDiscrete
 
-__all__ = ["SACActor", "SACCriticNCP", "SACActorDiscrete", "SACCriticNCPDiscrete"]
+__all__ = ["SACActor", "SACCritic", "SACCriticNCP", "SACActorDiscrete", "SACCriticDiscrete", "SACCriticNCPDiscrete"]

@@ -87,3 +87,17 @@ class SACCriticNCP(nn.Module):
 
     def forward(self, obs: torch.Tensor, actions: torch.Tensor) -> torch.Tensor:
         return self.ncp(torch.cat([obs, actions], dim=-1))
+
+
+class SACCritic(nn.Module):
+    """Liquid NCP critic: Q(obs, action) through the fused LiquidNCPNetwork with one output (continuous.py:146-191).  Not used by the
+    NeuroFlow agents (they take the NCP critics); kept for users who build their own."""
+
+    def __init__(self, num_obs: int, n_neurons: int, num_actions: int, *, device: torch.device | None = None) -> None:
+        super().__init__()
+        self.device = device
+        self.ncp = LiquidNCPNetwork(num_obs + num_actions, n_neurons, 1, device=device).to(device)
+
+    def forward(self, obs: torch.Tensor, actions: torch.Tensor, hidden: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        q_values, new_hidden = self.ncp(torch.cat([obs, actions], dim=-1), hidden)
+        return q_values, new_hidden

@@ -51,3 +51,16 @@ class SACCriticNCPDiscrete(nn.Module):
 
     def forward(self, obs: torch.Tensor) -> torch.Tensor:
         return self.ncp(obs)
+
+
+class SACCriticDiscrete(nn.Module):
+    """Liquid NCP critic: Q(obs, .) for every action through the fused LiquidNCPNetwork (discrete.py:103-145)."""
+
+    def __init__(self, num_obs: int, n_neurons: int, num_actions: int, *, device: torch.device | None = None) -> None:
+        super().__init__()
+        self.device = device
+        self.ncp = LiquidNCPNetwork(num_obs, n_neurons, num_actions, device=device).to(device)
+
+    def forward(self, obs: torch.Tensor, hidden: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        q_values, new_hidden = self.ncp(obs, hidden)
+        return q_values, new_hidden
