@@ -43,6 +43,29 @@ def gpu_time_ms(fn, warmup=5, iters=20):
     return e0.elapsed_time(e1) / iters
 
 
+def graph_time_ms(fn, reps=20):
+    """Device time per call with `reps` calls captured in ONE CUDA graph: no host gaps between the launches.  Eager timing of a
+    microsecond-scale kernel measures the Python / allocation cost per call instead (round 1 quoted 34 us for a 6.9 us gather)."""
+    import torch
+
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(reps):
+            fn()
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
 def cpu_time_ms(fn, warmup=1, iters=3):
     for _ in range(warmup):
         fn()
@@ -243,17 +266,21 @@ def main():
     for B in ([131072] if args.quick else [131072, 1_000_000]):
         torch.manual_seed(1)
         idx = torch.randint(0, big.buffer.size, (B,), device=dev)
-        big.buffer.use_shadow = False
-        pms = gpu_time_ms(lambda: big.buffer.gather(idx), warmup=5, iters=20)      # six separate arrays
-        big.buffer.use_shadow = True
-        gms = gpu_time_ms(lambda: big.buffer.gather(idx), warmup=5, iters=20)      # packed shadow table (default)
+        from velora_b200 import functional as VF
+
+        arrays = [getattr(big.buffer, k) for k in ("states", "actions", "rewards", "next_states", "dones", "hiddens")]
+        table, offsets, stride = big.buffer._shadow_table()
+        pms = graph_time_ms(lambda: VF.gather_rows(arrays, idx, big.buffer.size))      # six separate arrays
+        gms = graph_time_ms(lambda: VF.gather_packed(table, offsets, stride, [a.shape[1] for a in arrays], idx, big.buffer.size))   # packed table
+        eager_ms = gpu_time_ms(lambda: big.buffer.gather(idx), warmup=5, iters=20)
         gbs = 160.0 * B / (gms * 1e-3) / 1e9
         ref_ms = gpu_time_ms(lambda: [getattr(big.buffer, k)[idx] for k in ("states", "actions", "rewards", "next_states", "dones", "hiddens")],
                              warmup=3, iters=10)
         emit(config=f"cfg5 ReplayBuffer(1M,4,1,8) gather, batch {B}", metric="transitions_per_s", value=B / (gms * 1e-3), ms=gms,
              roofline={"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
                        "algorithmic_bytes_per_transition": 160},
-             six_array_gather_ms=pms, torch_six_index_kernels_ms=ref_ms)
+             six_array_gather_ms=pms, torch_six_index_kernels_ms=ref_ms, eager_call_ms=eager_ms,
+             timing="20 gathers captured in one CUDA graph (kernel time); eager_call_ms includes the Python / allocation cost per call")
         tms = gpu_time_ms(lambda: big._train_step(B), warmup=3, iters=10)
         emit(config=f"cfg5 sample + NeuroFlowCT update, batch {B}, 1 GPU", metric="transitions_per_s", value=B / (tms * 1e-3), ms=tms)
         bigg = make_agent(dev, 1_000_000, capturable=True, fused=True)
