@@ -407,6 +407,9 @@ struct BwdSmem {
     static constexpr int BAR = SW + C::S_TOTAL * 4;
     static constexpr int BYTES = BAR + 64;
     static_assert(BAR % 16 == 0, "barrier alignment");
+    // the two deliberate operand over-reads stay inside this CTA's window, in memory the kernel initialises:
+    static_assert(DS + 16 * PLANE <= WB, "the MN-major M = 128 stack (16 planes from DS) must end before the weight planes");
+    static_assert(Z + 10 * PLANE <= SBUF, "the N = 80 operand (10 planes from Z) must end inside the ds planes");
 };
 
 template <class C, bool VEC, int LAY>
