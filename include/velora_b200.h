@@ -218,6 +218,25 @@ int vb_sac_head_fwd(const float* x, const float* eps, const float* scale, const 
 int vb_sac_head_bwd(const float* x, const float* eps, const float* scale, float log_std_min, float log_std_max, int64_t B, int A,
                     const float* a_norm, const float* std_in, const float* d_actions, const float* d_log_prob, float* dx, void* stream);
 
+/* The loss arithmetic around the networks in NeuroFlowCT's train step (velora/models/nf/agent.py:194-209, 236-245; modules.py:700-706),
+ * one launch forward and one backward per loss; all tensors [B] (= [B,1] contiguous), scalars are device pointers; `workspace`:
+ * vb_sac_loss_workspace_bytes() bytes, zero-initialised once, one per stream.
+ *   critic:  target = r + (1 - done) * gamma * (min(q1_t, q2_t) - exp(log_alpha) * logp_next);  losses[k] = mean((q_k - target)^2)
+ *   actor:   out[0] = mean(exp(log_alpha) * logp - min(q1, q2)), out[1] = mean(logp)
+ *   entropy: out[0] = -log_alpha * mean(logp + target_entropy), out[1] = that mean */
+int64_t vb_sac_loss_workspace_bytes(void);
+int vb_sac_critic_loss_fwd(const float* q1, const float* q2, const float* q1_target, const float* q2_target, const float* logp_next,
+                           const float* rewards, const float* dones, const float* log_alpha, float gamma, int64_t B, float* target,
+                           float* losses, void* workspace, void* stream);
+int vb_sac_critic_loss_bwd(const float* q1, const float* q2, const float* target, const float* d_loss1, const float* d_loss2, int64_t B,
+                           float* dq1, float* dq2, void* stream);
+int vb_sac_actor_loss_fwd(const float* logp, const float* q1, const float* q2, const float* log_alpha, int64_t B, float* out,
+                          void* workspace, void* stream);
+int vb_sac_actor_loss_bwd(const float* q1, const float* q2, const float* log_alpha, const float* d_loss, int64_t B, float* dlogp,
+                          float* dq1, float* dq2, void* stream);
+int vb_sac_entropy_loss_fwd(const float* logp, const float* log_alpha, float target_entropy, int64_t B, float* out, void* workspace,
+                            void* stream);
+
 /* ------------------------------------------------------------------------------------------------ data-parallel exchange */
 /* One-shot all-reduce (sum, then * scale) of a small fp32 block over NVLink peer memory: the ONE exchange of the data-parallel path, the
  * parameter-gradient block of a backward.  peer_buffers: host array of `world` device pointers, entry r = rank r's

@@ -430,6 +430,127 @@ class SacHeadFn(torch.autograd.Function):
         return dx, None, None, None, None, None
 
 
+# ---------------------------------------------------------------------------------------------------- fused SAC losses
+_LOSS_WS = {}
+
+
+def _loss_workspace(dev: torch.device) -> torch.Tensor:
+    """Zero-initialised ticket + partial-sum area of the loss kernels, one per (device, stream); inside a graph capture a fresh one
+    from the graph's pool (zeroed by a captured memset)."""
+    n = int(_lib.lib().vb_sac_loss_workspace_bytes())
+    if torch.cuda.is_current_stream_capturing():
+        return torch.zeros(n, dtype=torch.uint8, device=dev)
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    ws = _LOSS_WS.get(key)
+    if ws is None:
+        ws = torch.zeros(n, dtype=torch.uint8, device=dev)
+        _LOSS_WS[key] = ws
+    return ws
+
+
+class SacCriticLossFn(torch.autograd.Function):
+    """(c1_loss, c2_loss) of NeuroFlowCT._update_critics (agent.py:194-209): the target from the target critics, the next log-prob,
+    reward and done flag (no gradient, as in the reference's `torch.no_grad()` block) and both MSE losses in one launch."""
+
+    @staticmethod
+    def forward(ctx, q1, q2, q1t, q2t, logp_next, rewards, dones, log_alpha, gamma):
+        L = _lib.lib()
+        dev = q1.device
+        B = q1.numel()
+        q1, q2, q1t, q2t, logp_next, rewards, dones = (_f32c(t.detach()).reshape(-1) for t in (q1, q2, q1t, q2t, logp_next, rewards, dones))
+        la = _f32c(log_alpha.detach()).reshape(1)
+        target = torch.empty(B, dtype=torch.float32, device=dev)
+        losses = torch.empty(2, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            ws = _loss_workspace(dev)
+            _count(1)
+            _lib.check(L.vb_sac_critic_loss_fwd(_lib.ptr(q1), _lib.ptr(q2), _lib.ptr(q1t), _lib.ptr(q2t), _lib.ptr(logp_next), _lib.ptr(rewards),
+                                                _lib.ptr(dones), _lib.ptr(la), float(gamma), B, _lib.ptr(target), _lib.ptr(losses), _lib.ptr(ws),
+                                                _lib.stream_ptr(dev)), "vb_sac_critic_loss_fwd")
+        ctx.save_for_backward(q1, q2, target)
+        ctx.set_materialize_grads(False)
+        return losses[0], losses[1]
+
+    @staticmethod
+    def backward(ctx, g1, g2):
+        q1, q2, target = ctx.saved_tensors
+        L = _lib.lib()
+        dev = q1.device
+        B = q1.numel()
+        dq1 = torch.empty((B, 1), dtype=torch.float32, device=dev) if g1 is not None else None
+        dq2 = torch.empty((B, 1), dtype=torch.float32, device=dev) if g2 is not None else None
+        g1c = _f32c(g1).reshape(1) if g1 is not None else None
+        g2c = _f32c(g2).reshape(1) if g2 is not None else None
+        with torch.cuda.device(dev):
+            _count(1)
+            _lib.check(L.vb_sac_critic_loss_bwd(_lib.ptr(q1), _lib.ptr(q2), _lib.ptr(target), _lib.ptr(g1c), _lib.ptr(g2c), B, _lib.ptr(dq1),
+                                                _lib.ptr(dq2), _lib.stream_ptr(dev)), "vb_sac_critic_loss_bwd")
+        return dq1, dq2, None, None, None, None, None, None, None
+
+
+class SacActorLossFn(torch.autograd.Function):
+    """mean(exp(log_alpha) * logp - min(q1, q2)) (agent.py:238-241), gradients to logp, q1, q2 and log_alpha."""
+
+    @staticmethod
+    def forward(ctx, logp, q1, q2, log_alpha):
+        L = _lib.lib()
+        dev = logp.device
+        B = logp.numel()
+        lp, a, b = (_f32c(t.detach()).reshape(-1) for t in (logp, q1, q2))
+        la = _f32c(log_alpha.detach()).reshape(1)
+        out = torch.empty(2, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            ws = _loss_workspace(dev)
+            _count(1)
+            _lib.check(L.vb_sac_actor_loss_fwd(_lib.ptr(lp), _lib.ptr(a), _lib.ptr(b), _lib.ptr(la), B, _lib.ptr(out), _lib.ptr(ws),
+                                               _lib.stream_ptr(dev)), "vb_sac_actor_loss_fwd")
+        ctx.save_for_backward(a, b, la, out)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b, la, out = ctx.saved_tensors
+        L = _lib.lib()
+        dev = a.device
+        B = a.numel()
+        gc = _f32c(g).reshape(1)
+        dlogp = torch.empty((B, 1), dtype=torch.float32, device=dev)
+        dq1 = torch.empty((B, 1), dtype=torch.float32, device=dev)
+        dq2 = torch.empty((B, 1), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _count(1)
+            _lib.check(L.vb_sac_actor_loss_bwd(_lib.ptr(a), _lib.ptr(b), _lib.ptr(la), _lib.ptr(gc), B, _lib.ptr(dlogp), _lib.ptr(dq1), _lib.ptr(dq2),
+                                               _lib.stream_ptr(dev)), "vb_sac_actor_loss_bwd")
+        # d/d log_alpha = g * alpha * mean(logp); the reference's backward populates it too (and the entropy step zeroes it again)
+        dla = (gc * la.exp() * out[1]).reshape(()) if ctx.needs_input_grad[3] else None
+        return dlogp, dq1, dq2, dla
+
+
+class SacEntropyLossFn(torch.autograd.Function):
+    """-mean(log_alpha * (logp + target_entropy).detach()) (modules.py:700-706)."""
+
+    @staticmethod
+    def forward(ctx, log_alpha, logp, target_entropy):
+        L = _lib.lib()
+        dev = logp.device
+        B = logp.numel()
+        lp = _f32c(logp.detach()).reshape(-1)
+        la = _f32c(log_alpha.detach()).reshape(1)
+        out = torch.empty(2, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            ws = _loss_workspace(dev)
+            _count(1)
+            _lib.check(L.vb_sac_entropy_loss_fwd(_lib.ptr(lp), _lib.ptr(la), float(target_entropy), B, _lib.ptr(out), _lib.ptr(ws), _lib.stream_ptr(dev)),
+                       "vb_sac_entropy_loss_fwd")
+        ctx.save_for_backward(out)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (out,) = ctx.saved_tensors
+        return (-(g * out[1])).reshape(()), None, None
+
+
 def _pack_liquid(L, dims, masks, params, dev, st):
     """vb_liquid_pack of the seven layers -> (packed block, masks as passed, heads mask type code)."""
     I, Ni, Nc, O = dims

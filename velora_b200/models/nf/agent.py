@@ -28,6 +28,9 @@ class NeuroFlowCTCore:
         self.seed = set_seed(seed)
         self.state_dim, self.action_dim = state_dim, action_dim
         self.gamma, self.tau = gamma, tau
+        # fused=True also takes the loss arithmetic around the networks (critic target + both MSE losses, actor loss, entropy loss) as
+        # one launch forward / one backward each (velora_b200/csrc/sac_loss.cu) instead of ~40 framework kernels per step
+        self.fused_losses = bool(fused)
         # capturable=True keeps the optimizer state on the device so that a whole train step can be captured in a CUDA graph
         okw = {"capturable": True} if capturable else None
         if fused:   # one-launch Adam and Polyak updates (velora_b200/optim.py); same optimizer state layout as Adam(capturable=True)
@@ -48,6 +51,18 @@ class NeuroFlowCTCore:
 
     def _update_critics(self, batch: BatchExperience) -> torch.Tensor:
         """agent.py:182-214"""
+        if getattr(self, "fused_losses", False) and batch.states.is_cuda:
+            from velora_b200 import functional as VF
+
+            with torch.no_grad():
+                next_actions, next_log_probs, _ = self.actor.forward(batch.next_states, batch.hiddens)
+                q1t, q2t = self.critic.target1(batch.next_states, next_actions), self.critic.target2(batch.next_states, next_actions)
+            current_q1, current_q2 = self.critic.predict(batch.states, batch.actions)
+            c1_loss, c2_loss = VF.SacCriticLossFn.apply(current_q1, current_q2, q1t, q2t, next_log_probs, batch.rewards, batch.dones,
+                                                        self.entropy.log_alpha, self.gamma)
+            critic_loss = c1_loss + c2_loss
+            self.critic.gradient_step(c1_loss, c2_loss)
+            return critic_loss
         with torch.no_grad():
             next_actions, next_log_probs, _ = self.actor.forward(batch.next_states, batch.hiddens)
             next_q = self.critic.target_predict(batch.next_states, next_actions)
@@ -68,9 +83,15 @@ class NeuroFlowCTCore:
         critic_loss = self._update_critics(batch)
         actions, log_probs, _ = self.actor.forward(batch.states, batch.hiddens)
         q1, q2 = self.critic.predict(batch.states, actions)
-        next_q = torch.min(q1, q2)
-        actor_loss = (self.entropy.alpha * log_probs - next_q).mean()
-        entropy_loss = self.entropy.compute_loss(log_probs)
+        if getattr(self, "fused_losses", False) and q1.is_cuda:
+            from velora_b200 import functional as VF
+
+            actor_loss = VF.SacActorLossFn.apply(log_probs, q1, q2, self.entropy.log_alpha)
+            entropy_loss = VF.SacEntropyLossFn.apply(self.entropy.log_alpha, log_probs.detach(), float(self.entropy.target))
+        else:
+            next_q = torch.min(q1, q2)
+            actor_loss = (self.entropy.alpha * log_probs - next_q).mean()
+            entropy_loss = self.entropy.compute_loss(log_probs)
         self.actor.gradient_step(actor_loss)
         self.entropy.gradient_step(entropy_loss)
         self.critic.update_targets()

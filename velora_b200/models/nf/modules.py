@@ -86,6 +86,15 @@ class CriticModule:
         soft_update(self.network2, self.target2, tau=self.tau)
 
     def gradient_step(self, c1_loss: torch.Tensor, c2_loss: torch.Tensor) -> None:
+        if c1_loss.grad_fn is not None and c1_loss.grad_fn is c2_loss.grad_fn:
+            # both losses come out of ONE fused node (functional.SacCriticLossFn): one backward pass; the two critics share no
+            # parameters, so this equals the reference's two separate passes (modules.py:401-415)
+            self.optim1.zero_grad()
+            self.optim2.zero_grad()
+            torch.autograd.backward([c1_loss, c2_loss])
+            self.optim1.step()
+            self.optim2.step()
+            return
         self.optim1.zero_grad()
         c1_loss.backward()
         self.optim1.step()
