@@ -261,6 +261,26 @@ def main():
     wall = (time.perf_counter() - t0) / 500
     emit(config="cfg2b NeuroFlowCT.predict captured in one CUDA graph, batch 1", metric="us_per_call", value=1e3 * ms1g, wall_us=1e6 * wall)
 
+    # ------------------------------------------------------------------ cfg 1 end to end: NeuroFlow("CartPole-v1", 20, 128).train(64, n_episodes=50)
+    # gymnasium is not installed: the environment is the CartPole-v1 physics restatement of baseline/envs_shim.py (labelled as such)
+    if not args.quick:
+        sys.path.insert(0, os.path.join(ROOT, "baseline"))
+        from envs_shim import CartPoleShim
+
+        from velora_b200.models import NeuroFlow
+
+        eagent = NeuroFlow(CartPoleShim(64), 20, 128, buffer_size=100_000, device=dev, seed=64, fused=True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        returns = eagent.train(64, n_episodes=50)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        n_env_steps = int(sum(returns))
+        emit(config="cfg1 NeuroFlow(CartPole shim, 20, 128).train(64, n_episodes=50): act + env.step + buffer.add + one fused train step per env step (eager)",
+             metric="wall_s_for_50_episodes", value=wall, env_steps=n_env_steps, ms_per_env_step=1e3 * wall / max(n_env_steps, 1),
+             mean_return_first10=sum(returns[:10]) / 10, mean_return_last10=sum(returns[-10:]) / 10,
+             note="environment = baseline/envs_shim.py (gymnasium is not installed); includes the 128-transition warm-up")
+
     # ------------------------------------------------------------------ cfg 5: gather + train step at large batch
     big = make_agent(dev, 1_000_000)
     for B in ([131072] if args.quick else [131072, 1_000_000]):
