@@ -72,9 +72,26 @@ def _worker(rank, world, port, out):
     whole_noise = VF.standard_normal_like(torch.zeros(5 * world, 3))
     dp.configure(True, reduce="mean")
     noise_ok = bool(torch.equal(torch.cat(shards), whole_noise)) and dp.rank() == rank
+    # discrete policy: every rank samples the GLOBAL batch from the gathered probabilities and keeps its rows (sac/discrete.py)
+    from velora_b200.models.sac import SACActorDiscrete
+
+    actor = SACActorDiscrete(4, 20, 3)
+    gp = torch.Generator().manual_seed(77)
+    probs_all = torch.softmax(torch.randn(6 * world, 3, generator=gp), dim=-1)
+    torch.manual_seed(321)
+    mine, _ = actor.get_sample(probs_all[rank * 6:(rank + 1) * 6])
+    after_dp = torch.rand(1)                     # the generator has advanced exactly as in the single-process draw
+    got = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(got, mine)
+    dp.configure(False)
+    torch.manual_seed(321)
+    whole, _ = actor.get_sample(probs_all)
+    after_single = torch.rand(1)
+    dp.configure(True, reduce="mean")
+    sample_ok = bool(torch.equal(torch.cat(got), whole)) and bool(torch.equal(after_dp, after_single))
     if rank == 0:
         torch.save({"same_params": same_params, "err": err, "bounds": (lo_, hi_), "mean": t.tolist(), "world": dp.world_size(),
-                    "noise_ok": noise_ok}, out)
+                    "noise_ok": noise_ok, "sample_ok": sample_ok}, out)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -88,6 +105,7 @@ def test_two_rank_gloo(tmp_path):
     assert r["err"] < 1e-12          # sum of shard gradients == gradient of the whole batch
     assert r["mean"] == [1.5, 1.5, 1.5]
     assert r["noise_ok"]             # the ranks' noise shards concatenate to the single-process draw of the global batch
+    assert r["sample_ok"]            # and so do the discrete policy's sampled actions; the generator advances identically
 
 
 def test_shard_bounds_cover_batch():

@@ -130,6 +130,7 @@ def test_two_rank_nccl_gradients_equal_single_process(tmp_path):
     out = str(tmp_path / "dp_gpu.pt")
     mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
     r = torch.load(out)
+    print("two-rank results:", r)
     assert r["liquid_allreduces"] == 1
     if r["oneshot_available"]:
         assert r["oneshot_used"] == 1 and r["oneshot_stress"] == 0.0, r

@@ -24,7 +24,20 @@ class SACActorDiscrete(nn.Module):
         # argument validation reads a device flag back to the host, which is illegal while a CUDA graph is being captured
         validate = not (probs.is_cuda and torch.cuda.is_current_stream_capturing())
         dist = Categorical(probs=probs, validate_args=validate)
-        actions = dist.sample()
+        from velora_b200 import dataparallel as _dp
+
+        if _dp.is_enabled() and _dp.world_size() > 1 and probs.dim() == 2:
+            # data-parallel: every rank samples the GLOBAL batch from the gathered probabilities (identical generators => identical draws,
+            # and the generator advances exactly like the single-process step) and keeps its own rows
+            import torch.distributed as tdist
+
+            n = probs.shape[0]
+            parts = [torch.empty_like(probs) for _ in range(_dp.world_size())]
+            tdist.all_gather(parts, probs.detach().contiguous(), group=_dp._state["group"])
+            full = Categorical(probs=torch.cat(parts), validate_args=validate).sample()
+            actions = full[_dp.rank() * n:(_dp.rank() + 1) * n]
+        else:
+            actions = dist.sample()
         return actions, dist.log_prob(actions).unsqueeze(-1)
 
     @torch.jit.ignore
