@@ -40,7 +40,20 @@ class BufferBase:
 
     # ------------------------------------------------------------------ packed shadow table
     def _arrays_key(self):
-        return tuple((id(getattr(self, name)), getattr(self, name)._version) for name in FIELDS)
+        """(identity, data pointer, version counter) of the six arrays.  The counter is bumped by every in-place torch op on the tensor,
+        NOT by writes through `.data` / detached aliases or by raw-pointer kernels: after such a write call `invalidate_shadow()`
+        (or set `use_shadow = False` on the buffer).  Tensors without a version counter (inference mode) never match: the table is
+        then rebuilt for every sample."""
+        def version(t):
+            try:
+                return t._version
+            except Exception:
+                return object()
+        return tuple((id(getattr(self, name)), getattr(self, name).data_ptr(), version(getattr(self, name))) for name in FIELDS)
+
+    def invalidate_shadow(self) -> None:
+        """Forget the packed table: the next `sample` rebuilds it from the six arrays (the truth)."""
+        self._shadow_key = None
 
     def _shadow_current(self) -> bool:
         return self._shadow is not None and self._shadow_key == self._arrays_key()
