@@ -75,7 +75,15 @@ struct Cfg {
     static constexpr int S_WIN = S_OUT + S_OUT_N, S_WIN_N = NI * Ip;          // win [NI][Ip]
     static constexpr int S_TOTAL = S_WIN + S_WIN_N;
     // saved forward factors: one float4 (A, Bc, Cc, mish'(c)) per command neuron + m in NC / 4 float4
-    static constexpr int NQ = NC + NC / 4;
+#ifndef VB_SAVE_RAW
+#define VB_SAVE_RAW 0
+#endif
+    // VB_SAVE_RAW = 0 (default): the forward saves the finished gate factors and m (160 B per sample-step).  = 1: it saves
+    // (tanh s_g, tanh s_h, gate, c) - 128 B - and the backward's role B forms the factors and mish(c) / mish'(c) itself.  Measured on
+    // config 3 (profiles/r02/README.md): forward 0.104 -> 0.094 ms but backward 0.203 -> 0.226 ms - role B's extra ~100 instructions
+    // sit on the step's dependency chain - so the work stays in the forward.
+    static constexpr bool SAVE_RAW = VB_SAVE_RAW != 0;
+    static constexpr int NQ = SAVE_RAW ? NC : NC + NC / 4;
     static constexpr int N_SMALL = I * NI + O * NC + NI + O;                  // dW_in, dW_out, db_in, db_out entries
 };
 
@@ -344,14 +352,20 @@ __global__ void __launch_bounds__(TM) liquid_fwd_tc_kernel(const float* __restri
                     float hn = fmaf(gate, d, tg);
                     h[2 * c + jj] = hn;
                     cc[jj] = s8[4 * jj + 3] + hn;
-                    if (SAVE) {
+                    if (SAVE && C::SAVE_RAW) {
+                        fa[jj] = tg; fb[jj] = th; fc[jj] = gate;
+                    } else if (SAVE) {
                         const float omg = 1.0f - gate;
                         fa[jj] = omg * fmaf(-tg, tg, 1.0f);
                         fb[jj] = gate * fmaf(-th, th, 1.0f);
                         fc[jj] = d * gate * omg;
                     }
                 }
-                if (SAVE) {
+                if (SAVE && C::SAVE_RAW) {
+                    mish2(cc[0], cc[1], m[2 * c], m[2 * c + 1]);
+                    sv[(2 * c) * TM] = make_float4(fa[0], fb[0], fc[0], cc[0]);
+                    sv[(2 * c + 1) * TM] = make_float4(fa[1], fb[1], fc[1], cc[1]);
+                } else if (SAVE) {
                     float g0, g1;
                     mish2_grad(cc[0], cc[1], m[2 * c], m[2 * c + 1], g0, g1);
                     sv[(2 * c) * TM] = make_float4(fa[0], fb[0], fc[0], g0);
@@ -360,7 +374,7 @@ __global__ void __launch_bounds__(TM) liquid_fwd_tc_kernel(const float* __restri
                     mish2(cc[0], cc[1], m[2 * c], m[2 * c + 1]);
                 }
             }
-            if (SAVE) {
+            if (SAVE && !C::SAVE_RAW) {
 #pragma unroll
                 for (int q = 0; q < C::NC / 4; ++q) sv[(C::NC + q) * TM] = make_float4(m[4 * q], m[4 * q + 1], m[4 * q + 2], m[4 * q + 3]);
             }
@@ -585,44 +599,52 @@ __global__ void __launch_bounds__(BT, (BwdSmem<C>::BYTES + 1024 > 58368 ? 3 : 4)
                     }
                 }
                 const float4* sv = saved + ((int64_t)t * n_tiles + tile) * (C::NQ * TM) + row;
-                // dW_out / db_out of this thread's own sample
-                {
-                    float m[C::NC];
-#pragma unroll
-                    for (int q = 0; q < C::NC / 4; ++q) {
-                        float4 v = __ldg(sv + (C::NC + q) * TM);
-                        m[4 * q] = v.x; m[4 * q + 1] = v.y; m[4 * q + 2] = v.z; m[4 * q + 3] = v.w;
-                    }
-#pragma unroll
-                    for (int o = 0; o < C::O; ++o) {
-#pragma unroll
-                        for (int j = 0; j < C::NC; ++j) acc[o * C::NC + j] = fmaf(dyr[o], m[j], acc[o * C::NC + j]);
-                        acc[C::O * C::NC + o] += dyr[o];
-                    }
-                }
                 store_half_chunk3<3>(zP, 1, row, 1, hp[0], hp[1], hp[2], hp[3]);
                 {
                     float f[8] = {hp[4], hp[5], hp[6], hp[7], 1.0f, 0.f, 0.f, 0.f};
                     store_chunk3<3>(zP, 2, row, f);
                 }
-                // gating derivatives from the saved factors, two neurons (= one 8-feature chunk of ds) at a time
+                // gating derivatives from the saved values, two neurons (= one 8-feature chunk of ds) at a time; dW_out / db_out of this
+                // thread's own sample along the way
                 const float* wo = sw + C::S_OUT;
+#pragma unroll
+                for (int o = 0; o < C::O; ++o) acc[C::O * C::NC + o] += dyr[o];
 #pragma unroll
                 for (int c = 0; c < C::NC / 2; ++c) {
                     float s8[8];
+                    float4 g[2];
+                    float mm[2];
+                    g[0] = __ldg(sv + (2 * c) * TM);
+                    g[1] = __ldg(sv + (2 * c + 1) * TM);
+                    if constexpr (C::SAVE_RAW) {        // (tanh s_g, tanh s_h, gate, c) -> (A, Bc, Cc, mish'(c)), m = mish(c)
+                        float d0, d1;
+                        mish2_grad(g[0].w, g[1].w, mm[0], mm[1], d0, d1);
+                        const float dm[2] = {d0, d1};
+#pragma unroll
+                        for (int jj = 0; jj < 2; ++jj) {
+                            const float tg = g[jj].x, th = g[jj].y, gate = g[jj].z, omg = 1.0f - gate;
+                            g[jj] = make_float4(omg * fmaf(-tg, tg, 1.0f), gate * fmaf(-th, th, 1.0f), (th - tg) * gate * omg, dm[jj]);
+                        }
+                    } else {
+                        const float4 mq = __ldg(sv + (C::NC + c / 2) * TM);
+                        mm[0] = (c & 1) ? mq.z : mq.x;
+                        mm[1] = (c & 1) ? mq.w : mq.y;
+                    }
 #pragma unroll
                     for (int jj = 0; jj < 2; ++jj) {
                         const int j = 2 * c + jj;
-                        const float4 g = __ldg(sv + j * TM);
                         float dm = 0.f;
 #pragma unroll
-                        for (int o = 0; o < C::O; ++o) dm = fmaf(dyr[o], wo[o * C::NCp + j], dm);
-                        const float dc = dm * g.w;
+                        for (int o = 0; o < C::O; ++o) {
+                            dm = fmaf(dyr[o], wo[o * C::NCp + j], dm);
+                            acc[o * C::NC + j] = fmaf(dyr[o], mm[jj], acc[o * C::NC + j]);
+                        }
+                        const float dc = dm * g[jj].w;
                         const float dhn = dc + dhc[j];
-                        s8[4 * jj + 0] = dhn * g.x;        // ds_g
-                        s8[4 * jj + 1] = dhn * g.y;        // ds_h
-                        s8[4 * jj + 2] = dhn * g.z;        // ds_f (both f heads)
-                        s8[4 * jj + 3] = dc;               // ds_proj
+                        s8[4 * jj + 0] = dhn * g[jj].x;        // ds_g
+                        s8[4 * jj + 1] = dhn * g[jj].y;        // ds_h
+                        s8[4 * jj + 2] = dhn * g[jj].z;        // ds_f (both f heads)
+                        s8[4 * jj + 3] = dc;                   // ds_proj
                     }
                     store_chunk3<4>(dsP, c, row, s8);
                 }
