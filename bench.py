@@ -32,6 +32,7 @@ UNIT = "sample-steps/s"
 SHAPE = dict(I=4, N=20, O=2, Ni=12, Nc=8)
 ALGO_BYTES_FWD = 4 * (SHAPE["I"] + SHAPE["O"] + SHAPE["Nc"])            # read x_t, write y_t, write h_t
 ALGO_BYTES_BWD = 4 * (2 * SHAPE["I"] + SHAPE["O"] + SHAPE["Nc"])        # read x_t, h_{t-1}, dy_t; write dx_t
+SAVED_BYTES = 4 * (5 * SHAPE["Nc"])                                      # round 2: gate factors + mish(c) the forward saves for the backward
 
 
 def workload_config(B: int, T: int) -> dict:
@@ -685,6 +686,9 @@ def run_ours(args) -> None:
             "roofline": {"bound": "hbm", "kernel": "liquid_bwd_tc_kernel", "achieved": bwd_gbs, "peak": hbm_peak,
                          "unit": "GB/s", "frac": bwd_gbs / hbm_peak, "traffic": traffic, "peak_kind": peak_kind,
                          "algorithmic_bytes_per_sample_step": ALGO_BYTES_BWD, "kernel_ms": bwd_ms,
+                         "saved_activation_bytes_per_sample_step": SAVED_BYTES,
+                         "traffic_note": "traffic exceeds the algorithmic bytes by design: the forward saves the gate factors (160 B per "
+                                         "sample-step) and the backward reads them back instead of re-running the five heads",
                          "fwd_kernel_ms": fwd_ms, "fwd_achieved": fwd_gbs,
                          "timing": "20 back-to-back launches between CUDA events on the launching stream, inputs rotating over 4 sets",
                          "eager_event_ms": {"bwd": eager_bwd_ms, "fwd": eager_fwd_ms},
