@@ -122,6 +122,13 @@ __device__ __forceinline__ void stg_row(float* p, const float (&src)[N], bool ve
     }
 }
 
+// streaming 128-bit load that does not allocate in L1 (the saved block is read exactly once)
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
 // Stage the three small-layer pieces of the packed block in shared memory: bulk (TMA) copies completing on an mbarrier when the
 // block is 16-byte aligned (torch allocations are), plain loads otherwise.  Called by all threads; returns after the data is visible.
 template <class C>
@@ -614,8 +621,8 @@ __global__ void __launch_bounds__(BT, (BwdSmem<C>::BYTES + 1024 > 58368 ? 3 : 4)
                     float s8[8];
                     float4 g[2];
                     float mm[2];
-                    g[0] = __ldg(sv + (2 * c) * TM);
-                    g[1] = __ldg(sv + (2 * c + 1) * TM);
+                    g[0] = ldg_stream(sv + (2 * c) * TM);
+                    g[1] = ldg_stream(sv + (2 * c + 1) * TM);
                     if constexpr (C::SAVE_RAW) {        // (tanh s_g, tanh s_h, gate, c) -> (A, Bc, Cc, mish'(c)), m = mish(c)
                         float d0, d1;
                         mish2_grad(g[0].w, g[1].w, mm[0], mm[1], d0, d1);
@@ -626,7 +633,7 @@ __global__ void __launch_bounds__(BT, (BwdSmem<C>::BYTES + 1024 > 58368 ? 3 : 4)
                             g[jj] = make_float4(omg * fmaf(-tg, tg, 1.0f), gate * fmaf(-th, th, 1.0f), (th - tg) * gate * omg, dm[jj]);
                         }
                     } else {
-                        const float4 mq = __ldg(sv + (C::NC + c / 2) * TM);
+                        const float4 mq = ldg_stream(sv + (C::NC + c / 2) * TM);
                         mm[0] = (c & 1) ? mq.z : mq.x;
                         mm[1] = (c & 1) ? mq.w : mq.y;
                     }
