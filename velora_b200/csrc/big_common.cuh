@@ -22,10 +22,10 @@ constexpr int STAGE_BYTES = STAGE_CHUNKS * PROWS * 16;                    // 199
 constexpr int RING = 3;
 constexpr int A_STAGES = 6;                  // stages 0..5 (chunks 0..35) contract over the a-part of z~ only
 // Element-wise threads per sample: warps w, w + 4, w + 8, ... address the same TMEM lanes and split a row's features.  Measured in round 2
-// (profiles/r02/README.md): six threads per sample (24 warps, 72 registers) execute 27 % more instructions (per-thread overheads) at 50 %
-// instead of 45 % issue utilisation - 4.52 ms against 4.41 ms for the training forward - so three it stays.
+// on the training forward at 32768 x 64 (profiles/r02/README.md): three threads 4.41 ms, four 4.29 ms, six 4.52 ms (24 warps at 72
+// registers execute 27 % more instructions - per-thread overheads - at 50 % instead of 45 % issue utilisation).
 #ifndef VB_BIG_EWT
-#define VB_BIG_EWT 3
+#define VB_BIG_EWT 4
 #endif
 constexpr int EWT = VB_BIG_EWT;
 constexpr int EW = TM * EWT;
