@@ -328,6 +328,14 @@ def gen_buffer(ref) -> dict:
 
 
 # ----------------------------------------------------------------------------------------------- train step (cfg 1/2)
+def _forget_scripted_classes() -> None:
+    """torch.jit caches one concrete type per module class, ignored methods included: a class that was scripted earlier in the same
+    process (another test) would keep its old `get_sample` after the patch below.  Start from an empty store."""
+    import torch.jit._recursive as _rec
+
+    _rec.concrete_type_store = _rec.ConcreteTypeStore()
+
+
 def gen_train(ref) -> dict:
     """Three NeuroFlowCT._train_step calls (velora/models/nf/agent.py:182-255) on a synthetic buffer, InvertedPendulum
     shapes (S=4, A=1, scale 3, bias 0; actor 20 / critic 128 neurons), batch 32, with the policy noise and the sampled
@@ -346,6 +354,7 @@ def gen_train(ref) -> dict:
         return x_t, Normal(mean, std).log_prob(x_t)
 
     orig = cont.SACActor.get_sample
+    _forget_scripted_classes()
     cont.SACActor.get_sample = torch.jit.ignore(get_sample)
     try:
         S, A, B, steps = 4, 1, 32, 3
@@ -399,6 +408,7 @@ def gen_train(ref) -> dict:
         out["dims"] = np.array([S, A, B, steps, n], dtype=np.int64)
     finally:
         cont.SACActor.get_sample = orig
+        _forget_scripted_classes()
     return out
 
 
@@ -425,6 +435,7 @@ def gen_train_discrete(ref) -> dict:
         return actions, torch.log(torch.gather(probs, -1, actions.unsqueeze(-1)))   # == Categorical(probs).log_prob(actions)[:, None]
 
     orig = disc.SACActorDiscrete.get_sample
+    _forget_scripted_classes()
     disc.SACActorDiscrete.get_sample = torch.jit.ignore(get_sample)
     try:
         S, A, B, steps = 4, 2, 32, 3
@@ -478,6 +489,7 @@ def gen_train_discrete(ref) -> dict:
         out["dims"] = np.array([S, A, B, steps, n], dtype=np.int64)
     finally:
         disc.SACActorDiscrete.get_sample = orig
+        _forget_scripted_classes()
     return out
 
 
