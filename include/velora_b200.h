@@ -49,7 +49,8 @@
 extern "C" {
 #endif
 
-#define VB_ABI_VERSION 3      /* 3: the liquid forward saves gate factors for the backward (vb_liquid_saved_bytes, `saved` arguments);
+#define VB_ABI_VERSION 4      /* 4: standalone NCPLiquidCell entry points (vb_cell_fwd / vb_cell_bwd), absent layers in vb_liquid_pack;
+                               *    3: the liquid forward saves gate factors for the backward (vb_liquid_saved_bytes, `saved` arguments);
                                *    2: layout flags, optimizer / policy-head / packed-gather / bf16-forward entry points added */
 
 /* argument errors */
@@ -141,6 +142,18 @@ int vb_liquid_unpack_grads(const float* dpacked, const void* m_in, int m_in_type
                            float* g_w_in, float* g_b_in, float* const* g_w_heads, float* const* g_b_heads,
                            float* g_w_out, float* g_b_out,
                            int I, int Ni, int Nc, int O, int accumulate, void* stream);
+
+/* The standalone NCPLiquidCell (reference velora/models/lnn/cell.py:147-169, one call = one step of the five heads, no inter / motor layer):
+ *     z = [x, h];  gate = sigmoid(f_g(z) + f_h(z));  h' = tanh(g(z)) (1 - gate) + gate tanh(h(z));  y = proj(z) + h'.
+ * `packed` is the liquid block for (I, Ni, Nc, O) = (In, In, Nc, Nc) written by vb_liquid_pack() with w_in = b_in = m_in = NULL and
+ * w_out = b_out = m_out = NULL (absent layers pack as zeros); vb_liquid_unpack_grads() with NULL g_w_in / g_w_out maps dpacked back to the heads.
+ *   x [B,In], h [B,Nc] or NULL (zeros) -> y [B,Nc], h_new [B,Nc];
+ *   dy [B,Nc], dh_new [B,Nc] or NULL -> dx [B,In] or NULL, dh [B,Nc] or NULL, dpacked (F layout of those dims, overwritten). */
+int64_t vb_cell_bwd_workspace_bytes(int In, int Nc);
+int vb_cell_fwd(const float* packed, const float* x, const float* h, float* y, float* h_new, int64_t B, int In, int Nc, void* stream);
+int vb_cell_bwd(const float* packed, const float* x, const float* h, const float* dy, const float* dh_new,
+                float* dx, float* dh, float* dpacked, int64_t B, int In, int Nc,
+                void* workspace, int64_t workspace_bytes, void* stream);
 
 /* The 512-neuron class (BASELINE config 4: LiquidNCPNetwork(8,512,1)) with the heads on tcgen05 in bf16 (bf16 operands, fp32 accumulation,
  * fp32 hidden state; 2e-2 relative contract) - opt-in; the fp32 contract of vb_liquid_fwd / vb_liquid_bwd stays on the tile kernels.

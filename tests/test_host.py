@@ -138,16 +138,10 @@ def test_layer_modules_formulas(golden):
     assert cell.head_size == 14
     assert np.array_equal(cell.sparsity_mask.numpy(), d["sd_sparsity_mask"])       # _prep_mask, cell.py:91-111
     cell.load_state_dict({k[3:]: torch.tensor(d[k]) for k in d.files if k.startswith("sd_")})
-    x = torch.tensor(d["x"], requires_grad=True)
-    h = torch.tensor(d["h"], requires_grad=True)
-    y, hn = cell(x, h)
-    assert np.array_equal(y.detach().numpy(), d["y"]) and np.array_equal(hn.detach().numpy(), d["hn"])
-    (y.sum() + 2.0 * hn.sum()).backward()
-    assert np.allclose(x.grad.numpy(), d["dx"], atol=1e-6) and np.allclose(h.grad.numpy(), d["dh"], atol=1e-6)
-    for k, p in cell.named_parameters():
-        assert np.allclose(p.grad.numpy(), d[f"grad_{k}"], atol=1e-6), k
-        if k.endswith("weight"):
-            assert torch.all(p.grad[cell.sparsity_mask == 0] == 0)                  # tests/models/test_lnn.py:570-576
+    assert [k for k, _ in cell.named_parameters()] == [k[5:] for k in d.files if k.startswith("grad_")]
+    # the cell's arithmetic lives in vb_cell_fwd / vb_cell_bwd (tests/test_liquid_gpu.py checks it against this golden): no CPU path
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        cell(torch.tensor(d["x"]), torch.tensor(d["h"]))
     # SparseLinear: masked weights are zero after init and the mask is applied in forward (test_lnn.py:429-480)
     mask = torch.tensor([[1, 0, 1], [0, 1, 0]])
     lin = SparseLinear(3, 2, mask)

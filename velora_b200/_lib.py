@@ -37,6 +37,9 @@ SIGNATURES = {
     "vb_liquid_fwd": (_i, [_p, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _p, _i64, _i, _p]),
     "vb_liquid_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _p, _i64, _i, _p]),
     "vb_liquid_unpack_grads": (_i, [_p, _p, _i, _pp, _i, _p, _i, _p, _p, _pp, _pp, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "vb_cell_bwd_workspace_bytes": (_i64, [_i, _i]),
+    "vb_cell_fwd": (_i, [_p, _p, _p, _p, _p, _i64, _i, _i, _p]),
+    "vb_cell_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _p, _i64, _p]),
     "vb_liquid_bf16_ok": (_i, [_i, _i, _i, _i]),
     "vb_liquid_bf16_fwd_workspace_bytes": (_i64, [_i, _i, _i, _i, _i64, _i]),
     "vb_liquid_bf16_saved_bytes": (_i64, [_i, _i, _i, _i, _i64, _i]),

@@ -76,6 +76,9 @@ int liquid_fwd(const float*, const float*, const float*, float*, float*, int64_t
 int64_t liquid_bwd_workspace_bytes(int, int, int, int);
 int liquid_bwd(const float*, const float*, const float*, const float*, const float*, const float*, const float*, float*, float*, float*,
                int64_t, int, int, int, int, int, void*, int64_t, cudaStream_t);
+int cell_fwd(const float*, const float*, const float*, float*, float*, int64_t, int, int, cudaStream_t);
+int cell_bwd(const float*, const float*, const float*, const float*, const float*, float*, float*, float*, int64_t, int, int, void*, int64_t,
+             cudaStream_t);
 int ncp_fwd(const float*, const float*, float*, int64_t, int, int, int, int, cudaStream_t);
 int64_t ncp_bwd_workspace_bytes(int, int, int, int);
 int ncp_bwd(const float*, const float*, const float*, float*, float*, int64_t, int, int, int, int, void*, int64_t, cudaStream_t);
@@ -127,6 +130,32 @@ extern "C" int64_t vb_liquid_bwd_workspace_bytes(int I, int Ni, int Nc, int O, i
     int64_t t = tc::has_tc_path(I, Ni, Nc, O) ? tc::bwd_workspace_bytes(I, Ni, Nc, O, B, T, !have_saved) : 0;
     return max64(max64(g, s), t);
 }
+
+// ---- the standalone NCPLiquidCell (cell.py:147-169): one step of the five heads without the inter / motor layers.  The packed block is the
+// network's with (I, Ni, Nc, O) = (In, In, Nc, Nc) and the inter / motor layers absent (vb_liquid_pack with NULL w_in / w_out).
+extern "C" int64_t vb_cell_bwd_workspace_bytes(int In, int Nc) {
+    if (!dims_ok(In, In, Nc, Nc)) return VB_ERR_BAD_DIMS;
+    return generic::liquid_bwd_workspace_bytes(In, In, Nc, Nc);
+}
+extern "C" int vb_cell_fwd(const float* packed, const float* x, const float* h, float* y, float* h_new, int64_t B, int In, int Nc,
+                           void* stream) {
+    VB_CHECK_ARG(dims_ok(In, In, Nc, Nc) && B >= 0, VB_ERR_BAD_DIMS, "vb_cell_fwd: bad dims B=%lld (%d,%d)", (long long)B, In, Nc);
+    if (B == 0) return 0;
+    VB_CHECK_ARG(packed && x && y && h_new, VB_ERR_NULL_POINTER, "vb_cell_fwd: null pointer");
+    return generic::cell_fwd(packed, x, h, y, h_new, B, In, Nc, (cudaStream_t)stream);
+}
+extern "C" int vb_cell_bwd(const float* packed, const float* x, const float* h, const float* dy, const float* dh_new, float* dx, float* dh,
+                           float* dpacked, int64_t B, int In, int Nc, void* workspace, int64_t workspace_bytes, void* stream) {
+    VB_CHECK_ARG(dims_ok(In, In, Nc, Nc) && B >= 0, VB_ERR_BAD_DIMS, "vb_cell_bwd: bad dims B=%lld (%d,%d)", (long long)B, In, Nc);
+    VB_CHECK_ARG(dpacked, VB_ERR_NULL_POINTER, "vb_cell_bwd: null dpacked");
+    if (B == 0) {
+        LiquidLayout L(In, In, Nc, Nc);
+        return (int)cudaMemsetAsync(dpacked, 0, (size_t)L.f_total * 4, (cudaStream_t)stream);
+    }
+    VB_CHECK_ARG(packed && x && dy, VB_ERR_NULL_POINTER, "vb_cell_bwd: null pointer");
+    return generic::cell_bwd(packed, x, h, dy, dh_new, dx, dh, dpacked, B, In, Nc, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
 extern "C" int64_t vb_ncp_bwd_workspace_bytes(int I, int Ni, int Nc, int O, int64_t B) {
     if (!dims_ok(I, Ni, Nc, O)) return VB_ERR_BAD_DIMS;
     int64_t t = (B >= kNcpTcMinBatch && ncp_tc::has_path(I, Ni, Nc, O)) ? ncp_tc::bwd_workspace_bytes(I, Ni, Nc, O) : 0;

@@ -58,7 +58,9 @@ static Plan make_plan(int rows, int packed_floats, int grad_floats, bool backwar
 }
 
 // ================================================================================================ liquid forward
-template <int BM>
+// CELL: the standalone NCPLiquidCell (cell.py:147-169): no inter layer (x [B, Ni] IS the a-part of z), no Mish / motor layer
+// (y = proj + h', Nc wide).  The layout is LiquidLayout(Ni, Ni, Nc, Nc); its inter / motor sections are unused.
+template <int BM, bool CELL>
 __global__ void __launch_bounds__(kTileThreads) liquid_fwd_generic_kernel(const float* __restrict__ packed, LiquidLayout L,
                                                                            const float* __restrict__ x, const float* __restrict__ h0,
                                                                            float* __restrict__ y, float* __restrict__ h_traj,
@@ -84,9 +86,13 @@ __global__ void __launch_bounds__(kTileThreads) liquid_fwd_generic_kernel(const 
         const int nvalid = (int)min((int64_t)BM, B - b0);
         load_rows<BM>(z + L.Ni * S, h0 ? h0 + b0 * L.Nc : nullptr, L.Nc, L.Nc, nvalid);
         for (int t = 0; t < T; ++t) {
-            load_rows<BM>(xs, x + (b0 * T + t) * L.I, (int64_t)T * L.I, L.I, nvalid);
-            __syncthreads();
-            dense<BM>(xs, L.I, P + L.win_t, L.NIp, P + L.b_in, L.Ni, [&](int j, int s, float v) { z[j * S + s] = mish_f(v); });
+            if (CELL) {
+                load_rows<BM>(z, x + (b0 * T + t) * L.Ni, (int64_t)T * L.Ni, L.Ni, nvalid);
+            } else {
+                load_rows<BM>(xs, x + (b0 * T + t) * L.I, (int64_t)T * L.I, L.I, nvalid);
+                __syncthreads();
+                dense<BM>(xs, L.I, P + L.win_t, L.NIp, P + L.b_in, L.Ni, [&](int j, int s, float v) { z[j * S + s] = mish_f(v); });
+            }
             __syncthreads();
             dense<BM>(z, L.K, P + L.wh_t, L.H4, P + L.b_h, L.H4, [&](int j, int s, float v) { sb[j * S + s] = v; });
             __syncthreads();
@@ -96,12 +102,17 @@ __global__ void __launch_bounds__(kTileThreads) liquid_fwd_generic_kernel(const 
                 float gate = sigmoid_f(sb[(2 * L.NCp + j) * S + s]);
                 float hn = fmaf(gate, th - tg, tg);
                 z[(L.Ni + j) * S + s] = hn;
-                mb[j * S + s] = mish_f(sb[(3 * L.NCp + j) * S + s] + hn);
+                const float c = sb[(3 * L.NCp + j) * S + s] + hn;
+                mb[j * S + s] = CELL ? c : mish_f(c);
             }
             __syncthreads();
-            dense<BM>(mb, L.Nc, P + L.wout_t, L.Op, P + L.b_out, L.O, [&](int o, int s, float v) { yb[o * S + s] = v; });
-            __syncthreads();
-            store_rows<BM>(y + (b0 * T + t) * L.O, (int64_t)T * L.O, yb, L.O, nvalid);
+            if (CELL) {
+                store_rows<BM>(y + (b0 * T + t) * L.Nc, (int64_t)T * L.Nc, mb, L.Nc, nvalid);
+            } else {
+                dense<BM>(mb, L.Nc, P + L.wout_t, L.Op, P + L.b_out, L.O, [&](int o, int s, float v) { yb[o * S + s] = v; });
+                __syncthreads();
+                store_rows<BM>(y + (b0 * T + t) * L.O, (int64_t)T * L.O, yb, L.O, nvalid);
+            }
             store_rows<BM>(h_traj + (b0 * T + t) * L.Nc, (int64_t)T * L.Nc, z + L.Ni * S, L.Nc, nvalid);
         }
         __syncthreads();
@@ -109,7 +120,7 @@ __global__ void __launch_bounds__(kTileThreads) liquid_fwd_generic_kernel(const 
 }
 
 // ================================================================================================ liquid backward
-template <int BM, bool ATOMIC>
+template <int BM, bool ATOMIC, bool CELL>
 __global__ void __launch_bounds__(kTileThreads) liquid_bwd_generic_kernel(
     const float* __restrict__ packed, LiquidLayout L, const float* __restrict__ x, const float* __restrict__ h0,
     const float* __restrict__ h_traj, const float* __restrict__ dy, const float* __restrict__ dh_traj,
@@ -150,18 +161,21 @@ __global__ void __launch_bounds__(kTileThreads) liquid_bwd_generic_kernel(
         const int nvalid = (int)min((int64_t)BM, B - b0);
         load_rows<BM>(dhc, dh_last ? dh_last + b0 * L.Nc : nullptr, L.Nc, L.Nc, nvalid);
         for (int t = T - 1; t >= 0; --t) {
-            load_rows<BM>(xs, x + (b0 * T + t) * L.I, (int64_t)T * L.I, L.I, nvalid);
+            if (CELL) load_rows<BM>(z, x + (b0 * T + t) * L.Ni, (int64_t)T * L.Ni, L.Ni, nvalid);
+            else load_rows<BM>(xs, x + (b0 * T + t) * L.I, (int64_t)T * L.I, L.I, nvalid);
             const float* hp = (t == 0) ? (h0 ? h0 + b0 * L.Nc : nullptr) : h_traj + (b0 * T + t - 1) * L.Nc;
             load_rows<BM>(z + L.Ni * S, hp, (t == 0) ? (int64_t)L.Nc : (int64_t)T * L.Nc, L.Nc, nvalid);
             load_rows<BM>(dyb, dy + (b0 * T + t) * L.O, (int64_t)T * L.O, L.O, nvalid);
             load_rows<BM>(dheb, dh_traj ? dh_traj + (b0 * T + t) * L.Nc : nullptr, (int64_t)T * L.Nc, L.Nc, nvalid);
             __syncthreads();
             // recompute
-            dense<BM>(xs, L.I, P + L.win_t, L.NIp, P + L.b_in, L.Ni, [&](int j, int s, float v) {
-                ub[j * S + s] = v;
-                z[j * S + s] = mish_f(v);
-            });
-            __syncthreads();
+            if (!CELL) {
+                dense<BM>(xs, L.I, P + L.win_t, L.NIp, P + L.b_in, L.Ni, [&](int j, int s, float v) {
+                    ub[j * S + s] = v;
+                    z[j * S + s] = mish_f(v);
+                });
+                __syncthreads();
+            }
             dense<BM>(z, L.K, P + L.wh_t, L.H4, P + L.b_h, L.H4, [&](int j, int s, float v) { sb[j * S + s] = v; });
             __syncthreads();
             // gating derivatives; sb is overwritten by ds
@@ -170,10 +184,14 @@ __global__ void __launch_bounds__(kTileThreads) liquid_bwd_generic_kernel(
                 float tg = tanh_f(sb[j * S + s]), th = tanh_f(sb[(L.NCp + j) * S + s]);
                 float gate = sigmoid_f(sb[(2 * L.NCp + j) * S + s]);
                 float hn = fmaf(gate, th - tg, tg);
-                float dmc;
-                float m = mish_fwd_grad(sb[(3 * L.NCp + j) * S + s] + hn, dmc);
-                float dm = 0.f;
-                for (int o = 0; o < L.O; ++o) dm = fmaf(dyb[o * S + s], P[L.wout + o * L.NCp + j], dm);
+                float dmc = 1.0f, m = 0.f, dm;
+                if (CELL) {
+                    dm = dyb[j * S + s];            // y = c: the upstream gradient is dL/dc itself
+                } else {
+                    m = mish_fwd_grad(sb[(3 * L.NCp + j) * S + s] + hn, dmc);
+                    dm = 0.f;
+                    for (int o = 0; o < L.O; ++o) dm = fmaf(dyb[o * S + s], P[L.wout + o * L.NCp + j], dm);
+                }
                 float dc = dm * dmc;
                 float dhn = dc + dhc[j * S + s] + dheb[j * S + s];
                 float omg = 1.0f - gate;
@@ -187,15 +205,24 @@ __global__ void __launch_bounds__(kTileThreads) liquid_bwd_generic_kernel(
             // dz = ds W  ->  du (inter part), carry (hidden part)
             dense<BM>(sb, L.H4, P + L.wh, L.Kp, nullptr, L.K, [&](int i, int s, float v) {
                 if (i < L.Ni) {
-                    float d;
-                    (void)mish_fwd_grad(ub[i * S + s], d);
-                    dub[i * S + s] = v * d;
+                    if (CELL) {
+                        if (dx && s < nvalid) dx[(b0 * T + t + (int64_t)s * T) * L.Ni + i] = v;      // dL/dx = the a-part of dz
+                    } else {
+                        float d;
+                        (void)mish_fwd_grad(ub[i * S + s], d);
+                        dub[i * S + s] = v * d;
+                    }
                 } else {
                     dhc[(i - L.Ni) * S + s] = v;
                 }
             });
             __syncthreads();
             // dx = du W_in (written straight to global) and the weight gradients of this step
+            if (CELL) {
+                wgrad<BM, ATOMIC>(acc + L.wh_t, L.H4, acc + L.b_h, z, L.K, sb, L.H4);
+                __syncthreads();
+                continue;
+            }
             if (dx) {
                 float* dxt = dx + (b0 * T + t) * L.I;
                 const int64_t pitch = (int64_t)T * L.I;
@@ -372,20 +399,29 @@ static int grid_for(K kernel, int smem, int64_t n_tiles, int cap_per_sm, int* gr
     return 0;
 }
 
-int liquid_fwd(const float* packed, const float* x, const float* h0, float* y, float* h_traj, int64_t B, int T,
-               int I, int Ni, int Nc, int O, cudaStream_t stream) {
+template <bool CELL>
+static int liquid_fwd_impl(const float* packed, const float* x, const float* h0, float* y, float* h_traj, int64_t B, int T,
+                           int I, int Ni, int Nc, int O, cudaStream_t stream) {
     LiquidLayout L(I, Ni, Nc, O);
     Plan p = make_plan(liquid_fwd_rows(L), L.total, 0, false);
     VB_CHECK_ARG(p.BM, VB_ERR_TOO_LARGE, "liquid forward: activations of (%d,%d,%d,%d) do not fit shared memory", I, Ni, Nc, O);
     int grid = 1, rc = 0;
 #define LAUNCH(BM_)                                                                                                    \
-    rc = grid_for(liquid_fwd_generic_kernel<BM_>, p.smem_bytes, (B + BM_ - 1) / BM_, 0, &grid);                        \
+    rc = grid_for(liquid_fwd_generic_kernel<BM_, CELL>, p.smem_bytes, (B + BM_ - 1) / BM_, 0, &grid);                  \
     if (rc) return rc;                                                                                                 \
-    liquid_fwd_generic_kernel<BM_><<<grid, kTileThreads, p.smem_bytes, stream>>>(packed, L, x, h0, y, h_traj, B, T, p.stage_w);
+    liquid_fwd_generic_kernel<BM_, CELL><<<grid, kTileThreads, p.smem_bytes, stream>>>(packed, L, x, h0, y, h_traj, B, T, p.stage_w);
     if (p.BM == 32) { LAUNCH(32) } else if (p.BM == 16) { LAUNCH(16) } else { LAUNCH(8) }
 #undef LAUNCH
     VB_LAUNCH_CHECK();
     return 0;
+}
+int liquid_fwd(const float* packed, const float* x, const float* h0, float* y, float* h_traj, int64_t B, int T,
+               int I, int Ni, int Nc, int O, cudaStream_t stream) {
+    return liquid_fwd_impl<false>(packed, x, h0, y, h_traj, B, T, I, Ni, Nc, O, stream);
+}
+// standalone cell: x [B, In], h [B, Nc] -> y [B, Nc], h' [B, Nc]
+int cell_fwd(const float* packed, const float* x, const float* h, float* y, float* h_new, int64_t B, int In, int Nc, cudaStream_t stream) {
+    return liquid_fwd_impl<true>(packed, x, h, y, h_new, B, 1, In, In, Nc, Nc, stream);
 }
 
 int64_t liquid_bwd_workspace_bytes(int I, int Ni, int Nc, int O) {
@@ -396,9 +432,10 @@ int64_t liquid_bwd_workspace_bytes(int I, int Ni, int Nc, int O) {
     return (int64_t)sms * 2 * L.f_total * 4;
 }
 
-int liquid_bwd(const float* packed, const float* x, const float* h0, const float* h_traj, const float* dy,
-               const float* dh_traj, const float* dh_last, float* dx, float* dh0, float* dpacked, int64_t B, int T,
-               int I, int Ni, int Nc, int O, void* ws, int64_t ws_bytes, cudaStream_t stream) {
+template <bool CELL>
+static int liquid_bwd_impl(const float* packed, const float* x, const float* h0, const float* h_traj, const float* dy,
+                           const float* dh_traj, const float* dh_last, float* dx, float* dh0, float* dpacked, int64_t B, int T,
+                           int I, int Ni, int Nc, int O, void* ws, int64_t ws_bytes, cudaStream_t stream) {
     LiquidLayout L(I, Ni, Nc, O);
     Plan p = make_plan(liquid_bwd_rows(L), L.total, L.f_total, true);
     VB_CHECK_ARG(p.BM, VB_ERR_TOO_LARGE, "liquid backward: activations of (%d,%d,%d,%d) do not fit shared memory", I, Ni, Nc, O);
@@ -406,9 +443,9 @@ int liquid_bwd(const float* packed, const float* x, const float* h0, const float
     if (p.smem_acc) {
         VB_CHECK_ARG(ws && ws_bytes >= liquid_bwd_workspace_bytes(I, Ni, Nc, O), VB_ERR_WORKSPACE, "vb_liquid_bwd: workspace too small");
 #define LAUNCH(BM_)                                                                                                    \
-    rc = grid_for(liquid_bwd_generic_kernel<BM_, false>, p.smem_bytes, (B + BM_ - 1) / BM_, 2, &grid);                  \
+    rc = grid_for(liquid_bwd_generic_kernel<BM_, false, CELL>, p.smem_bytes, (B + BM_ - 1) / BM_, 2, &grid);            \
     if (rc) return rc;                                                                                                 \
-    liquid_bwd_generic_kernel<BM_, false><<<grid, kTileThreads, p.smem_bytes, stream>>>(                                \
+    liquid_bwd_generic_kernel<BM_, false, CELL><<<grid, kTileThreads, p.smem_bytes, stream>>>(                          \
         packed, L, x, h0, h_traj, dy, dh_traj, dh_last, dx, dh0, reinterpret_cast<float*>(ws), B, T, p.stage_w);
         if (p.BM == 32) { LAUNCH(32) } else if (p.BM == 16) { LAUNCH(16) } else { LAUNCH(8) }
 #undef LAUNCH
@@ -418,15 +455,25 @@ int liquid_bwd(const float* packed, const float* x, const float* h0, const float
     } else {
         VB_CUDA(cudaMemsetAsync(dpacked, 0, (size_t)L.f_total * 4, stream));
 #define LAUNCH(BM_)                                                                                                    \
-    rc = grid_for(liquid_bwd_generic_kernel<BM_, true>, p.smem_bytes, (B + BM_ - 1) / BM_, 0, &grid);                   \
+    rc = grid_for(liquid_bwd_generic_kernel<BM_, true, CELL>, p.smem_bytes, (B + BM_ - 1) / BM_, 0, &grid);             \
     if (rc) return rc;                                                                                                 \
-    liquid_bwd_generic_kernel<BM_, true><<<grid, kTileThreads, p.smem_bytes, stream>>>(                                 \
+    liquid_bwd_generic_kernel<BM_, true, CELL><<<grid, kTileThreads, p.smem_bytes, stream>>>(                           \
         packed, L, x, h0, h_traj, dy, dh_traj, dh_last, dx, dh0, dpacked, B, T, p.stage_w);
         if (p.BM == 32) { LAUNCH(32) } else if (p.BM == 16) { LAUNCH(16) } else { LAUNCH(8) }
 #undef LAUNCH
         VB_LAUNCH_CHECK();
     }
     return 0;
+}
+int liquid_bwd(const float* packed, const float* x, const float* h0, const float* h_traj, const float* dy,
+               const float* dh_traj, const float* dh_last, float* dx, float* dh0, float* dpacked, int64_t B, int T,
+               int I, int Ni, int Nc, int O, void* ws, int64_t ws_bytes, cudaStream_t stream) {
+    return liquid_bwd_impl<false>(packed, x, h0, h_traj, dy, dh_traj, dh_last, dx, dh0, dpacked, B, T, I, Ni, Nc, O, ws, ws_bytes, stream);
+}
+// standalone cell: dy [B, Nc] (gradient on y = proj + h'), dh_new [B, Nc] or NULL (gradient on h') -> dx [B, In], dh [B, Nc], dpacked
+int cell_bwd(const float* packed, const float* x, const float* h, const float* dy, const float* dh_new, float* dx, float* dh,
+             float* dpacked, int64_t B, int In, int Nc, void* ws, int64_t ws_bytes, cudaStream_t stream) {
+    return liquid_bwd_impl<true>(packed, x, h, nullptr, dy, dh_new, nullptr, dx, dh, dpacked, B, 1, In, In, Nc, Nc, ws, ws_bytes, stream);
 }
 
 int ncp_fwd(const float* packed, const float* x, float* y, int64_t B, int I, int Ni, int Nc, int O, cudaStream_t stream) {

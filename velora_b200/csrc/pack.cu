@@ -39,10 +39,10 @@ __global__ void liquid_pack_kernel(LiquidSrc s, LiquidLayout L, float* __restric
         float v = 0.f;
         if (idx < L.b_in) {                       // win_t [I][NIp]
             int i = idx / L.NIp, j = idx % L.NIp;
-            if (j < L.Ni) v = s.w_in[j * L.I + i] * mask_rc(s.m_in, s.t_in, j, i, L.Ni, L.I);
+            if (j < L.Ni && s.w_in) v = s.w_in[j * L.I + i] * mask_rc(s.m_in, s.t_in, j, i, L.Ni, L.I);
         } else if (idx < L.wh_t) {                // b_in
             int j = idx - L.b_in;
-            if (j < L.Ni) v = s.b_in[j];
+            if (j < L.Ni && s.b_in) v = s.b_in[j];
         } else if (idx < L.b_h) {                 // wh_t [K][4][NCp]
             int e = idx - L.wh_t;
             int i = e / L.H4, r = e % L.H4;
@@ -55,14 +55,14 @@ __global__ void liquid_pack_kernel(LiquidSrc s, LiquidLayout L, float* __restric
         } else if (idx < L.b_out) {               // wout [O][NCp]
             int e = idx - L.wout;
             int o = e / L.NCp, j = e % L.NCp;
-            if (j < L.Nc) v = s.w_out[o * L.Nc + j] * mask_rc(s.m_out, s.t_out, o, j, L.O, L.Nc);
+            if (j < L.Nc && s.w_out) v = s.w_out[o * L.Nc + j] * mask_rc(s.m_out, s.t_out, o, j, L.O, L.Nc);
         } else if (idx < L.f_total) {             // b_out
             int o = idx - L.b_out;
-            if (o < L.O) v = s.b_out[o];
+            if (o < L.O && s.b_out) v = s.b_out[o];
         } else if (idx < L.wh) {                  // win [Ni][Ip]
             int e = idx - L.win;
             int j = e / L.Ip, i = e % L.Ip;
-            if (i < L.I) v = s.w_in[j * L.I + i] * mask_rc(s.m_in, s.t_in, j, i, L.Ni, L.I);
+            if (i < L.I && s.w_in) v = s.w_in[j * L.I + i] * mask_rc(s.m_in, s.t_in, j, i, L.Ni, L.I);
         } else if (idx < L.wout_t) {              // wh [4*NCp][Kp]
             int e = idx - L.wh;
             int r = e / L.Kp, i = e % L.Kp;
@@ -71,7 +71,7 @@ __global__ void liquid_pack_kernel(LiquidSrc s, LiquidLayout L, float* __restric
         } else {                                  // wout_t [Nc][Op]
             int e = idx - L.wout_t;
             int j = e / L.Op, o = e % L.Op;
-            if (o < L.O) v = s.w_out[o * L.Nc + j] * mask_rc(s.m_out, s.t_out, o, j, L.O, L.Nc);
+            if (o < L.O && s.w_out) v = s.w_out[o * L.Nc + j] * mask_rc(s.m_out, s.t_out, o, j, L.O, L.Nc);
         }
         packed[idx] = v;
     }
@@ -96,7 +96,7 @@ __global__ void liquid_unpack_kernel(const float* __restrict__ dp, LiquidGradDst
         int e = idx;
         if (e < n_in) {
             int j = e / L.I, i = e % L.I;
-            put(d.g_w_in, e, dp[L.win_t + i * L.NIp + j] * mask_rc(d.m_in, d.t_in, j, i, L.Ni, L.I), acc);
+            if (d.g_w_in) put(d.g_w_in, e, dp[L.win_t + i * L.NIp + j] * mask_rc(d.m_in, d.t_in, j, i, L.Ni, L.I), acc);
             continue;
         }
         e -= n_in;
@@ -118,7 +118,7 @@ __global__ void liquid_unpack_kernel(const float* __restrict__ dp, LiquidGradDst
         e -= 5 * (n_h + L.Nc);
         if (e < n_out) {
             int o = e / L.Nc, j = e % L.Nc;
-            put(d.g_w_out, e, dp[L.wout + o * L.NCp + j] * mask_rc(d.m_out, d.t_out, o, j, L.O, L.Nc), acc);
+            if (d.g_w_out) put(d.g_w_out, e, dp[L.wout + o * L.NCp + j] * mask_rc(d.m_out, d.t_out, o, j, L.O, L.Nc), acc);
             continue;
         }
         e -= n_out;
@@ -228,7 +228,8 @@ extern "C" int vb_liquid_pack(const float* w_in, const float* b_in, const void* 
                               const float* w_out, const float* b_out, const void* m_out, int m_out_type,
                               int I, int Ni, int Nc, int O, float* packed, void* stream) {
     VB_CHECK_ARG(dims_ok(I, Ni, Nc, O), VB_ERR_BAD_DIMS, "vb_liquid_pack: bad dims I=%d Ni=%d Nc=%d O=%d", I, Ni, Nc, O);
-    VB_CHECK_ARG(w_in && b_in && m_in && w_heads && b_heads && m_heads && w_out && b_out && m_out && packed,
+    // the inter and / or motor layer may be absent (all three of its pointers NULL): a standalone NCPLiquidCell packs its five heads only
+    VB_CHECK_ARG(w_heads && b_heads && m_heads && packed && (w_in ? (b_in && m_in) : (!b_in && !m_in)) && (w_out ? (b_out && m_out) : (!b_out && !m_out)),
                  VB_ERR_NULL_POINTER, "vb_liquid_pack: null pointer");
     LiquidSrc s;
     s.w_in = w_in; s.b_in = b_in; s.m_in = m_in;
@@ -250,7 +251,7 @@ extern "C" int vb_liquid_unpack_grads(const float* dpacked, const void* m_in, in
                                       float* g_w_out, float* g_b_out,
                                       int I, int Ni, int Nc, int O, int accumulate, void* stream) {
     VB_CHECK_ARG(dims_ok(I, Ni, Nc, O), VB_ERR_BAD_DIMS, "vb_liquid_unpack_grads: bad dims");
-    VB_CHECK_ARG(dpacked && m_in && m_heads && m_out && g_w_heads && g_b_heads, VB_ERR_NULL_POINTER,
+    VB_CHECK_ARG(dpacked && m_heads && g_w_heads && g_b_heads && (m_in || !g_w_in) && (m_out || !g_w_out), VB_ERR_NULL_POINTER,
                  "vb_liquid_unpack_grads: null pointer");
     LiquidGradDst d;
     d.g_w_in = g_w_in; d.g_b_in = g_b_in; d.m_in = m_in;

@@ -219,6 +219,84 @@ class LiquidSeqFn(torch.autograd.Function):
         return (dx, dh0, None, None, None, *grads)
 
 
+class CellFn(torch.autograd.Function):
+    """y[B,Nc], h_new[B,Nc] = NCPLiquidCell(x[B,In], h[B,Nc]; five masked heads) - one kernel forward, one backward (cell.py:147-169)."""
+
+    @staticmethod
+    def forward(ctx, x, h, dims, masks, *params):
+        # params: (w, b) x5 in head order g, h, f->g, f->h, proj; masks: the five head masks (the cell's sparsity mask, not differentiable)
+        In, Nc = dims
+        L = _lib.lib()
+        _lib.require_cuda(x, "NCPLiquidCell.forward")
+        dev = x.device
+        x, h = _f32c(x), _f32c(h)
+        B = x.shape[0]
+        params = [_f32c(p.detach()) for p in params]
+        w_h = [params[2 * k] for k in range(5)]
+        b_h = [params[2 * k + 1] for k in range(5)]
+        masks = tuple(_lib.mask_arg(m, dev) for m in masks)
+        heads_type = _lib.common_mask_type(masks)
+        if heads_type is None:
+            masks = tuple(m.contiguous() for m in masks)
+            heads_type = _lib.mask_type(masks[0])
+        with torch.cuda.device(dev):
+            st = _lib.stream_ptr(dev)
+            packed = torch.empty(L.vb_liquid_packed_floats(In, In, Nc, Nc), dtype=torch.float32, device=dev)
+            _count(1)
+            _lib.check(
+                L.vb_liquid_pack(None, None, None, 0, _lib.ptr_array(w_h), _lib.ptr_array(b_h), _lib.ptr_array(list(masks)), heads_type,
+                                 None, None, None, 0, In, In, Nc, Nc, _lib.ptr(packed), st),
+                "vb_liquid_pack",
+            )
+            y = torch.empty((B, Nc), dtype=torch.float32, device=dev)
+            h_new = torch.empty((B, Nc), dtype=torch.float32, device=dev)
+            with _timed("cell_fwd", 1):
+                _lib.check(L.vb_cell_fwd(_lib.ptr(packed), _lib.ptr(x), _lib.ptr(h), _lib.ptr(y), _lib.ptr(h_new), B, In, Nc, st),
+                           "vb_cell_fwd")
+        ctx.dims, ctx.masks, ctx.heads_type = dims, masks, heads_type
+        ctx.save_for_backward(x, h, packed)
+        ctx.set_materialize_grads(False)
+        return y, h_new
+
+    @staticmethod
+    def backward(ctx, dy, dh_new):
+        x, h, packed = ctx.saved_tensors
+        In, Nc = ctx.dims
+        L = _lib.lib()
+        dev = x.device
+        B = x.shape[0]
+        dy = _f32c(dy) if dy is not None else torch.zeros((B, Nc), dtype=torch.float32, device=dev)
+        dh_new = _f32c(dh_new)
+        with torch.cuda.device(dev):
+            st = _lib.stream_ptr(dev)
+            dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+            dh = torch.empty_like(h) if ctx.needs_input_grad[1] else None
+            dpacked = torch.empty(L.vb_liquid_grad_floats(In, In, Nc, Nc), dtype=torch.float32, device=dev)
+            ws = _workspace(dev, L.vb_cell_bwd_workspace_bytes(In, Nc))
+            with _timed("cell_bwd", 2):
+                _lib.check(
+                    L.vb_cell_bwd(_lib.ptr(packed), _lib.ptr(x), _lib.ptr(h), _lib.ptr(dy), _lib.ptr(dh_new), _lib.ptr(dx), _lib.ptr(dh),
+                                  _lib.ptr(dpacked), B, In, Nc, _lib.ptr(ws), ws.numel(), st),
+                    "vb_cell_bwd",
+                )
+            _dp.maybe_allreduce(dpacked)
+            need = ctx.needs_input_grad[4:]
+            shapes = [(Nc, In + Nc), (Nc,)] * 5
+            grads: List[Optional[torch.Tensor]] = [
+                torch.empty(s, dtype=torch.float32, device=dev) if need[k] else None for k, s in enumerate(shapes)
+            ]
+            _count(1)
+            _lib.check(
+                L.vb_liquid_unpack_grads(
+                    _lib.ptr(dpacked), None, 0, _lib.ptr_array(list(ctx.masks)), ctx.heads_type, None, 0,
+                    None, None, _lib.ptr_array([grads[2 * k] for k in range(5)]), _lib.ptr_array([grads[2 * k + 1] for k in range(5)]),
+                    None, None, In, In, Nc, Nc, 0, st,
+                ),
+                "vb_liquid_unpack_grads",
+            )
+        return (dx, dh, None, None, *grads)
+
+
 class NcpFn(torch.autograd.Function):
     """y[B,O] = ncp(x[B,I]; three masked layers)."""
 

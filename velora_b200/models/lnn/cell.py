@@ -2,15 +2,16 @@
 
 Mirror of velora/models/lnn/cell.py:10-169: five SparseLinear heads (g, h, f->g, f->h, proj) over cat([x, h]);
     gate = sigmoid(f_g + f_h);  h' = tanh(g) (1 - gate) + gate tanh(h);  y = proj + h'.
-Inside LiquidNCPNetwork the heads are parameter containers for the fused kernels; called on its own the cell
-evaluates the same formula with framework ops.
+Inside LiquidNCPNetwork the heads are parameter containers for the fused network kernels; called on its own the cell runs
+one fused kernel forward and one backward (vb_cell_fwd / vb_cell_bwd through functional.CellFn).  There is no CPU path.
 """
 
-from typing import Tuple
+from typing import List, Tuple
 
 import torch
 import torch.nn as nn
 
+from velora_b200 import functional as VF
 from velora_b200.models.lnn.sparse import SparseLinear
 from velora_b200.models.weight import WeightInitType
 
@@ -55,17 +56,26 @@ class NCPLiquidCell(nn.Module):
         recurrent = torch.ones((n_hidden, n_hidden), device=self.device)
         return torch.abs(torch.concatenate([mask.detach(), recurrent]).T).to(self.device)
 
-    def _new_hidden(self, x: torch.Tensor, g_out: torch.Tensor, h_out: torch.Tensor) -> torch.Tensor:
-        g = self.tanh(g_out)
-        h = self.tanh(h_out)
-        gate = self.sigmoid(self.f_head_to_g(x) + self.f_head_to_h(x))
-        return g * (1.0 - gate) + gate * h
-
     def update_mask(self, mask: torch.Tensor) -> None:
         self.sparsity_mask = self._prep_mask(mask.to(self.device))
 
+    @torch.jit.ignore
+    def _fused(self, x: torch.Tensor, hidden: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        heads = [self.g_head, self.h_head, self.f_head_to_g, self.f_head_to_h, self.proj]
+        dev = self.g_head.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError(
+                "velora_b200.NCPLiquidCell has no CPU path: build it with device=torch.device('cuda') "
+                f"(parameters are on '{dev}')"
+            )
+        x = x.to(dtype=torch.float32, device=dev)
+        hidden = hidden.to(dtype=torch.float32, device=dev)
+        params: List[torch.Tensor] = []
+        for h in heads:
+            params += [h.weight, h.bias]
+        # masks come from each head's own buffer, as in LiquidNCPNetwork._fused_seq
+        return VF.CellFn.apply(x, hidden, (self.in_features, self.n_hidden), tuple(h.mask for h in heads), *params)
+
     def forward(self, x: torch.Tensor, hidden: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-        x, hidden = x.to(self.device), hidden.to(self.device)
-        z = torch.cat([x, hidden], dim=1)
-        new_hidden = self._new_hidden(z, self.g_head(z), self.h_head(z))
-        return self.proj(z) + new_hidden, new_hidden
+        """(x [B, in], h [B, n_hidden]) -> (y [B, n_hidden], h' [B, n_hidden])   (cell.py:147-169)"""
+        return self._fused(x, hidden)
