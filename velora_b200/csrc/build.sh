@@ -7,6 +7,8 @@ mkdir -p "$OUT"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr -Xptxas -v"
 # VB_TRACE_BUILD=1 compiles the clock64 phase instrumentation of the tcgen05 backward kernel in (profiles/microbench/trace_run.py)
+# VB_EXTRA_FLAGS: experiment switches (e.g. -DVB_FWD_PIPELINED=0) for a side build under VB_OUT
+FLAGS="$FLAGS $VB_EXTRA_FLAGS"
 if [ -n "$VB_TRACE_BUILD" ]; then FLAGS="$FLAGS -DVB_ENABLE_TRACE"; touch liquid_tc.cu; fi
 SRCS="api.cu pack.cu liquid_small.cu liquid_tc.cu generic.cu gather.cu optim.cu ncp_tc.cu liquid_big.cu liquid_big_bwd.cu collective.cu sac_loss.cu"
 OBJS=""

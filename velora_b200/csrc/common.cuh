@@ -241,6 +241,57 @@ __device__ __forceinline__ void mish2_grad(float x0, float x1, float& y0, float&
 }
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// ---- packed fp32 pairs (sm_100: FFMA2 / FMUL2 / FADD2).  One packed instruction does two IEEE fp32 operations in ONE issue slot (the FMA
+// pipe is busy two cycles, so the flop rate is unchanged: profiles/microbench/ffma2.cu measures 127 scalar FMA / clk / SM either way) - the
+// lever for kernels bound by instruction issue rather than by a pipe.  A pair lives in an aligned 64-bit register; pk / lo / hi are
+// register renames, not instructions.  MUFU and min / max stay scalar.
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 pk(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ float lo(f2 a) { float l; asm("{\n\t.reg .b32 t;\n\tmov.b64 {%0, t}, %1;\n\t}" : "=f"(l) : "l"(a)); return l; }
+__device__ __forceinline__ float hi(f2 a) { float h; asm("{\n\t.reg .b32 t;\n\tmov.b64 {t, %0}, %1;\n\t}" : "=f"(h) : "l"(a)); return h; }
+__device__ __forceinline__ f2 bc2(float c) { return pk(c, c); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) { f2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+// 2^min(x, clamp) of both halves (the clamp keeps a NaN)
+__device__ __forceinline__ f2 ex2_min2(f2 x, float clamp) { return pk(ex2_approx(min_keep_nan(lo(x), clamp)), ex2_approx(min_keep_nan(hi(x), clamp))); }
+__device__ __forceinline__ f2 rcp2(f2 x) { return pk(rcp_approx(lo(x)), rcp_approx(hi(x))); }
+
+// tanh(sg), tanh(sh), sigmoid(sf) of two neurons at once: tanh2_sigmoid() above in packed form (per neuron ONE reciprocal serves all three)
+__device__ __forceinline__ void tanh2_sigmoid_p(f2 sg, f2 sh, f2 sf, f2& tg, f2& th, f2& gate) {
+    const f2 one = bc2(1.0f);
+    f2 a = add2(ex2_min2(mul2(sg, bc2(2.0f * kLog2e)), 9.0f * 2.0f * kLog2e), one);
+    f2 b = add2(ex2_min2(mul2(sh, bc2(2.0f * kLog2e)), 9.0f * 2.0f * kLog2e), one);
+    f2 c = add2(ex2_min2(mul2(sf, bc2(-kLog2e)), 30.0f * kLog2e), one);
+    f2 ab = mul2(a, b);
+    f2 r = rcp2(mul2(ab, c));
+    f2 rab = mul2(c, r);
+    gate = mul2(ab, r);
+    tg = fma2(mul2(b, bc2(-2.0f)), rab, one);
+    th = fma2(mul2(a, bc2(-2.0f)), rab, one);
+}
+// Mish of four values held as two pairs: 1 / d_i from the two reciprocals of the cross products d_A d_B (no lane swap needed)
+__device__ __forceinline__ void mish4_p(f2 xa, f2 xb, f2& ya, f2& yb) {
+    const f2 two = bc2(2.0f);
+    f2 na = ex2_min2(mul2(xa, bc2(kLog2e)), 9.0f * kLog2e), nb = ex2_min2(mul2(xb, bc2(kLog2e)), 9.0f * kLog2e);
+    f2 wa = mul2(na, add2(na, two)), wb = mul2(nb, add2(nb, two));
+    f2 da = add2(wa, two), db = add2(wb, two);
+    f2 rr = rcp2(mul2(da, db));
+    ya = mul2(xa, mul2(wa, mul2(db, rr)));
+    yb = mul2(xb, mul2(wb, mul2(da, rr)));
+}
+// Mish and Mish' of a pair (mish_fwd_grad above in packed form; one reciprocal per value)
+__device__ __forceinline__ void mish_grad_p(f2 x, f2& y, f2& g) {
+    f2 n = ex2_min2(mul2(x, bc2(kLog2e)), 20.0f * kLog2e);
+    f2 w = mul2(n, add2(n, bc2(2.0f)));
+    f2 r = rcp2(add2(w, bc2(2.0f)));
+    f2 t = mul2(w, r);
+    f2 p = mul2(fma2(n, n, n), r);
+    g = fma2(mul2(x, bc2(4.0f)), mul2(p, r), t);
+    y = mul2(x, t);
+}
 #endif  // __CUDACC__
 
 }  // namespace vb

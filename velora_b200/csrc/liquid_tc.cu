@@ -75,15 +75,10 @@ struct Cfg {
     static constexpr int S_WIN = S_OUT + S_OUT_N, S_WIN_N = NI * Ip;          // win [NI][Ip]
     static constexpr int S_TOTAL = S_WIN + S_WIN_N;
     // saved forward factors: one float4 (A, Bc, Cc, mish'(c)) per command neuron + m in NC / 4 float4
-#ifndef VB_SAVE_RAW
-#define VB_SAVE_RAW 0
-#endif
-    // VB_SAVE_RAW = 0 (default): the forward saves the finished gate factors and m (160 B per sample-step).  = 1: it saves
-    // (tanh s_g, tanh s_h, gate, c) - 128 B - and the backward's role B forms the factors and mish(c) / mish'(c) itself.  Measured on
-    // config 3 (profiles/r02/README.md): forward 0.104 -> 0.094 ms but backward 0.203 -> 0.226 ms - role B's extra ~100 instructions
-    // sit on the step's dependency chain - so the work stays in the forward.
-    static constexpr bool SAVE_RAW = VB_SAVE_RAW != 0;
-    static constexpr int NQ = SAVE_RAW ? NC : NC + NC / 4;
+    // saved forward factors per sample-step: per pair of command neurons (2c, 2c + 1) the float4s (A0, A1, Bc0, Bc1) and (Cc0, Cc1, G0, G1)
+    // [G = mish'(c)], then m = mish(c) in NC / 4 float4s.  (Saving the raw tanh / gate values instead - 128 B - and forming the factors in the
+    // backward was measured in round 2: forward 0.104 -> 0.094 ms but backward 0.203 -> 0.226 ms, profiles/r02/README.md.)
+    static constexpr int NQ = NC + NC / 4;
     static constexpr int N_SMALL = I * NI + O * NC + NI + O;                  // dW_in, dW_out, db_in, db_out entries
 };
 
@@ -178,24 +173,41 @@ __device__ __forceinline__ void inter_layer(const float* sw, const float (&x)[C:
             u[4 * q + 3] = fmaf(x[i], w.w, u[4 * q + 3]);
         }
 }
+// the same on packed pairs: u2[k] = (u[2k], u[2k + 1]); one LDS.128 brings two weight pairs, one FFMA2 does two neurons
+template <class C>
+__device__ __forceinline__ void inter_layer_p(const float* sw, const float (&x)[C::I], f2 (&u)[C::NI / 2]) {
+    const ulonglong2* w2 = reinterpret_cast<const ulonglong2*>(sw + C::S_IN);
+#pragma unroll
+    for (int q = 0; q < C::NI / 4; ++q) {
+        const ulonglong2 b = w2[C::I * (C::NIp / 4) + q];
+        u[2 * q] = b.x; u[2 * q + 1] = b.y;
+    }
+#pragma unroll
+    for (int i = 0; i < C::I; ++i) {
+        const f2 xx = bc2(x[i]);
+#pragma unroll
+        for (int q = 0; q < C::NI / 4; ++q) {
+            const ulonglong2 w = w2[i * (C::NIp / 4) + q];
+            u[2 * q] = fma2(xx, w.x, u[2 * q]);
+            u[2 * q + 1] = fma2(xx, w.y, u[2 * q + 1]);
+        }
+    }
+}
 
 // z~ = [a (NI), h (NC), 1, 0..] -> chunks 0..2 of the three part planes (forward: one thread owns the whole row)
 template <class C>
-__device__ __forceinline__ void store_z(unsigned char* zP, int row, const float (&a)[C::NI], const float (&h)[C::NC]) {
-    float zt[24];
-#pragma unroll
-    for (int i = 0; i < 24; ++i) zt[i] = 0.f;
-#pragma unroll
-    for (int j = 0; j < C::NI; ++j) zt[j] = a[j];
-#pragma unroll
-    for (int j = 0; j < C::NC; ++j) zt[C::NI + j] = h[j];
-    zt[C::ONE] = 1.0f;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        float f[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] = zt[8 * c + e];
-        store_chunk3<3>(zP, c, row, f);
+__device__ __forceinline__ void store_z_p(unsigned char* zP, int row, const f2 (&a)[C::NI / 2], const f2 (&h)[C::NC / 2]) {
+    static_assert(C::NI == 12 && C::NC == 8, "chunk 0 = a[0..8), chunk 1 = a[8..12) | h[0..4), chunk 2 = h[4..8) | 1 | 0");
+    store_chunk3_p<3>(zP, 0, row, a[0], a[1], a[2], a[3]);
+    store_chunk3_p<3>(zP, 1, row, a[4], a[5], h[0], h[1]);
+    {   // chunk 2: the parts of the constant tail (1, 0, 0, 0) are known: bf16(1) = 0x3f80, residuals 0
+        uint2 pa, pb, pc;
+        split3_p(h[2], pa.x, pb.x, pc.x);
+        split3_p(h[3], pa.y, pb.y, pc.y);
+        uint4* p = reinterpret_cast<uint4*>(zP);
+        p[(0 * 3 + 2) * TM + row] = make_uint4(pa.x, pa.y, 0x00003f80u, 0u);
+        p[(1 * 3 + 2) * TM + row] = make_uint4(pb.x, pb.y, 0u, 0u);
+        p[(2 * 3 + 2) * TM + row] = make_uint4(pc.x, pc.y, 0u, 0u);
     }
 }
 
@@ -210,6 +222,27 @@ __device__ __forceinline__ void store_half_chunk3(unsigned char* planes, int chu
     p[((1 * CPP + chunk) * TM + row) * 2 + half] = b;
     p[((2 * CPP + chunk) * TM + row) * 2 + half] = c;
 }
+
+// Experiment switches of the forward kernel (side builds: VB_OUT=../lib_exp VB_EXTRA_FLAGS="-DVB_FWD_PIPELINED=1" build.sh; measured on
+// config 3, same box, profiles/r02/README.md):
+//   VB_FWD_PIPELINED = 1: the inter layer of step t + 1 is computed in the shadow of step t's MMAs.  One CTA per SM: 2700 -> 2330 cycles
+//     per step (B <= 19k: 5-8 % faster); four CTAs per SM (the benchmarked size): 0.099 -> 0.105 ms, so it stays off.
+//   VB_FWD_LD24 = 0: three separate 8-column TMEM loads per chunk, each with its own wait, instead of three in flight: no difference.
+#ifndef VB_FWD_PIPELINED
+#define VB_FWD_PIPELINED 0
+#endif
+constexpr bool kFwdPipelined = VB_FWD_PIPELINED != 0;
+#ifndef VB_FWD_LD24
+#define VB_FWD_LD24 1
+#endif
+
+
+// clock64 phase trace of the forward kernel (VB_TRACE_BUILD=1 build.sh; profiles/microbench/trace_fwd.py)
+#ifdef VB_ENABLE_TRACE
+#define VB_TR(k) do { if (tr_on) tr[tr_n][k] = clock64(); } while (0)
+#else
+#define VB_TR(k) do { } while (0)
+#endif
 
 // ================================================================================================ forward
 template <class C>
@@ -254,11 +287,11 @@ __global__ void __launch_bounds__(TM) liquid_fwd_tc_kernel(const float* __restri
     constexpr bool vx = VEC, vy = VEC, vh = VEC;
     const RowMap<LAY> rx(vec_flags & LAY_X, B, T), ry(vec_flags & LAY_Y, B, T), rh(vec_flags & LAY_H, B, T);
 
-    // stacked heads operand (see issue_heads_stacked); head outputs in NEURON-MAJOR order n' = 4 j + hs, so that one 8-column
-    // chunk holds two complete neurons
+    // stacked heads operand (see issue_heads_stacked); head outputs in PAIR order n' = 8 (j / 2) + 2 hs + j % 2: one 8-column chunk holds
+    // two complete neurons and adjacent columns hold the same head of both, i.e. the packed pairs of the epilogue
     if (warp < 3) {
         const int n = lane, c = warp;     // features 8c .. 8c+7 of output n'
-        const int col = (n & 3) * C::NCp + (n >> 2);
+        const int col = ((n & 7) >> 1) * C::NCp + 2 * (n >> 3) + (n & 1);
         float v[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -301,109 +334,167 @@ __global__ void __launch_bounds__(TM) liquid_fwd_tc_kernel(const float* __restri
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t b = tile * TM + tid;
         const bool valid = b < B;
-        float h[C::NC];
+        f2 h2[C::NC / 2];          // hidden state as packed pairs (h[2k], h[2k + 1])
+        {
+            float h[C::NC];
 #pragma unroll
-        for (int j = 0; j < C::NC; ++j) h[j] = 0.f;
-        if (valid && h0) ldg_row<C::NC>(h, h0 + b * C::NC, vh);
+            for (int j = 0; j < C::NC; ++j) h[j] = 0.f;
+            if (valid && h0) ldg_row<C::NC>(h, h0 + b * C::NC, vh);
+#pragma unroll
+            for (int k = 0; k < C::NC / 2; ++k) h2[k] = pk(h[2 * k], h[2 * k + 1]);
+        }
+        // a2 = mish(W_in x_t + b_in); xn = the next input row, prefetched (with kFwdPipelined a2 is carried from the previous step)
+        f2 a2[C::NI / 2];
         float xn[C::I];
 #pragma unroll
         for (int i = 0; i < C::I; ++i) xn[i] = 0.f;
-        if (valid) ldg_row<C::I>(xn, x + rx(b, 0) * C::I, vx);
+        if constexpr (kFwdPipelined) {
+            float x0[C::I];
+#pragma unroll
+            for (int i = 0; i < C::I; ++i) x0[i] = 0.f;
+            if (valid) ldg_row<C::I>(x0, x + rx(b, 0) * C::I, vx);
+            if (valid && T > 1) ldg_row<C::I>(xn, x + rx(b, 1) * C::I, vx);
+            f2 u[C::NI / 2];
+            inter_layer_p<C>(sw, x0, u);
+#pragma unroll
+            for (int k = 0; k < C::NI / 2; k += 2) mish4_p(u[k], u[k + 1], a2[k], a2[k + 1]);
+        } else {
+            if (valid) ldg_row<C::I>(xn, x + rx(b, 0) * C::I, vx);
+        }
+#ifdef VB_ENABLE_TRACE
+        long long tr[3][8];
+        int tr_n = 0;
+        const bool tr_lane = lane == 0 && (blockIdx.x == 0 || blockIdx.x == 300) && (warp == 0 || warp == 2);
+#endif
+        // The element-wise work runs on packed fp32 pairs (FFMA2 / FMUL2 / FADD2: two neurons per issue slot): 963 -> 698 instructions per
+        // thread-step, 0.104 -> 0.099 ms on config 3 (profiles/r02/README.md).
         for (int t = 0; t < T; ++t) {
-            float xr[C::I];
+#ifdef VB_ENABLE_TRACE
+            const bool tr_on = tr_lane && t >= 16 && t < 19;
+            if (tr_on) tr_n = t - 16;
+#endif
+            VB_TR(0);
+            if constexpr (!kFwdPipelined) {
+                {
+                    float xr[C::I];
 #pragma unroll
-            for (int i = 0; i < C::I; ++i) xr[i] = xn[i];
-            if (valid && t + 1 < T) ldg_row<C::I>(xn, x + rx(b, t + 1) * C::I, vx);   // prefetch the next step's input
-            float a[C::NI];
-            {
-                float u[C::NI];
-                inter_layer<C>(sw, xr, u);
+                    for (int i = 0; i < C::I; ++i) xr[i] = xn[i];
+                    if (valid && t + 1 < T) ldg_row<C::I>(xn, x + rx(b, t + 1) * C::I, vx);
+                    f2 u[C::NI / 2];
+                    inter_layer_p<C>(sw, xr, u);
 #pragma unroll
-                for (int j = 0; j < C::NI; j += 4) {
-                    float u4[4] = {u[j], u[j + 1], u[j + 2], u[j + 3]}, a4[4];
-                    mish4(u4, a4);
-                    a[j] = a4[0]; a[j + 1] = a4[1]; a[j + 2] = a4[2]; a[j + 3] = a4[3];
+                    for (int k = 0; k < C::NI / 2; k += 2) mish4_p(u[k], u[k + 1], a2[k], a2[k + 1]);
                 }
             }
-            store_z<C>(zP, tid, a, h);
+            store_z_p<C>(zP, tid, a2, h2);
             fence_async_smem();
             tc_fence_before();
+            VB_TR(1);
             __syncthreads();
             if (tid == 0) {
                 tc_fence_after();
+                VB_TR(3);
                 issue_heads_stacked(tmem, z_addr, w_addr);
                 mma_commit(bar1);
             }
+            VB_TR(2);
+            // in the shadow of the MMAs: the inter layer of the NEXT step (it does not depend on this step's heads)
+            if (kFwdPipelined && t + 1 < T) {
+                float xr[C::I];
+#pragma unroll
+                for (int i = 0; i < C::I; ++i) xr[i] = xn[i];
+                if (valid && t + 2 < T) ldg_row<C::I>(xn, x + rx(b, t + 2) * C::I, vx);   // prefetch one more step ahead
+                f2 u[C::NI / 2];
+                inter_layer_p<C>(sw, xr, u);
+#pragma unroll
+                for (int k = 0; k < C::NI / 2; k += 2) mish4_p(u[k], u[k + 1], a2[k], a2[k + 1]);
+            }
+            VB_TR(4);
             mbar_wait(bar1, ph1);
             ph1 ^= 1;
+            VB_TR(5);
             tc_fence_after();
-            float m[C::NC];
-            float4* sv = SAVE ? saved + ((int64_t)t * n_tiles + tile) * (C::NQ * TM) + tid : nullptr;
+            f2 m2[C::NC / 2];
+            ulonglong2* sv = SAVE ? reinterpret_cast<ulonglong2*>(saved + ((int64_t)t * n_tiles + tile) * (C::NQ * TM) + tid) : nullptr;
+            const f2 one = bc2(1.0f);
 #pragma unroll
             for (int c = 0; c < C::NC / 2; ++c) {
-                float s8[8];
+                // 24 columns = one 8-column chunk x (W_hi, W_mid, W_lo): column 24 c + 8 g + 2 hs + jj is z W_g of head hs, neuron 2c + jj
+                f2 s4[4];
                 {
-                    float hi[8], mid[8], lo[8];
-                    tmem_ld8(taddr + 24 * c, hi);
-                    tmem_ld8(taddr + 24 * c + 8, mid);
-                    tmem_ld8(taddr + 24 * c + 16, lo);
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) s8[e] = (lo[e] + mid[e]) + hi[e];
-                }
-                float cc[2], fa[2], fb[2], fc[2];
-#pragma unroll
-                for (int jj = 0; jj < 2; ++jj) {
-                    float tg, th, gate;
-                    tanh2_sigmoid(s8[4 * jj + 0], s8[4 * jj + 1], s8[4 * jj + 2], tg, th, gate);
-                    const float d = th - tg;
-                    float hn = fmaf(gate, d, tg);
-                    h[2 * c + jj] = hn;
-                    cc[jj] = s8[4 * jj + 3] + hn;
-                    if (SAVE && C::SAVE_RAW) {
-                        fa[jj] = tg; fb[jj] = th; fc[jj] = gate;
-                    } else if (SAVE) {
-                        const float omg = 1.0f - gate;
-                        fa[jj] = omg * fmaf(-tg, tg, 1.0f);
-                        fb[jj] = gate * fmaf(-th, th, 1.0f);
-                        fc[jj] = d * gate * omg;
+                    f2 v[12];
+#if VB_FWD_LD24
+                    tmem_ld24_p(taddr + 24 * c, v);
+#else
+                    {
+                        f2 q[4];
+                        tmem_ld8_p(taddr + 24 * c, q);
+                        v[0] = q[0]; v[1] = q[1]; v[2] = q[2]; v[3] = q[3];
+                        tmem_ld8_p(taddr + 24 * c + 8, q);
+                        v[4] = q[0]; v[5] = q[1]; v[6] = q[2]; v[7] = q[3];
+                        tmem_ld8_p(taddr + 24 * c + 16, q);
+                        v[8] = q[0]; v[9] = q[1]; v[10] = q[2]; v[11] = q[3];
                     }
-                }
-                if (SAVE && C::SAVE_RAW) {
-                    mish2(cc[0], cc[1], m[2 * c], m[2 * c + 1]);
-                    sv[(2 * c) * TM] = make_float4(fa[0], fb[0], fc[0], cc[0]);
-                    sv[(2 * c + 1) * TM] = make_float4(fa[1], fb[1], fc[1], cc[1]);
-                } else if (SAVE) {
-                    float g0, g1;
-                    mish2_grad(cc[0], cc[1], m[2 * c], m[2 * c + 1], g0, g1);
-                    sv[(2 * c) * TM] = make_float4(fa[0], fb[0], fc[0], g0);
-                    sv[(2 * c + 1) * TM] = make_float4(fa[1], fb[1], fc[1], g1);
-                } else {
-                    mish2(cc[0], cc[1], m[2 * c], m[2 * c + 1]);
-                }
-            }
-            if (SAVE && !C::SAVE_RAW) {
+#endif
 #pragma unroll
-                for (int q = 0; q < C::NC / 4; ++q) sv[(C::NC + q) * TM] = make_float4(m[4 * q], m[4 * q + 1], m[4 * q + 2], m[4 * q + 3]);
+                    for (int e = 0; e < 4; ++e) s4[e] = add2(add2(v[8 + e], v[4 + e]), v[e]);
+                }
+                f2 tg, th, gate;
+                tanh2_sigmoid_p(s4[0], s4[1], s4[2], tg, th, gate);
+                const f2 d = sub2(th, tg);
+                const f2 hn = fma2(gate, d, tg);
+                h2[c] = hn;
+                const f2 cc2 = add2(s4[3], hn);
+                f2 g2;
+                mish_grad_p(cc2, m2[c], g2);
+                if (SAVE) {
+                    const f2 omg = sub2(one, gate);
+                    const f2 fa = mul2(omg, sub2(one, mul2(tg, tg)));
+                    const f2 fb = mul2(gate, sub2(one, mul2(th, th)));
+                    const f2 fc = mul2(mul2(d, gate), omg);
+                    sv[(2 * c) * TM] = make_ulonglong2(fa, fb);
+                    sv[(2 * c + 1) * TM] = make_ulonglong2(fc, g2);
+                }
             }
+            if (SAVE) {
+#pragma unroll
+                for (int q = 0; q < C::NC / 4; ++q) sv[(C::NC + q) * TM] = make_ulonglong2(m2[2 * q], m2[2 * q + 1]);
+            }
+            VB_TR(6);
             float yo[C::O];
             {
                 const float* wo = sw + C::S_OUT;
 #pragma unroll
                 for (int o = 0; o < C::O; ++o) {
-                    float acc = wo[C::O * C::NCp + o];
+                    f2 acc = pk(wo[C::O * C::NCp + o], 0.f);
 #pragma unroll
                     for (int q = 0; q < C::NC / 4; ++q) {
-                        float4 w = *reinterpret_cast<const float4*>(wo + o * C::NCp + 4 * q);
-                        acc = fmaf(m[4 * q], w.x, fmaf(m[4 * q + 1], w.y, fmaf(m[4 * q + 2], w.z, fmaf(m[4 * q + 3], w.w, acc))));
+                        const ulonglong2 w = *reinterpret_cast<const ulonglong2*>(wo + o * C::NCp + 4 * q);
+                        acc = fma2(m2[2 * q], w.x, acc);
+                        acc = fma2(m2[2 * q + 1], w.y, acc);
                     }
-                    yo[o] = acc;
+                    yo[o] = lo(acc) + hi(acc);
                 }
             }
             if (valid) {
                 if (y) stg_row<C::O>(y + ry(b, t) * C::O, yo, vy);
-                if (h_traj) stg_row<C::NC>(h_traj + rh(b, t) * C::NC, h, vh);
+                if (h_traj) {
+                    float h[C::NC];
+#pragma unroll
+                    for (int k = 0; k < C::NC / 2; ++k) { h[2 * k] = lo(h2[k]); h[2 * k + 1] = hi(h2[k]); }
+                    stg_row<C::NC>(h_traj + rh(b, t) * C::NC, h, vh);
+                }
             }
+            VB_TR(7);
         }
+#ifdef VB_ENABLE_TRACE
+        if (tr_lane && T >= 19)
+            for (int n = 0; n < 3; ++n)
+                printf("FWDTRACE cta %d warp %d step %d : top %lld | storez %lld | sync+issue %lld (issue %lld) | next-inter %lld | mmawait %lld | heads-epi %lld | motor+stores %lld | next-top %lld\n",
+                       (int)blockIdx.x, warp, 16 + n, tr[n][0] - tr[0][0], tr[n][1] - tr[n][0], tr[n][2] - tr[n][1],
+                       warp == 0 ? tr[n][2] - tr[n][3] : 0LL, tr[n][4] - tr[n][2], tr[n][5] - tr[n][4], tr[n][6] - tr[n][5], tr[n][7] - tr[n][6],
+                       n < 2 ? tr[n + 1][0] - tr[n][7] : 0LL);
+#endif
     }
     tc_fence_before();
     __syncthreads();
@@ -621,18 +712,12 @@ __global__ void __launch_bounds__(BT, (BwdSmem<C>::BYTES + 1024 > 58368 ? 3 : 4)
                     float s8[8];
                     float4 g[2];
                     float mm[2];
-                    g[0] = ldg_stream(sv + (2 * c) * TM);
-                    g[1] = ldg_stream(sv + (2 * c + 1) * TM);
-                    if constexpr (C::SAVE_RAW) {        // (tanh s_g, tanh s_h, gate, c) -> (A, Bc, Cc, mish'(c)), m = mish(c)
-                        float d0, d1;
-                        mish2_grad(g[0].w, g[1].w, mm[0], mm[1], d0, d1);
-                        const float dm[2] = {d0, d1};
-#pragma unroll
-                        for (int jj = 0; jj < 2; ++jj) {
-                            const float tg = g[jj].x, th = g[jj].y, gate = g[jj].z, omg = 1.0f - gate;
-                            g[jj] = make_float4(omg * fmaf(-tg, tg, 1.0f), gate * fmaf(-th, th, 1.0f), (th - tg) * gate * omg, dm[jj]);
-                        }
-                    } else {
+                    {   // saved per neuron pair: (A0, A1, Bc0, Bc1), (Cc0, Cc1, G0, G1)
+                        const float4 qa = ldg_stream(sv + (2 * c) * TM), qb = ldg_stream(sv + (2 * c + 1) * TM);
+                        g[0] = make_float4(qa.x, qa.z, qb.x, qb.z);
+                        g[1] = make_float4(qa.y, qa.w, qb.y, qb.w);
+                    }
+                    {
                         const float4 mq = ldg_stream(sv + (C::NC + c / 2) * TM);
                         mm[0] = (c & 1) ? mq.z : mq.x;
                         mm[1] = (c & 1) ? mq.w : mq.y;

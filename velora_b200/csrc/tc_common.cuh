@@ -71,6 +71,28 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
+// eight consecutive columns as four packed pairs (columns 2k, 2k + 1)
+__device__ __forceinline__ void tmem_ld8_p(uint32_t taddr, f2 (&v)[4]) {
+    asm volatile("{\n\t.reg .b32 r<8>;\n\t"
+                 "tcgen05.ld.sync.aligned.32x32b.x8.b32 {r0,r1,r2,r3,r4,r5,r6,r7}, [%4];\n\t"
+                 "tcgen05.wait::ld.sync.aligned;\n\t"
+                 "mov.b64 %0, {r0, r1};\n\tmov.b64 %1, {r2, r3};\n\tmov.b64 %2, {r4, r5};\n\tmov.b64 %3, {r6, r7};\n\t}"
+                 : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3]) : "r"(taddr) : "memory");
+}
+// 24 consecutive columns as 12 packed pairs: three x8 loads in flight, one wait
+__device__ __forceinline__ void tmem_ld24_p(uint32_t taddr, f2 (&v)[12]) {
+    asm volatile("{\n\t.reg .b32 r<24>;\n\t"
+                 "tcgen05.ld.sync.aligned.32x32b.x8.b32 {r0,r1,r2,r3,r4,r5,r6,r7}, [%12];\n\t"
+                 "tcgen05.ld.sync.aligned.32x32b.x8.b32 {r8,r9,r10,r11,r12,r13,r14,r15}, [%13];\n\t"
+                 "tcgen05.ld.sync.aligned.32x32b.x8.b32 {r16,r17,r18,r19,r20,r21,r22,r23}, [%14];\n\t"
+                 "tcgen05.wait::ld.sync.aligned;\n\t"
+                 "mov.b64 %0, {r0, r1};\n\tmov.b64 %1, {r2, r3};\n\tmov.b64 %2, {r4, r5};\n\tmov.b64 %3, {r6, r7};\n\t"
+                 "mov.b64 %4, {r8, r9};\n\tmov.b64 %5, {r10, r11};\n\tmov.b64 %6, {r12, r13};\n\tmov.b64 %7, {r14, r15};\n\t"
+                 "mov.b64 %8, {r16, r17};\n\tmov.b64 %9, {r18, r19};\n\tmov.b64 %10, {r20, r21};\n\tmov.b64 %11, {r22, r23};\n\t}"
+                 : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3]), "=l"(v[4]), "=l"(v[5]), "=l"(v[6]), "=l"(v[7]), "=l"(v[8]), "=l"(v[9]),
+                   "=l"(v[10]), "=l"(v[11])
+                 : "r"(taddr), "r"(taddr + 8), "r"(taddr + 16) : "memory");
+}
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
     uint32_t r[4];
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
@@ -111,6 +133,39 @@ __device__ __forceinline__ void split3(float x0, float x1, uint32_t& p1, uint32_
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p2) : "f"(r1), "f"(r0));
     float q0 = r0 - __uint_as_float(p2 << 16), q1 = r1 - __uint_as_float(p2 & 0xffff0000u);
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p3) : "f"(q1), "f"(q0));
+}
+
+// split3 of a packed pair: the two residual subtractions are one FADD2 each
+__device__ __forceinline__ void split3_p(f2 x, uint32_t& p1, uint32_t& p2, uint32_t& p3) {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p1) : "f"(hi(x)), "f"(lo(x)));
+    f2 r = sub2(x, pk(__uint_as_float(p1 << 16), __uint_as_float(p1 & 0xffff0000u)));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p2) : "f"(hi(r)), "f"(lo(r)));
+    f2 q = sub2(r, pk(__uint_as_float(p2 << 16), __uint_as_float(p2 & 0xffff0000u)));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p3) : "f"(hi(q)), "f"(lo(q)));
+}
+// four pairs (eight consecutive features) -> one 16-byte chunk in each of the three part planes
+template <int CPP>
+__device__ __forceinline__ void store_chunk3_p(unsigned char* planes, int chunk, int row, f2 f0, f2 f1, f2 f2_, f2 f3) {
+    uint4 a, b, c;
+    split3_p(f0, a.x, b.x, c.x);
+    split3_p(f1, a.y, b.y, c.y);
+    split3_p(f2_, a.z, b.z, c.z);
+    split3_p(f3, a.w, b.w, c.w);
+    uint4* p = reinterpret_cast<uint4*>(planes);
+    p[(0 * CPP + chunk) * TM + row] = a;
+    p[(1 * CPP + chunk) * TM + row] = b;
+    p[(2 * CPP + chunk) * TM + row] = c;
+}
+// two pairs (four consecutive features) -> the lower (half = 0) or upper (half = 1) 8 bytes of one chunk in each part plane
+template <int CPP>
+__device__ __forceinline__ void store_half_chunk3_p(unsigned char* planes, int chunk, int row, int half, f2 f0, f2 f1) {
+    uint2 a, b, c;
+    split3_p(f0, a.x, b.x, c.x);
+    split3_p(f1, a.y, b.y, c.y);
+    uint2* p = reinterpret_cast<uint2*>(planes);
+    p[((0 * CPP + chunk) * TM + row) * 2 + half] = a;
+    p[((1 * CPP + chunk) * TM + row) * 2 + half] = b;
+    p[((2 * CPP + chunk) * TM + row) * 2 + half] = c;
 }
 
 // eight consecutive features of this thread's sample -> one 16-byte chunk in each of the three part planes
