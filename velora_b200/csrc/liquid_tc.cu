@@ -237,7 +237,7 @@ constexpr bool kFwdPipelined = VB_FWD_PIPELINED != 0;
 #endif
 
 
-// clock64 phase trace of the forward kernel (VB_TRACE_BUILD=1 build.sh; profiles/microbench/trace_fwd.py)
+// clock64 phase traces of both kernels (VB_TRACE_BUILD=1 build.sh; profiles/microbench/trace_fwd.py, trace_bwd.py)
 #ifdef VB_ENABLE_TRACE
 #define VB_TR(k) do { if (tr_on) tr[tr_n][k] = clock64(); } while (0)
 #else
@@ -643,7 +643,17 @@ __global__ void __launch_bounds__(BT, (BwdSmem<C>::BYTES + 1024 > 58368 ? 3 : 4)
         for (int i = 0; i < C::I; ++i) xn[i] = 0.f;
         if (!roleB && valid) ldg_row<C::I>(xn, x + rx(b, T - 1) * C::I, vx);
 
+#ifdef VB_ENABLE_TRACE
+        long long tr[3][8];
+        int tr_n = 0;
+        const bool tr_lane = lane == 0 && (blockIdx.x == 0 || blockIdx.x == 300) && (warp == 0 || warp == 2 || warp == 4 || warp == 6);
+#endif
         for (int t = T - 1; t >= 0; --t) {
+#ifdef VB_ENABLE_TRACE
+            const bool tr_on = tr_lane && t <= 16 && t > 13;
+            if (tr_on) tr_n = 16 - t;
+#endif
+            VB_TR(0);
             // ------------------------------------------------------------------ phase 1: operands of this step
             // the previous dW batch has finished reading the z~ / ds planes (it was queued right behind the dz this CTA already
             // waited for and has had all of phase 2 to complete: this wait is normally free)
@@ -653,11 +663,21 @@ __global__ void __launch_bounds__(BT, (BwdSmem<C>::BYTES + 1024 > 58368 ? 3 : 4)
                 dw_in_flight = false;
             }
             if (since_flush >= kFlush) flush_dw();
+            VB_TR(1);
             if (!roleB) {
                 float xr[C::I];
 #pragma unroll
                 for (int i = 0; i < C::I; ++i) xr[i] = xn[i];
                 if (valid && t > 0) ldg_row<C::I>(xn, x + rx(b, t - 1) * C::I, vx);
+                // role A has slack before the barrier: it pulls the NEXT step's saved factors of its warp's 32 samples (NQ x 512 B, read by
+                // role B's warp wq + 4) from DRAM into L2, one 128-byte line per lane.  Role B's loads are issued chunk by chunk (its register
+                // budget keeps only one neuron pair's factors live), so each of them used to wait a full DRAM latency: 0.200 -> 0.192 ms.
+                if (t > 0) {
+                    const char* nx = reinterpret_cast<const char*>(saved + ((int64_t)(t - 1) * n_tiles + tile) * (C::NQ * TM) + wq * 32);
+#pragma unroll
+                    for (int l = lane; l < C::NQ * 4; l += 32)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + (l >> 2) * (TM * 16) + (l & 3) * 128));
+                }
                 float u[C::NI];
                 inter_layer<C>(sw, xr, u);
                 // Mish'(u) and x_t wait in this thread's TMEM lane (16 spare columns) for the dz MMA; a goes to the z~ planes
@@ -743,6 +763,7 @@ __global__ void __launch_bounds__(BT, (BwdSmem<C>::BYTES + 1024 > 58368 ? 3 : 4)
             }
             fence_async_smem();
             tc_fence_before();
+            VB_TR(2);
             __syncthreads();
             if (tid == TM) {                    // one lane of role B issues: B is idle until dz arrives
                 tc_fence_after();
@@ -768,9 +789,11 @@ __global__ void __launch_bounds__(BT, (BwdSmem<C>::BYTES + 1024 > 58368 ? 3 : 4)
             }
             since_flush += 1;
             dw_in_flight = true;
+            VB_TR(3);
             // ------------------------------------------------------------------ phase 2: consume dz
             mbar_wait(bar_dz, ph_dz);
             ph_dz ^= 1;
+            VB_TR(4);
             tc_fence_after();
             if (!roleB) {
                 float du[C::NI], xr2[C::I];
@@ -841,7 +864,15 @@ __global__ void __launch_bounds__(BT, (BwdSmem<C>::BYTES + 1024 > 58368 ? 3 : 4)
                 for (int j = 0; j < C::NC; ++j) dhc[j] = dz8[j];
                 tc_fence_before();
             }
+            VB_TR(5);
         }
+#ifdef VB_ENABLE_TRACE
+        if (tr_lane && T >= 19)
+            for (int n = 0; n < 3; ++n)
+                printf("BWDTRACE cta %d warp %d step %d : top %lld | dw-wait/flush %lld | phase1 %lld | sync(+issue) %lld | dz-wait %lld | phase2 %lld | next-top %lld\n",
+                       (int)blockIdx.x, warp, 16 - n, tr[n][0] - tr[0][0], tr[n][1] - tr[n][0], tr[n][2] - tr[n][1], tr[n][3] - tr[n][2],
+                       tr[n][4] - tr[n][3], tr[n][5] - tr[n][4], n < 2 ? tr[n + 1][0] - tr[n][5] : 0LL);
+#endif
         if (roleB && valid && dh0) stg_row<C::NC>(dh0 + b * C::NC, dhc, vh);
     }
     if (dw_in_flight) mbar_wait(bar_dw, ph_dw);
