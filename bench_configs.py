@@ -381,7 +381,7 @@ def main():
          value=B * T / (ms4 * 1e-3), ms=ms4,
          roofline={"bound": "tensor", "achieved": flops / (ms4 * 1e-3) / 1e12, "peak": pk.get("bf16_tflops_sustained", 1400.0), "unit": "TFLOP/s",
                    "frac": flops / (ms4 * 1e-3) / 1e12 / pk.get("bf16_tflops_sustained", 1400.0)},
-         note="not yet on tensor cores: the bf16 tcgen05 path for the 512-neuron class is the next kernel")
+         note="the fp32 contract of the 512-neuron class (tile kernels); its bf16 tcgen05 forward + backward is timed by bench_cfg4.py")
 
 
 if __name__ == "__main__":

@@ -186,7 +186,8 @@ int64_t vb_ncp_bwd_workspace_bytes(int I, int Ni, int Nc, int O, int64_t B);
 /* NCPNetwork.forward (ncp.py:299-328): x [B,I] -> y [B,O] */
 int vb_ncp_fwd(const float* packed, const float* x, float* y, int64_t B, int I, int Ni, int Nc, int O,
                int flags, void* stream);
-/* backward with recompute: dy [B,O] -> dx [B,I] (or NULL), dpacked (F layout, overwritten) */
+/* backward with recompute: dy [B,O] -> dx [B,I] (or NULL), dpacked (F layout, overwritten; NULL = dL/dx only: a critic evaluated inside the
+ * actor loss, agent.py:236-245, whose parameter gradients the reference computes and then discards at the next zero_grad) */
 int vb_ncp_bwd(const float* packed, const float* x, const float* dy, float* dx, float* dpacked,
                int64_t B, int I, int Ni, int Nc, int O,
                void* workspace, int64_t workspace_bytes, int flags, void* stream);

@@ -123,3 +123,31 @@ def test_ncp_empty_batch(golden):
     assert x.grad.shape == (0, 5)
     for k, p in net.named_parameters():
         assert p.grad is not None and torch.count_nonzero(p.grad) == 0, k
+
+
+def test_frozen_parameters_backward_returns_dx_only(golden):
+    """Inside functional.frozen_parameters() a critic's parameters are constants: same output, same dL/dx, no parameter gradients
+    (vb_ncp_bwd with dpacked = NULL) - the critics inside the SAC actor loss (agent.py:236-245)."""
+    import velora_b200 as vb
+    from velora_b200 import functional as VF
+    from velora_b200.models.lnn import NCPNetwork
+
+    dev = torch.device("cuda")
+    for B in (64, 5000):                 # tile kernels / tensor-core kernels
+        vb.set_seed(5)
+        net = NCPNetwork(5, 128, 1, device=dev)
+        x1 = torch.randn(B, 5, device=dev, requires_grad=True)
+        x2 = x1.detach().clone().requires_grad_(True)
+        r = torch.randn(B, device=dev)
+        y1 = net(x1)
+        (y1.reshape(-1) * r).sum().backward()
+        ref_grads = [p.grad.clone() for p in net.parameters()]
+        net.zero_grad()
+        with VF.frozen_parameters():
+            y2 = net(x2)
+        (y2.reshape(-1) * r).sum().backward()
+        assert torch.equal(y1, y2)
+        assert torch.equal(x1.grad, x2.grad)
+        assert all(p.grad is None or not p.grad.any() for p in net.parameters())
+        assert all(g.abs().sum() > 0 for g in ref_grads)
+        assert not VF.parameters_frozen()

@@ -212,9 +212,9 @@ extern "C" int vb_ncp_fwd(const float* packed, const float* x, float* y, int64_t
 extern "C" int vb_ncp_bwd(const float* packed, const float* x, const float* dy, float* dx, float* dpacked,
                           int64_t B, int I, int Ni, int Nc, int O, void* workspace, int64_t workspace_bytes, int flags, void* stream) {
     VB_CHECK_ARG(dims_ok(I, Ni, Nc, O) && B >= 0, VB_ERR_BAD_DIMS, "vb_ncp_bwd: bad dims");
-    VB_CHECK_ARG(dpacked && (B == 0 || (packed && x && dy)), VB_ERR_NULL_POINTER, "vb_ncp_bwd: null pointer");
+    VB_CHECK_ARG((dpacked || dx) && (B == 0 || (packed && x && dy)), VB_ERR_NULL_POINTER, "vb_ncp_bwd: null pointer");
     if (B == 0) {
-        VB_CUDA(cudaMemsetAsync(dpacked, 0, (size_t)NcpLayout(I, Ni, Nc, O).f_total * 4, (cudaStream_t)stream));
+        if (dpacked) VB_CUDA(cudaMemsetAsync(dpacked, 0, (size_t)NcpLayout(I, Ni, Nc, O).f_total * 4, (cudaStream_t)stream));
         return 0;
     }
     if (!(flags & (VB_FLAG_FORCE_GENERIC | VB_FLAG_FORCE_FFMA)) && B >= kNcpTcMinBatch && ncp_tc::has_path(I, Ni, Nc, O))

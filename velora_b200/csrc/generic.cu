@@ -346,13 +346,15 @@ __global__ void __launch_bounds__(kTileThreads) ncp_bwd_kernel(const float* __re
                 if (s < nvalid) dxt[(int64_t)s * L.I + i] = v;
             });
         }
-        wgrad<BM, ATOMIC>(acc + L.w1_t, L.NIp, acc + L.b1, xs, L.I, du1, L.Ni);
-        wgrad<BM, ATOMIC>(acc + L.w2_t, L.NCp, acc + L.b2, a1, L.Ni, du2, L.Nc);
-        wgrad<BM, ATOMIC>(acc + L.w3, L.NCp, nullptr, dyb, L.O, a2, L.Nc);
-        for (int o = threadIdx.x; o < L.O; o += kTileThreads) {
-            float a = 0.f;
-            for (int s = 0; s < BM; ++s) a += dyb[o * S + s];
-            acc_add<ATOMIC>(acc + L.b3 + o, a);
+        if (grad_out) {       // NULL: the caller wants dL/dx only (a critic evaluated inside the actor loss)
+            wgrad<BM, ATOMIC>(acc + L.w1_t, L.NIp, acc + L.b1, xs, L.I, du1, L.Ni);
+            wgrad<BM, ATOMIC>(acc + L.w2_t, L.NCp, acc + L.b2, a1, L.Ni, du2, L.Nc);
+            wgrad<BM, ATOMIC>(acc + L.w3, L.NCp, nullptr, dyb, L.O, a2, L.Nc);
+            for (int o = threadIdx.x; o < L.O; o += kTileThreads) {
+                float a = 0.f;
+                for (int s = 0; s < BM; ++s) a += dyb[o * S + s];
+                acc_add<ATOMIC>(acc + L.b3 + o, a);
+            }
         }
         __syncthreads();
     }
@@ -505,7 +507,7 @@ int ncp_bwd(const float* packed, const float* x, const float* dy, float* dx, flo
     Plan p = make_plan(ncp_bwd_rows(L), L.total, L.f_total, true, B);
     VB_CHECK_ARG(p.BM, VB_ERR_TOO_LARGE, "ncp backward: activations of (%d,%d,%d,%d) do not fit shared memory", I, Ni, Nc, O);
     int grid = 1, rc = 0;
-    if (p.smem_acc) {
+    if (p.smem_acc && dpacked) {
         VB_CHECK_ARG(ws && ws_bytes >= ncp_bwd_workspace_bytes(I, Ni, Nc, O), VB_ERR_WORKSPACE, "vb_ncp_bwd: workspace too small");
 #define LAUNCH(BM_)                                                                                           \
     rc = grid_for(ncp_bwd_kernel<BM_, false>, p.smem_bytes, (B + BM_ - 1) / BM_, 2, &grid);                    \
@@ -517,7 +519,7 @@ int ncp_bwd(const float* packed, const float* x, const float* dy, float* dx, flo
         reduce_rows_kernel<<<(L.f_total + 31) / 32, 1024, 0, stream>>>(reinterpret_cast<float*>(ws), grid, L.f_total, dpacked);
         VB_LAUNCH_CHECK();
     } else {
-        VB_CUDA(cudaMemsetAsync(dpacked, 0, (size_t)L.f_total * 4, stream));
+        if (dpacked) VB_CUDA(cudaMemsetAsync(dpacked, 0, (size_t)L.f_total * 4, stream));
 #define LAUNCH(BM_)                                                                                           \
     rc = grid_for(ncp_bwd_kernel<BM_, true>, p.smem_bytes, (B + BM_ - 1) / BM_, 0, &grid);                     \
     if (rc) return rc;                                                                                        \

@@ -652,7 +652,8 @@ static int launch_bwd(const float* packed, const float* x, const float* dy, floa
     float* d3buf = partials + (int64_t)grid * C::F_TOTAL;
     ncp_bwd_tc_kernel<C><<<grid, 2 * TM, S::BYTES, stream>>>(packed, x, dy, dx, partials, d3buf, B);
     VB_LAUNCH_CHECK();
-    reduce_rows_tc_kernel<<<(C::F_TOTAL + 31) / 32, 1024, 0, stream>>>(partials, grid, C::F_TOTAL, dpacked);
+    if (dpacked)      // NULL: dL/dx only; the per-CTA partial rows stay in the workspace, unread
+        reduce_rows_tc_kernel<<<(C::F_TOTAL + 31) / 32, 1024, 0, stream>>>(partials, grid, C::F_TOTAL, dpacked);
     VB_LAUNCH_CHECK();
     return 0;
 }

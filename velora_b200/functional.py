@@ -9,6 +9,8 @@ from __future__ import annotations
 import ctypes as C
 from typing import List, Optional, Sequence, Tuple
 
+import threading
+
 import torch
 
 from . import _lib
@@ -297,6 +299,28 @@ class CellFn(torch.autograd.Function):
         return (dx, dh, None, None, *grads)
 
 
+# Networks called inside `frozen_parameters()` treat their parameters as constants: the backward returns dL/dx only.  The SAC actor
+# update differentiates the actor loss through both critics (agent.py:236-245); the reference lets autograd fill the critics' .grad there
+# and throws it away at the next critic zero_grad (modules.py:409-415) - here that work (two weight-gradient passes, two unpacks, twelve
+# accumulations at batch 64) is not done at all.
+_FROZEN = threading.local()
+
+
+class frozen_parameters:
+    def __enter__(self):
+        self.prev = getattr(_FROZEN, "on", False)
+        _FROZEN.on = True
+        return self
+
+    def __exit__(self, *exc):
+        _FROZEN.on = self.prev
+        return False
+
+
+def parameters_frozen() -> bool:
+    return getattr(_FROZEN, "on", False)
+
+
 class NcpFn(torch.autograd.Function):
     """y[B,O] = ncp(x[B,I]; three masked layers)."""
 
@@ -345,7 +369,11 @@ class NcpFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             st = _lib.stream_ptr(dev)
             dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
-            dpacked = torch.empty(L.vb_ncp_grad_floats(I, Ni, Nc, O), dtype=torch.float32, device=dev)
+            need = ctx.needs_input_grad[4:]
+            want_params = any(need)
+            if not want_params and dx is None:
+                return (None,) * 10
+            dpacked = torch.empty(L.vb_ncp_grad_floats(I, Ni, Nc, O), dtype=torch.float32, device=dev) if want_params else None
             ws = _workspace(dev, L.vb_ncp_bwd_workspace_bytes(I, Ni, Nc, O, B))
             with _timed("ncp_bwd", 2):
                 _lib.check(
@@ -353,8 +381,9 @@ class NcpFn(torch.autograd.Function):
                                  B, I, Ni, Nc, O, _lib.ptr(ws), ws.numel(), ctx.flags, st),
                     "vb_ncp_bwd",
                 )
+            if not want_params:       # parameters frozen for this call (frozen_parameters()): dL/dx only
+                return (dx, None, None, None) + (None,) * 6
             _dp.maybe_allreduce(dpacked)
-            need = ctx.needs_input_grad[4:]
             shapes = [(Ni, I), (Ni,), (Nc, Ni), (Nc,), (O, Nc), (O,)]
             grads = [torch.empty(s, dtype=torch.float32, device=dev) if need[k] else None for k, s in enumerate(shapes)]
             _count(1)

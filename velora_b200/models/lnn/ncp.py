@@ -75,6 +75,8 @@ class LiquidNCPNetwork(nn.Module):
         for h in heads:
             params += [h.weight, h.bias]
         params += [self.motor.weight, self.motor.bias]
+        if VF.parameters_frozen():
+            params = [p.detach() for p in params]
         dims = (self.in_features, int(self.inter.out_features), int(cmd.n_hidden), int(self.motor.out_features))
         return VF.LiquidSeqFn.apply(x, h0, dims, int(self.kernel_flags), masks, *params)
 
@@ -202,7 +204,10 @@ class NCPNetwork(nn.Module):
         x = x.to(dtype=torch.float32, device=dev)
         dims = (self.in_features, int(l1.out_features), int(l2.out_features), int(l3.out_features))
         masks = (l1.mask, l2.mask, l3.mask)
-        return VF.NcpFn.apply(x, dims, int(self.kernel_flags), masks, l1.weight, l1.bias, l2.weight, l2.bias, l3.weight, l3.bias)
+        params = (l1.weight, l1.bias, l2.weight, l2.bias, l3.weight, l3.bias)
+        if VF.parameters_frozen():
+            params = tuple(p.detach() for p in params)
+        return VF.NcpFn.apply(x, dims, int(self.kernel_flags), masks, *params)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """x [B, in] -> y [B, out] (or [out] when B == 1)."""

@@ -82,10 +82,16 @@ class NeuroFlowCTCore:
     def _train_on(self, batch: BatchExperience) -> Dict[str, torch.Tensor]:
         critic_loss = self._update_critics(batch)
         actions, log_probs, _ = self.actor.forward(batch.states, batch.hiddens)
-        q1, q2 = self.critic.predict(batch.states, actions)
-        if getattr(self, "fused_losses", False) and q1.is_cuda:
+        fused = getattr(self, "fused_losses", False) and actions.is_cuda
+        if fused:
             from velora_b200 import functional as VF
 
+            # the critics' own gradients of the ACTOR loss are never used (the next critic update starts with zero_grad): dL/d(action) only
+            with VF.frozen_parameters():
+                q1, q2 = self.critic.predict(batch.states, actions)
+        else:
+            q1, q2 = self.critic.predict(batch.states, actions)
+        if fused:
             actor_loss = VF.SacActorLossFn.apply(log_probs, q1, q2, self.entropy.log_alpha)
             entropy_loss = VF.SacEntropyLossFn.apply(self.entropy.log_alpha, log_probs.detach(), float(self.entropy.target))
         else:
@@ -230,6 +236,7 @@ class NeuroFlowCore(NeuroFlowCTCore):
         self.hidden_dim = self.actor.hidden_size
         self.entropy = EntropyModuleDiscrete(action_dim, initial_alpha=initial_alpha, optim=optim, lr=alpha_lr, device=device, optim_kwargs=okw)
         self.loss = nn.MSELoss()
+        self.fused_losses = bool(fused)
         self.buffer = ReplayBuffer(buffer_size, state_dim, 1, self.actor.hidden_size, device=device)   # action index stored as one float
 
     def _update_critics(self, batch: BatchExperience) -> torch.Tensor:
@@ -254,7 +261,15 @@ class NeuroFlowCore(NeuroFlowCTCore):
         """agent.py:592-636"""
         critic_loss = self._update_critics(batch)
         _, probs, log_probs, _ = self.actor.forward(batch.states, batch.hiddens)
-        q1, q2 = self.critic.predict(batch.states)
+        if getattr(self, "fused_losses", False) and probs.is_cuda:
+            from velora_b200 import functional as VF
+
+            # Q(s, .) does not depend on the actor: with the critics' parameters frozen there is no critic backward at all in the actor
+            # update (the reference computes their gradients here and discards them at the next zero_grad)
+            with VF.frozen_parameters():
+                q1, q2 = self.critic.predict(batch.states)
+        else:
+            q1, q2 = self.critic.predict(batch.states)
         next_q = torch.min(q1, q2)
         actor_loss = probs * (self.entropy.alpha * log_probs - next_q)
         actor_loss = torch.sum(actor_loss, dim=-1, keepdim=False).mean()
