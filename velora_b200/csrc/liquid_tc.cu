@@ -634,13 +634,15 @@ __global__ void __launch_bounds__(BT, (BwdSmem<C>::BYTES + 1024 > 58368 ? 3 : 4)
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t b = tile * TM + row;
         const bool valid = b < B;
-        float dhc[C::NC];          // role B: dL/dh_t carried backwards
+        // the step-carried state of the two roles shares ONE register array (the allocator sees both roles' live ranges in the one loop):
+        // role B: dhc = dL/dh_t carried backwards;  role A: xn = x_t prefetched one step ahead
+        constexpr int NCARRY = C::NC > C::I ? C::NC : C::I;
+        float carry[NCARRY];
 #pragma unroll
-        for (int j = 0; j < C::NC; ++j) dhc[j] = 0.f;
+        for (int j = 0; j < NCARRY; ++j) carry[j] = 0.f;
+        float (&dhc)[C::NC] = reinterpret_cast<float (&)[C::NC]>(carry);
+        float (&xn)[C::I] = reinterpret_cast<float (&)[C::I]>(carry);
         if (roleB && valid && dh_last) ldg_row<C::NC>(dhc, dh_last + b * C::NC, vh);
-        float xn[C::I];            // role A: x_t prefetched one step ahead
-#pragma unroll
-        for (int i = 0; i < C::I; ++i) xn[i] = 0.f;
         if (!roleB && valid) ldg_row<C::I>(xn, x + rx(b, T - 1) * C::I, vx);
 
 #ifdef VB_ENABLE_TRACE
