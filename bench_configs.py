@@ -261,6 +261,29 @@ def main():
     wall = (time.perf_counter() - t0) / 500
     emit(config="cfg2b NeuroFlowCT.predict captured in one CUDA graph, batch 1", metric="us_per_call", value=1e3 * ms1g, wall_us=1e6 * wall)
 
+    # ---- the other per-environment-step call: ReplayBuffer.add
+    from velora_b200.buffer import ReplayBuffer
+
+    rb = ReplayBuffer(100_000, 4, 1, 8, device=dev)
+    rb.add_multi(torch.randn(64, 4, device=dev), torch.randn(64, 1, device=dev), torch.ones(64, device=dev), torch.randn(64, 4, device=dev),
+                 torch.zeros(64, device=dev), torch.randn(64, 8, device=dev))
+    rb.gather(torch.arange(64, device=dev))          # shadow table built: every add keeps it current
+    st, ac, ns, hd = torch.randn(4, device=dev), torch.randn(1, device=dev), torch.randn(4, device=dev), torch.randn(8, device=dev)
+    add_us = {}
+    for fused in (True, False):
+        rb.fused_add = fused
+        for _ in range(50):
+            rb.add(st, ac, 1.0, ns, False, hd)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(500):
+            rb.add(st, ac, 1.0, ns, False, hd)
+        torch.cuda.synchronize()
+        add_us[fused] = 1e6 * (time.perf_counter() - t0) / 500
+    rb.fused_add = True
+    emit(config="cfg1/2 ReplayBuffer.add, one transition per call (with the packed shadow row)", metric="wall_us_per_call", value=add_us[True],
+         six_indexing_assignments_plus_shadow_refresh_us=add_us[False], launches={"fused": 1, "indexing": 7})
+
     # ------------------------------------------------------------------ cfg 1 end to end: NeuroFlow("CartPole-v1", 20, 128).train(64, n_episodes=50)
     # gymnasium is not installed: the environment is the CartPole-v1 physics restatement of baseline/envs_shim.py (labelled as such)
     if not args.quick:

@@ -143,3 +143,46 @@ def test_gather_empty_index_vector():
         buf.use_shadow = shadow
         got = buf.gather(torch.zeros(0, dtype=torch.int64, device="cuda"))
         assert got.states.shape == (0, 4) and got.hiddens.shape == (0, 8) and got.rewards.shape == (0, 1)
+
+
+def test_add_is_one_launch_and_equals_the_indexing_writes():
+    """BufferBase.add (base.py:73-101) through vb_buffer_add_row: same array contents as the reference's six indexing assignments for
+    every value kind the agents pass (float32 rows, an int64 action index, 0-dim tensors, Python numbers, host scalar tensors), wrap-around
+    included; values on another device fall back to the indexing writes."""
+    from velora_b200 import functional as VF
+    from velora_b200.buffer import ReplayBuffer
+
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev).manual_seed(3)
+    ours = ReplayBuffer(7, 4, 1, 8, device=dev)
+    ref = {k: torch.zeros_like(getattr(ours, k)) for k in FIELDS}
+    pos = 0
+    for n in range(17):
+        s, s2, h = (torch.randn(w, device=dev, generator=g) for w in (4, 4, 8))
+        kind = n % 4
+        action = [torch.randn(1, device=dev, generator=g), torch.tensor(n % 3, device=dev), torch.tensor([n % 3], device=dev),
+                  torch.randn((), device=dev, generator=g)][kind]
+        reward = [1.5, torch.tensor(0.25 * n), float(n), torch.tensor(2.0, device=dev)][kind]
+        done = [False, True, torch.tensor(True), torch.tensor(0.0, device=dev)][kind]
+        before = VF.LAUNCHES
+        ours.add(s, action, reward, s2, done, h)
+        assert VF.LAUNCHES - before == 1 + (1 if action.dtype != torch.float32 else 0) * 0      # one kernel of ours (dtype casts are torch's)
+        ref["states"][pos] = s
+        ref["actions"][pos] = action
+        ref["rewards"][pos] = reward
+        ref["next_states"][pos] = s2
+        ref["dones"][pos] = done
+        ref["hiddens"][pos] = h
+        pos = (pos + 1) % 7
+        if n == 9:
+            ours.gather(torch.arange(ours.size, device=dev))      # builds the shadow table: later adds must keep it current
+    assert ours.position == pos and ours.size == 7 and ours._shadow_current()
+    for k in FIELDS:
+        assert torch.equal(getattr(ours, k), ref[k]), k
+    got = ours.gather(torch.arange(7, device=dev))
+    for k in FIELDS:
+        assert torch.equal(getattr(got, k), ref[k]), k
+    # CPU rows: the reference's own indexing writes (they copy across devices)
+    before = VF.LAUNCHES
+    ours.add(torch.ones(4), torch.ones(1), 0.0, torch.ones(4), False, torch.ones(8))
+    assert torch.equal(ours.states[pos], torch.ones(4, device=dev)) and ours._shadow_current()

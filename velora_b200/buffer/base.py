@@ -20,6 +20,7 @@ FIELDS = FIELD_NAMES
 
 
 class BufferBase:
+    fused_add = True      # `add` as one launch (vb_buffer_add_row); False = the reference's six indexing assignments
     def __init__(self, capacity: int, state_dim: int, action_dim: int, hidden_dim: int, *, device: torch.device | None = None) -> None:
         self.capacity = capacity
         self.state_dim = state_dim
@@ -79,6 +80,10 @@ class BufferBase:
         """Appends one transition (overwriting the oldest once full)."""
         i = self.position
         tracked = self._shadow_current()
+        if self.fused_add and self.states.is_cuda and self._add_fused(i, (state, action, reward, next_state, done, hidden), tracked):
+            self.position = (i + 1) % self.capacity
+            self.size = min(self.size + 1, self.capacity)
+            return
         self.states[i] = state.to(torch.float32)
         self.actions[i] = action
         self.rewards[i] = reward
@@ -89,6 +94,37 @@ class BufferBase:
             self._refresh_shadow(row0=i, n=1)
         self.position = (i + 1) % self.capacity
         self.size = min(self.size + 1, self.capacity)
+
+    def _add_fused(self, i: int, values, tracked: bool) -> bool:
+        """The six assignments of `add` (and the shadow row) in one launch (vb_buffer_add_row) when every tensor value already lives on
+        the buffer's device with the row's element count; anything else takes the reference's indexing writes.  The kernel does not bump
+        the arrays' version counters, and it writes the shadow row itself, so a current shadow table stays current."""
+        from velora_b200 import functional as VF
+
+        arrays = [getattr(self, name) for name in FIELDS]
+        vals = []
+        for a, v in zip(arrays, values):
+            if isinstance(v, torch.Tensor):
+                if v.device != a.device:
+                    if v.numel() == 1 and v.device.type == "cpu":
+                        vals.append(float(v))          # a host scalar tensor: no device round trip
+                        continue
+                    return False
+                if v.numel() != a.shape[1] and v.numel() != 1:
+                    return False
+                v = v.detach().to(torch.float32).contiguous()
+                if v.numel() == 1 and a.shape[1] != 1:
+                    v = v.expand(a.shape[1]).contiguous()
+                vals.append(v)
+            elif isinstance(v, (bool, int, float)):
+                vals.append(float(v))
+            else:
+                return False
+        if tracked:
+            VF.buffer_add_row(arrays, vals, i, self._shadow, self._shadow_offsets, self._shadow_stride)
+        else:
+            VF.buffer_add_row(arrays, vals, i)
+        return True
 
     def add_multi(self, states: torch.Tensor, actions: torch.Tensor, rewards: torch.Tensor, next_states: torch.Tensor,
                   dones: torch.Tensor, hiddens: torch.Tensor) -> None:

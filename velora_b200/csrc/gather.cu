@@ -151,6 +151,53 @@ extern "C" int vb_pack_rows(const float* const* src, const int* row_floats, cons
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ one-launch add
+// BufferBase.add (velora/buffer/base.py:73-101) writes ONE transition with six indexing assignments (six launches, two of them scalar
+// fills) and the shadow table needs a seventh: here the row goes into the six arrays and the packed row in one launch.
+namespace vb {
+struct AddRowArgs {
+    float* dst[kMaxGatherArrays];
+    const float* src[kMaxGatherArrays];     // device row of row_floats values, or NULL: broadcast `scalar`
+    float scalar[kMaxGatherArrays];
+    int row_floats[kMaxGatherArrays];
+    int offset[kMaxGatherArrays];
+    int n;
+};
+__global__ void __launch_bounds__(64) buffer_add_row_kernel(AddRowArgs a, int64_t row, float* __restrict__ shadow, int row_stride) {
+#pragma unroll
+    for (int k = 0; k < kMaxGatherArrays; ++k) {
+        if (k < a.n) {
+            for (int c = threadIdx.x; c < a.row_floats[k]; c += blockDim.x) {
+                const float v = a.src[k] ? __ldg(a.src[k] + c) : a.scalar[k];
+                a.dst[k][row * a.row_floats[k] + c] = v;
+                if (shadow) shadow[row * row_stride + a.offset[k] + c] = v;
+            }
+        }
+    }
+}
+}  // namespace vb
+
+extern "C" int vb_buffer_add_row(float* const* dst, const int* row_floats, const float* const* src, const float* scalars, int n_arrays,
+                                 int64_t row, int64_t capacity, float* shadow, int row_stride, const int* offsets, void* stream) {
+    VB_CHECK_ARG(dst && row_floats && src && scalars, VB_ERR_NULL_POINTER, "vb_buffer_add_row: null pointer");
+    VB_CHECK_ARG(n_arrays >= 1 && n_arrays <= kMaxGatherArrays && row >= 0 && row < capacity, VB_ERR_BAD_DIMS,
+                 "vb_buffer_add_row: bad sizes (row %lld of %lld)", (long long)row, (long long)capacity);
+    VB_CHECK_ARG(!shadow || (offsets && row_stride > 0), VB_ERR_NULL_POINTER, "vb_buffer_add_row: shadow table without a layout");
+    AddRowArgs a;
+    a.n = n_arrays;
+    for (int k = 0; k < kMaxGatherArrays; ++k) { a.dst[k] = nullptr; a.src[k] = nullptr; a.scalar[k] = 0.f; a.row_floats[k] = 0; a.offset[k] = 0; }
+    for (int k = 0; k < n_arrays; ++k) {
+        VB_CHECK_ARG(dst[k] && row_floats[k] > 0, VB_ERR_BAD_DIMS, "vb_buffer_add_row: array %d", k);
+        VB_CHECK_ARG(!shadow || (offsets[k] >= 0 && offsets[k] + row_floats[k] <= row_stride), VB_ERR_BAD_DIMS,
+                     "vb_buffer_add_row: array %d does not fit the packed row", k);
+        a.dst[k] = dst[k]; a.src[k] = src[k]; a.scalar[k] = scalars[k]; a.row_floats[k] = row_floats[k];
+        a.offset[k] = shadow ? offsets[k] : 0;
+    }
+    buffer_add_row_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(a, row, shadow, row_stride);
+    VB_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" int vb_gather_packed(const float* packed, int row_stride, const int* offsets, float* const* dst, const int* row_floats,
                                 int n_arrays, const int64_t* idx, int64_t B, int64_t n_rows, void* stream) {
     VB_CHECK_ARG(packed && offsets, VB_ERR_NULL_POINTER, "vb_gather_packed: null pointer");

@@ -450,6 +450,26 @@ def pack_rows(arrays: Sequence[torch.Tensor], packed: torch.Tensor, offsets: Seq
         )
 
 
+def buffer_add_row(arrays: Sequence[torch.Tensor], values: Sequence, row: int, shadow: Optional[torch.Tensor] = None,
+                   offsets: Optional[Sequence[int]] = None, stride: int = 0) -> None:
+    """arrays[k][row] = values[k] for all k in ONE launch (and the packed shadow row with it).  values[k]: a float32 CUDA tensor of
+    arrays[k].shape[1] elements, or a Python number broadcast over the row."""
+    L = _lib.lib()
+    dev = arrays[0].device
+    n = len(arrays)
+    widths = [a.shape[1] for a in arrays]
+    srcs = [v if isinstance(v, torch.Tensor) else None for v in values]
+    scal = [0.0 if isinstance(v, torch.Tensor) else float(v) for v in values]
+    with torch.cuda.device(dev):
+        _count(1)
+        _lib.check(
+            L.vb_buffer_add_row(_lib.ptr_array(list(arrays)), (C.c_int * n)(*widths), _lib.ptr_array(srcs), (C.c_float * n)(*scal), n,
+                                int(row), int(arrays[0].shape[0]), _lib.ptr(shadow), int(stride),
+                                (C.c_int * n)(*offsets) if offsets is not None else None, _lib.stream_ptr(dev)),
+            "vb_buffer_add_row",
+        )
+
+
 def gather_packed(packed: torch.Tensor, offsets: Sequence[int], stride: int, widths: Sequence[int], indices: torch.Tensor,
                   n_rows: int) -> Tuple[torch.Tensor, ...]:
     """gather_rows reading the packed shadow table (one run of sectors per transition)."""
