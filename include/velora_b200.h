@@ -211,6 +211,10 @@ int vb_gather_rows(const float* const* src, float* const* dst, const int* row_fl
  * one sector in each of six arrays. */
 int vb_pack_rows(const float* const* src, const int* row_floats, const int* offsets, int n_arrays, float* packed,
                  int row_stride, const int64_t* rows, int64_t row0, int64_t n, int64_t capacity, void* stream);
+/* [B,T,F] (batch-major) -> [T,B,F] (time-major) for to_time_major != 0, the reverse otherwise; F <= 64 floats per row.  Used by the host
+ * side to hand batch-major sequence tensors to the tensor-core liquid kernels in the layout they read at full speed. */
+int vb_transpose_rows(const float* src, float* dst, int64_t B, int T, int F, int to_time_major, void* stream);
+
 /* BufferBase.add (velora/buffer/base.py:73-101): one transition into the (<= 8) arrays - row `row` of dst[k] gets the row_floats[k] values at
  * src[k] (device) or, where src[k] is NULL, the host value scalars[k] (reward, done) - and, when `shadow` is given, into the packed row. */
 int vb_buffer_add_row(float* const* dst, const int* row_floats, const float* const* src, const float* scalars, int n_arrays,

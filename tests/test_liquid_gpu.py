@@ -538,3 +538,50 @@ def test_512_neuron_bf16_training_vs_fp32_path(B, T):
     y, hl = net.forward_seq_bf16(x, None)
     torch.autograd.backward([y, hl], [ry, rh])
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.parameters())
+
+
+@pytest.mark.parametrize("B,T,F", [(1, 1, 1), (33, 5, 4), (1000, 37, 2), (257, 64, 8), (70, 33, 10), (40, 9, 20), (65, 3, 64)])
+def test_row_transposition_kernel(B, T, F):
+    """vb_transpose_rows: [B,T,F] <-> [T,B,F], ragged tiles on both axes."""
+    from velora_b200 import _lib
+
+    dev = torch.device("cuda")
+    L = _lib.lib()
+    src = torch.randn(B, T, F, device=dev)
+    out = torch.full((T, B, F), float("nan"), device=dev)
+    _lib.check(L.vb_transpose_rows(_lib.ptr(src), _lib.ptr(out), B, T, F, 1, _lib.stream_ptr(dev)), "vb_transpose_rows")
+    assert torch.equal(out, src.permute(1, 0, 2))
+    back = torch.full((B, T, F), float("nan"), device=dev)
+    _lib.check(L.vb_transpose_rows(_lib.ptr(out), _lib.ptr(back), B, T, F, 0, _lib.stream_ptr(dev)), "vb_transpose_rows")
+    assert torch.equal(back, src)
+
+
+def test_large_batch_major_call_is_relaid_and_equals_time_major():
+    """A batch-major call above functional.RELAYOUT_MIN_ROWS is transposed once and runs on the time-major fast path: results bit-equal to
+    the same call on time-major storage, gradients returned for the caller's tensors."""
+    import velora_b200 as vb
+    from velora_b200 import functional as VF
+    from velora_b200.models.lnn import LiquidNCPNetwork
+
+    dev = torch.device("cuda")
+    B, T = 4096, 8
+    assert B * T >= VF.RELAYOUT_MIN_ROWS
+    vb.set_seed(11)
+    net = LiquidNCPNetwork(4, 20, 2, device=dev)
+    xt = torch.randn(T, B, 4, device=dev)
+    rt = torch.randn(T, B, 2, device=dev)
+    rh = torch.randn(B, 8, device=dev)
+    res = []
+    for batch_major in (False, True):
+        x = xt.permute(1, 0, 2)
+        ry = rt.permute(1, 0, 2)
+        if batch_major:
+            x, ry = x.contiguous(), ry.contiguous()
+        x = x.detach().requires_grad_(True)
+        net.zero_grad()
+        y, ht, hl = net.forward_seq(x, None, return_last=True)
+        torch.autograd.backward([y, hl], [ry, rh])
+        res.append((y.detach().clone(), ht.detach().clone(), x.grad.clone(), [p.grad.clone() for p in net.parameters()]))
+    (y0, h0, dx0, g0), (y1, h1, dx1, g1) = res
+    assert torch.equal(y0, y1) and torch.equal(h0, h1) and torch.equal(dx0, dx1)
+    assert all(torch.equal(a, b) for a, b in zip(g0, g1))

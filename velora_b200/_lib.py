@@ -55,6 +55,7 @@ SIGNATURES = {
     "vb_ncp_unpack_grads": (_i, [_p, _pp, _i, _pp, _pp, _i, _i, _i, _i, _i, _p]),
     "vb_gather_rows": (_i, [_pp, _pp, C.POINTER(C.c_int), _i, _p, _i64, _i64, _p]),
     "vb_pack_rows": (_i, [_pp, C.POINTER(C.c_int), C.POINTER(C.c_int), _i, _p, _i, _p, _i64, _i64, _i64, _p]),
+    "vb_transpose_rows": (_i, [_p, _p, _i64, _i, _i, _i, _p]),
     "vb_buffer_add_row": (_i, [_pp, _p, _pp, _p, _i, _i64, _i64, _p, _i, _p, _p]),
     "vb_gather_packed": (_i, [_p, _i, C.POINTER(C.c_int), _pp, C.POINTER(C.c_int), _i, _p, _i64, _i64, _p]),
     "vb_adam_multi": (_i, [_pp, _pp, _pp, _pp, _pp, C.POINTER(C.c_int64), _i, C.c_float, C.c_float, C.c_float, C.c_float, _p]),

@@ -207,3 +207,71 @@ extern "C" int vb_gather_packed(const float* packed, int row_stride, const int* 
     for (int k = 0; k < n_arrays; ++k) { src[k] = packed + offsets[k]; strides[k] = row_stride; }
     return gather_impl(src, strides, dst, row_floats, n_arrays, idx, B, n_rows, stream, "vb_gather_packed");
 }
+
+// ------------------------------------------------------------------------------------------------ [B,T,F] <-> [T,B,F]
+// The liquid tensor-core kernels read one row per thread: with time-major storage a warp's 32 rows are contiguous, with batch-major
+// storage they are T rows apart (32 lines per access instead of 4: measured 0.43 against 0.29 ms on config 3).  A batch-major sequence
+// tensor is therefore re-laid once per call by this tiled transposition of F-float rows (both sides coalesced, HBM-bound).
+namespace vb {
+// V = float, float2 or float4: a row is F elements of V
+template <int TT, class V>
+__global__ void __launch_bounds__(256) transpose_rows_kernel(const V* __restrict__ src, V* __restrict__ dst, int64_t B, int T, int F,
+                                                             int to_time_major) {
+    extern __shared__ __align__(16) unsigned char tile_raw[];
+    V* tile = reinterpret_cast<V*>(tile_raw);        // [32 samples][TT * F + 1]
+    const int pitch = TT * F + 1;
+    const int64_t b0 = (int64_t)blockIdx.y * 32;
+    const int t0 = blockIdx.x * TT;
+    const int nt = min(TT, T - t0);
+    const int run = nt * F;                          // elements of one sample inside the tile (contiguous in the batch-major tensor)
+    const int nb = (int)min((int64_t)32, B - b0);
+    // batch-major side: sample s, elements [t0 * F, t0 * F + run) of its T * F row;  time-major side: step t, elements [b0 * F, (b0 + nb) * F)
+    if (to_time_major) {
+        for (int e = threadIdx.x; e < nb * run; e += 256) {
+            const int s = e / run, j = e - s * run;
+            tile[s * pitch + j] = __ldg(src + ((b0 + s) * T + t0) * F + j);
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < nt * nb * F; e += 256) {
+            const int t = e / (nb * F), r = e - t * (nb * F), s = r / F, f = r - s * F;
+            dst[((int64_t)(t0 + t) * B + b0) * F + r] = tile[s * pitch + t * F + f];
+        }
+    } else {
+        for (int e = threadIdx.x; e < nt * nb * F; e += 256) {
+            const int t = e / (nb * F), r = e - t * (nb * F), s = r / F, f = r - s * F;
+            tile[s * pitch + t * F + f] = __ldg(src + ((int64_t)(t0 + t) * B + b0) * F + r);
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < nb * run; e += 256) {
+            const int s = e / run, j = e - s * run;
+            dst[((b0 + s) * T + t0) * F + j] = tile[s * pitch + j];
+        }
+    }
+}
+
+template <class V>
+static int launch_transpose(const float* src, float* dst, int64_t B, int T, int F, int to_time_major, cudaStream_t stream) {
+    const int row_bytes = F * (int)sizeof(V);
+    const int TT = row_bytes <= 32 ? 32 : (row_bytes <= 64 ? 16 : 4);
+    const dim3 grid((T + TT - 1) / TT, (unsigned)((B + 31) / 32));
+    const size_t smem = (size_t)32 * (TT * F + 1) * sizeof(V);
+    const V* s = reinterpret_cast<const V*>(src);
+    V* d = reinterpret_cast<V*>(dst);
+    if (TT == 32) transpose_rows_kernel<32, V><<<grid, 256, smem, stream>>>(s, d, B, T, F, to_time_major);
+    else if (TT == 16) transpose_rows_kernel<16, V><<<grid, 256, smem, stream>>>(s, d, B, T, F, to_time_major);
+    else transpose_rows_kernel<4, V><<<grid, 256, smem, stream>>>(s, d, B, T, F, to_time_major);
+    VB_LAUNCH_CHECK();
+    return 0;
+}
+}  // namespace vb
+
+extern "C" int vb_transpose_rows(const float* src, float* dst, int64_t B, int T, int F, int to_time_major, void* stream) {
+    VB_CHECK_ARG(B >= 0 && T >= 1 && F >= 1 && F <= 64, VB_ERR_BAD_DIMS, "vb_transpose_rows: bad sizes B=%lld T=%d F=%d", (long long)B, T, F);
+    if (B == 0) return 0;
+    VB_CHECK_ARG(src && dst && src != dst, VB_ERR_NULL_POINTER, "vb_transpose_rows: null or aliased pointer");
+    VB_CHECK_ARG((B + 31) / 32 <= 65535, VB_ERR_TOO_LARGE, "vb_transpose_rows: batch too large for one launch");
+    const uintptr_t al = reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst);
+    if ((F & 3) == 0 && (al & 15) == 0) return launch_transpose<float4>(src, dst, B, T, F / 4, to_time_major, (cudaStream_t)stream);
+    if ((F & 1) == 0 && (al & 7) == 0) return launch_transpose<float2>(src, dst, B, T, F / 2, to_time_major, (cudaStream_t)stream);
+    return launch_transpose<float>(src, dst, B, T, F, to_time_major, (cudaStream_t)stream);
+}

@@ -94,6 +94,27 @@ def _seq(t: Optional[torch.Tensor], tm_ok: bool) -> Tuple[Optional[torch.Tensor]
     return t.contiguous(), False
 
 
+RELAYOUT_MIN_ROWS = 16384     # B * T from which a batch-major sequence tensor is re-laid time-major for the tensor-core kernels
+
+
+def _time_major_copy(t: torch.Tensor) -> torch.Tensor:
+    """Contiguous fp32 [B,T,F] -> the same values in time-major storage ([T,B,F] viewed as [B,T,F]): one tiled transposition
+    (vb_transpose_rows).  The liquid tensor-core kernels read one row per thread; time-major rows of a warp are contiguous."""
+    B, T, F = t.shape
+    out = torch.empty((T, B, F), dtype=torch.float32, device=t.device)
+    L = _lib.lib()
+    with torch.cuda.device(t.device):
+        _count(1)
+        _lib.check(L.vb_transpose_rows(_lib.ptr(t), _lib.ptr(out), B, T, F, 1, _lib.stream_ptr(t.device)), "vb_transpose_rows")
+    return out.permute(1, 0, 2)
+
+
+def _relayout(t: Optional[torch.Tensor], is_tm: bool, tm_ok: bool) -> Tuple[Optional[torch.Tensor], bool]:
+    if t is None or is_tm or not tm_ok or not t.is_contiguous() or t.shape[0] * t.shape[1] < RELAYOUT_MIN_ROWS or t.shape[2] > 64:
+        return t, is_tm
+    return _time_major_copy(t), True
+
+
 class LiquidSeqFn(torch.autograd.Function):
     """y[B,T,O], h_traj[B,T,Nc], h_last[B,Nc] = liquid(x[B,T,I], h0[B,Nc] | None; 7 masked layers)."""
 
@@ -109,6 +130,7 @@ class LiquidSeqFn(torch.autograd.Function):
         # warp accesses; the outputs are allocated that way and returned as [B,T,F] views
         tm_ok = T > 1 and bool(L.vb_liquid_time_major_ok(I, Ni, Nc, O, flags))
         x, x_tm = _seq(x, tm_ok)
+        x, x_tm = _relayout(x, x_tm, tm_ok)          # batch-major input of a large call: one transposition, then the fast layout throughout
         h0c = _f32c(h0)
         params = [_f32c(p.detach()) for p in params]
         w_in, b_in = params[0], params[1]
@@ -180,6 +202,8 @@ class LiquidSeqFn(torch.autograd.Function):
         tm_ok, x_tm = ctx.layout
         dy, dy_tm = _seq(dy, tm_ok) if dy is not None else (torch.zeros((B, T, O), dtype=torch.float32, device=dev), False)
         dh_traj, dh_tm = _seq(dh_traj, tm_ok)
+        dy, dy_tm = _relayout(dy, dy_tm, tm_ok)
+        dh_traj, dh_tm = _relayout(dh_traj, dh_tm, tm_ok)
         dh_last = _f32c(dh_last)
         lay = (X_TM | DX_TM if x_tm else 0) | (H_TM if tm_ok else 0) | (Y_TM if dy_tm else 0) | (DH_TM if dh_tm else 0)
         need_x = ctx.needs_input_grad[0]
