@@ -103,6 +103,7 @@ class BufferBase:
 
         arrays = [getattr(self, name) for name in FIELDS]
         vals = []
+        f32 = torch.float32
         for a, v in zip(arrays, values):
             if isinstance(v, torch.Tensor):
                 if v.device != a.device:
@@ -110,20 +111,26 @@ class BufferBase:
                         vals.append(float(v))          # a host scalar tensor: no device round trip
                         continue
                     return False
-                if v.numel() != a.shape[1] and v.numel() != 1:
-                    return False
-                v = v.detach().to(torch.float32).contiguous()
-                if v.numel() == 1 and a.shape[1] != 1:
-                    v = v.expand(a.shape[1]).contiguous()
+                w = a.shape[1]
+                if v.numel() != w:
+                    if v.numel() != 1:
+                        return False
+                    v = v.detach().to(f32).reshape(1).expand(w).contiguous()
+                elif v.dtype is not f32 or not v.is_contiguous() or v.requires_grad:
+                    v = v.detach().to(f32).contiguous()
                 vals.append(v)
             elif isinstance(v, (bool, int, float)):
                 vals.append(float(v))
             else:
                 return False
-        if tracked:
-            VF.buffer_add_row(arrays, vals, i, self._shadow, self._shadow_offsets, self._shadow_stride)
-        else:
-            VF.buffer_add_row(arrays, vals, i)
+        # the ctypes view of the six arrays (pointers, widths, shadow layout) is rebuilt only when an array was replaced
+        key = tuple(a.data_ptr() for a in arrays) + (self._shadow.data_ptr() if tracked else 0,)
+        cache = getattr(self, "_add_args", None)
+        if cache is None or cache[0] != key:
+            cache = (key, VF.buffer_add_args(arrays, self._shadow if tracked else None,
+                                            self._shadow_offsets if tracked else None, self._shadow_stride if tracked else 0))
+            self._add_args = cache
+        VF.buffer_add_row_cached(cache[1], vals, i)
         return True
 
     def add_multi(self, states: torch.Tensor, actions: torch.Tensor, rewards: torch.Tensor, next_states: torch.Tensor,

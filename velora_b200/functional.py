@@ -494,6 +494,37 @@ def buffer_add_row(arrays: Sequence[torch.Tensor], values: Sequence, row: int, s
         )
 
 
+def buffer_add_args(arrays: Sequence[torch.Tensor], shadow: Optional[torch.Tensor], offsets: Optional[Sequence[int]], stride: int):
+    """The call-invariant ctypes arguments of vb_buffer_add_row for one buffer (see buffer_add_row_cached)."""
+    n = len(arrays)
+    widths = [a.shape[1] for a in arrays]
+    dev = arrays[0].device
+    return dict(n=n, dev=dev, dst=_lib.ptr_array(list(arrays)), widths=(C.c_int * n)(*widths), capacity=int(arrays[0].shape[0]),
+                shadow=_lib.ptr(shadow), stride=int(stride), offsets=(C.c_int * n)(*offsets) if offsets is not None else None,
+                src=(C.c_void_p * n)(), scal=(C.c_float * n)(), keep=(arrays, shadow))
+
+
+def buffer_add_row_cached(args, values: Sequence, row: int) -> None:
+    """buffer_add_row with the per-buffer arguments prepared once: the per-call work is six pointer / scalar stores and one launch."""
+    src, scal = args["src"], args["scal"]
+    for k, v in enumerate(values):
+        if isinstance(v, torch.Tensor):
+            src[k] = v.data_ptr()
+            scal[k] = 0.0
+        else:
+            src[k] = None
+            scal[k] = v
+    dev = args["dev"]
+    global LAUNCHES
+    LAUNCHES += 1
+    with torch.cuda.device(dev):
+        _lib.check(
+            _lib.lib().vb_buffer_add_row(args["dst"], args["widths"], src, scal, args["n"], int(row), args["capacity"], args["shadow"],
+                                         args["stride"], args["offsets"], _lib.stream_ptr(dev)),
+            "vb_buffer_add_row",
+        )
+
+
 def gather_packed(packed: torch.Tensor, offsets: Sequence[int], stride: int, widths: Sequence[int], indices: torch.Tensor,
                   n_rows: int) -> Tuple[torch.Tensor, ...]:
     """gather_rows reading the packed shadow table (one run of sectors per transition)."""
