@@ -259,6 +259,32 @@ int vb_sac_actor_loss_bwd(const float* q1, const float* q2, const float* log_alp
 int vb_sac_entropy_loss_fwd(const float* logp, const float* log_alpha, float target_entropy, int64_t B, float* out, void* workspace,
                             void* stream);
 
+/* The same for the discrete agent (NeuroFlow, agent.py:549-590, 592-636; modules.py:820-838): q / probs are [B,A] row-major, actions [B] hold the
+ * action index as a float (the replay buffer's storage), logp [B] is the log-probability of the sampled action.
+ *   critic:  target = r + (1 - done) gamma sum_a p'(a) (min(q1_t, q2_t)(a) - alpha log(p'(a) + 1e-8));  losses[k] = mean((q_k[b, action_b] - target)^2)
+ *   actor:   out[0] = mean_b sum_a p(a) (alpha logp_b - min(q1, q2)(a)),  out[1] = mean_b (logp_b sum_a p(a));  gradients to p and logp
+ *   entropy: out[0] = log_alpha (H - target_entropy), out[1] = H - target_entropy,  H = -mean_b sum_a p(a) log(p(a) + 1e-8) */
+int vb_sacd_critic_loss_fwd(const float* q1, const float* q2, const float* actions, const float* next_probs, const float* q1_target,
+                            const float* q2_target, const float* rewards, const float* dones, const float* log_alpha, float gamma,
+                            int64_t B, int A, float* target, float* losses, void* workspace, void* stream);
+int vb_sacd_critic_loss_bwd(const float* q1, const float* q2, const float* actions, const float* target, const float* d_loss1,
+                            const float* d_loss2, int64_t B, int A, float* dq1, float* dq2, void* stream);
+int vb_sacd_actor_loss_fwd(const float* probs, const float* logp, const float* q1, const float* q2, const float* log_alpha, int64_t B,
+                           int A, float* out, void* workspace, void* stream);
+int vb_sacd_actor_loss_bwd(const float* probs, const float* logp, const float* q1, const float* q2, const float* log_alpha,
+                           const float* d_loss, int64_t B, int A, float* dprobs, float* dlogp, void* stream);
+int vb_sacd_entropy_loss_fwd(const float* probs, const float* log_alpha, float target_entropy, int64_t B, int A, float* out,
+                             void* workspace, void* stream);
+
+/* The tail of SACActorDiscrete.forward after the network (velora/models/sac/discrete.py:41-57, 80-101): probs = softmax(logits) [B,A];
+ * Categorical(probs) normalises once more; actions [B] (int64) = argmax(p_n / noise) with noise [B,A] ~ Exp(1) drawn by the caller from torch's
+ * generator (what torch.multinomial does for one sample); log_prob [B] = log(clamp(p_n[action], eps, 1 - eps)).  A <= 64.
+ * Backward: d_probs [B,A] or NULL, d_log_prob [B] or NULL -> d_logits [B,A]. */
+int vb_categorical_head_fwd(const float* logits, const float* noise, int64_t B, int A, float* probs, int64_t* actions, float* log_prob,
+                            void* stream);
+int vb_categorical_head_bwd(const float* probs, const int64_t* actions, const float* d_probs, const float* d_log_prob, int64_t B, int A,
+                            float* d_logits, void* stream);
+
 /* ------------------------------------------------------------------------------------------------ data-parallel exchange */
 /* One-shot all-reduce (sum, then * scale) of a small fp32 block over NVLink peer memory: the ONE exchange of the data-parallel path, the
  * parameter-gradient block of a backward.  peer_buffers: host array of `world` device pointers, entry r = rank r's

@@ -67,6 +67,13 @@ SIGNATURES = {
     "vb_sac_actor_loss_fwd": (_i, [_p, _p, _p, _p, _i64, _p, _p, _p]),
     "vb_sac_actor_loss_bwd": (_i, [_p, _p, _p, _p, _i64, _p, _p, _p, _p]),
     "vb_sac_entropy_loss_fwd": (_i, [_p, _p, C.c_float, _i64, _p, _p, _p]),
+    "vb_categorical_head_fwd": (_i, [_p, _p, _i64, _i, _p, _p, _p, _p]),
+    "vb_categorical_head_bwd": (_i, [_p, _p, _p, _p, _i64, _i, _p, _p]),
+    "vb_sacd_critic_loss_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, C.c_float, _i64, _i, _p, _p, _p, _p]),
+    "vb_sacd_critic_loss_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i, _p, _p, _p]),
+    "vb_sacd_actor_loss_fwd": (_i, [_p, _p, _p, _p, _p, _i64, _i, _p, _p, _p]),
+    "vb_sacd_actor_loss_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i, _p, _p, _p]),
+    "vb_sacd_entropy_loss_fwd": (_i, [_p, _p, C.c_float, _i64, _i, _p, _p, _p]),
     "vb_allreduce_oneshot_buffer_bytes": (_i64, [_i64]),
     "vb_allreduce_oneshot": (_i, [_p, _i64, _pp, _i, _i, _i64, C.c_float, _p, _p]),
     "vb_polyak_multi": (_i, [_pp, _pp, C.POINTER(C.c_int64), _i, C.c_float, _p]),

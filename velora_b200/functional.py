@@ -855,3 +855,148 @@ class LiquidBf16SeqFn(torch.autograd.Function):
                 "vb_liquid_unpack_grads",
             )
         return (dx, dh0, None, None, *grads)
+
+
+# ------------------------------------------------------------------------------------------------ discrete agent (NeuroFlow) losses
+class SacdCriticLossFn(torch.autograd.Function):
+    """(c1_loss, c2_loss) of NeuroFlow._update_critics (agent.py:549-590): the soft state value of the next state from the actor's
+    probabilities and the target critics (no gradient), the Q-values of the taken actions, both MSE losses - one launch."""
+
+    @staticmethod
+    def forward(ctx, q1, q2, actions, next_probs, q1t, q2t, rewards, dones, log_alpha, gamma):
+        L = _lib.lib()
+        dev = q1.device
+        B, A = q1.shape
+        q1, q2, next_probs, q1t, q2t = (_f32c(t.detach()) for t in (q1, q2, next_probs, q1t, q2t))
+        actions, rewards, dones = (_f32c(t.detach()).reshape(-1) for t in (actions, rewards, dones))
+        la = _f32c(log_alpha.detach()).reshape(1)
+        target = torch.empty(B, dtype=torch.float32, device=dev)
+        losses = torch.empty(2, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            ws = _loss_workspace(dev)
+            _count(1)
+            _lib.check(L.vb_sacd_critic_loss_fwd(_lib.ptr(q1), _lib.ptr(q2), _lib.ptr(actions), _lib.ptr(next_probs), _lib.ptr(q1t), _lib.ptr(q2t),
+                                                 _lib.ptr(rewards), _lib.ptr(dones), _lib.ptr(la), float(gamma), B, A, _lib.ptr(target),
+                                                 _lib.ptr(losses), _lib.ptr(ws), _lib.stream_ptr(dev)), "vb_sacd_critic_loss_fwd")
+        ctx.save_for_backward(q1, q2, actions, target)
+        ctx.set_materialize_grads(False)
+        return losses[0], losses[1]
+
+    @staticmethod
+    def backward(ctx, g1, g2):
+        q1, q2, actions, target = ctx.saved_tensors
+        L = _lib.lib()
+        dev = q1.device
+        B, A = q1.shape
+        dq1 = torch.empty((B, A), dtype=torch.float32, device=dev) if g1 is not None else None
+        dq2 = torch.empty((B, A), dtype=torch.float32, device=dev) if g2 is not None else None
+        g1c = _f32c(g1).reshape(1) if g1 is not None else None
+        g2c = _f32c(g2).reshape(1) if g2 is not None else None
+        with torch.cuda.device(dev):
+            _count(1)
+            _lib.check(L.vb_sacd_critic_loss_bwd(_lib.ptr(q1), _lib.ptr(q2), _lib.ptr(actions), _lib.ptr(target), _lib.ptr(g1c), _lib.ptr(g2c), B, A,
+                                                 _lib.ptr(dq1), _lib.ptr(dq2), _lib.stream_ptr(dev)), "vb_sacd_critic_loss_bwd")
+        return (dq1, dq2) + (None,) * 8
+
+
+class SacdActorLossFn(torch.autograd.Function):
+    """mean_b sum_a p(a) (exp(log_alpha) logp_b - min(q1, q2)(a)) (agent.py:605-612); gradients to p, logp and log_alpha - the critics are
+    constants here (their gradient of this loss is never used)."""
+
+    @staticmethod
+    def forward(ctx, probs, logp, q1, q2, log_alpha):
+        L = _lib.lib()
+        dev = probs.device
+        B, A = probs.shape
+        p, a, b = (_f32c(t.detach()) for t in (probs, q1, q2))
+        lp = _f32c(logp.detach()).reshape(-1)
+        la = _f32c(log_alpha.detach()).reshape(1)
+        out = torch.empty(2, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            ws = _loss_workspace(dev)
+            _count(1)
+            _lib.check(L.vb_sacd_actor_loss_fwd(_lib.ptr(p), _lib.ptr(lp), _lib.ptr(a), _lib.ptr(b), _lib.ptr(la), B, A, _lib.ptr(out), _lib.ptr(ws),
+                                                _lib.stream_ptr(dev)), "vb_sacd_actor_loss_fwd")
+        ctx.save_for_backward(p, lp, a, b, la, out)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        p, lp, a, b, la, out = ctx.saved_tensors
+        L = _lib.lib()
+        dev = p.device
+        B, A = p.shape
+        gc = _f32c(g).reshape(1)
+        dprobs = torch.empty((B, A), dtype=torch.float32, device=dev)
+        dlogp = torch.empty((B, 1), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _count(1)
+            _lib.check(L.vb_sacd_actor_loss_bwd(_lib.ptr(p), _lib.ptr(lp), _lib.ptr(a), _lib.ptr(b), _lib.ptr(la), _lib.ptr(gc), B, A,
+                                                _lib.ptr(dprobs), _lib.ptr(dlogp), _lib.stream_ptr(dev)), "vb_sacd_actor_loss_bwd")
+        dla = (gc * la.exp() * out[1]).reshape(()) if ctx.needs_input_grad[4] else None
+        return dprobs, dlogp, None, None, dla
+
+
+class SacdEntropyLossFn(torch.autograd.Function):
+    """log_alpha (H - target), H = -mean_b sum_a p(a) log(p(a) + 1e-8) with no gradient into p (modules.py:820-838)."""
+
+    @staticmethod
+    def forward(ctx, log_alpha, probs, target_entropy):
+        L = _lib.lib()
+        dev = probs.device
+        B, A = probs.shape
+        p = _f32c(probs.detach())
+        la = _f32c(log_alpha.detach()).reshape(1)
+        out = torch.empty(2, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            ws = _loss_workspace(dev)
+            _count(1)
+            _lib.check(L.vb_sacd_entropy_loss_fwd(_lib.ptr(p), _lib.ptr(la), float(target_entropy), B, A, _lib.ptr(out), _lib.ptr(ws),
+                                                  _lib.stream_ptr(dev)), "vb_sacd_entropy_loss_fwd")
+        ctx.save_for_backward(out)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (out,) = ctx.saved_tensors
+        return (g * out[1]).reshape(()), None, None
+
+
+class CategoricalHeadFn(torch.autograd.Function):
+    """(actions [B] int64, probs [B,A], log_prob [B,1]) = the tail of SACActorDiscrete.forward (discrete.py:41-57, 80-101) for logits [B,A] and
+    Exp(1) noise [B,A] drawn by the caller with torch's generator - one launch forward, one backward."""
+
+    @staticmethod
+    def forward(ctx, logits, noise):
+        L = _lib.lib()
+        dev = logits.device
+        B, A = logits.shape
+        x, q = _f32c(logits.detach()), _f32c(noise)
+        probs = torch.empty((B, A), dtype=torch.float32, device=dev)
+        actions = torch.empty((B,), dtype=torch.int64, device=dev)
+        logp = torch.empty((B, 1), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _count(1)
+            _lib.check(L.vb_categorical_head_fwd(_lib.ptr(x), _lib.ptr(q), B, A, _lib.ptr(probs), _lib.ptr(actions), _lib.ptr(logp),
+                                                 _lib.stream_ptr(dev)), "vb_categorical_head_fwd")
+        ctx.save_for_backward(probs, actions)
+        ctx.mark_non_differentiable(actions)
+        ctx.set_materialize_grads(False)
+        return actions, probs, logp
+
+    @staticmethod
+    def backward(ctx, _ga, d_probs, d_logp):
+        probs, actions = ctx.saved_tensors
+        if d_probs is None and d_logp is None:
+            return None, None
+        L = _lib.lib()
+        dev = probs.device
+        B, A = probs.shape
+        dp = _f32c(d_probs) if d_probs is not None else None
+        dl = _f32c(d_logp).reshape(-1) if d_logp is not None else None
+        dx = torch.empty((B, A), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _count(1)
+            _lib.check(L.vb_categorical_head_bwd(_lib.ptr(probs), _lib.ptr(actions), _lib.ptr(dp), _lib.ptr(dl), B, A, _lib.ptr(dx),
+                                                 _lib.stream_ptr(dev)), "vb_categorical_head_bwd")
+        return dx, None

@@ -230,7 +230,8 @@ class NeuroFlowCore(NeuroFlowCTCore):
             if optim is not torch.optim.Adam:
                 raise ValueError("fused=True replaces torch.optim.Adam only")
             optim, okw = FusedAdam, None
-        self.actor = ActorModuleDiscrete(state_dim, actor_neurons, action_dim, optim=optim, lr=actor_lr, device=device, optim_kwargs=okw)
+        self.actor = ActorModuleDiscrete(state_dim, actor_neurons, action_dim, optim=optim, lr=actor_lr, device=device, optim_kwargs=okw,
+                                         fused_head=fused)
         self.critic = CriticModuleDiscrete(state_dim, critic_neurons, action_dim, optim=optim, lr=critic_lr, tau=tau, device=device,
                                            optim_kwargs=okw, fused_update=fused)
         self.hidden_dim = self.actor.hidden_size
@@ -241,6 +242,18 @@ class NeuroFlowCore(NeuroFlowCTCore):
 
     def _update_critics(self, batch: BatchExperience) -> torch.Tensor:
         """agent.py:549-590"""
+        if getattr(self, "fused_losses", False) and batch.states.is_cuda:
+            from velora_b200 import functional as VF
+
+            with torch.no_grad():
+                _, next_probs, _, _ = self.actor.forward(batch.next_states, batch.hiddens)
+                t1, t2 = self.critic.target_pair(batch.next_states)
+            q1, q2 = self.critic.predict(batch.states)
+            c1_loss, c2_loss = VF.SacdCriticLossFn.apply(q1, q2, batch.actions, next_probs, t1, t2, batch.rewards, batch.dones,
+                                                         self.entropy.log_alpha, self.gamma)
+            critic_loss = c1_loss.detach() + c2_loss.detach()
+            self.critic.gradient_step(c1_loss, c2_loss)
+            return critic_loss
         with torch.no_grad():
             _, next_probs, _, _ = self.actor.forward(batch.next_states, batch.hiddens)
             next_log_probs = torch.log(next_probs + 1e-8)
@@ -270,10 +283,14 @@ class NeuroFlowCore(NeuroFlowCTCore):
                 q1, q2 = self.critic.predict(batch.states)
         else:
             q1, q2 = self.critic.predict(batch.states)
-        next_q = torch.min(q1, q2)
-        actor_loss = probs * (self.entropy.alpha * log_probs - next_q)
-        actor_loss = torch.sum(actor_loss, dim=-1, keepdim=False).mean()
-        entropy_loss = self.entropy.compute_loss(probs, torch.log(probs + 1e-8))
+        if getattr(self, "fused_losses", False) and probs.is_cuda:
+            actor_loss = VF.SacdActorLossFn.apply(probs, log_probs, q1, q2, self.entropy.log_alpha)
+            entropy_loss = VF.SacdEntropyLossFn.apply(self.entropy.log_alpha, probs.detach(), self.entropy.target_value)
+        else:
+            next_q = torch.min(q1, q2)
+            actor_loss = probs * (self.entropy.alpha * log_probs - next_q)
+            actor_loss = torch.sum(actor_loss, dim=-1, keepdim=False).mean()
+            entropy_loss = self.entropy.compute_loss(probs, torch.log(probs + 1e-8))
         self.actor.gradient_step(actor_loss)
         self.entropy.gradient_step(entropy_loss)
         self.critic.update_targets()

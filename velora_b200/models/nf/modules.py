@@ -185,9 +185,9 @@ class ActorModuleDiscrete:
     """modules.py:190-318"""
 
     def __init__(self, state_dim: int, n_neurons: int, action_dim: int, *, optim: Type[optim.Optimizer] = optim.Adam,
-                 lr: float = 3e-4, device: torch.device | None = None, optim_kwargs: dict | None = None):
+                 lr: float = 3e-4, device: torch.device | None = None, optim_kwargs: dict | None = None, fused_head: bool = False):
         self.device = device
-        self.network = SACActorDiscrete(state_dim, n_neurons, action_dim, device=device).to(device)
+        self.network = SACActorDiscrete(state_dim, n_neurons, action_dim, device=device, fused_head=fused_head).to(device)
         self.hidden_size = self.network.ncp.hidden_size
         self.optim = optim(self.network.parameters(), lr=lr, **(optim_kwargs or {}))
         self.active_params = self.network.ncp.active_params
@@ -252,7 +252,11 @@ class CriticModuleDiscrete:
         return _concurrently(self._side, lambda: self.network1(obs), lambda: self.network2(obs))
 
     def target_predict(self, obs: torch.Tensor) -> torch.Tensor:
-        return torch.min(*_concurrently(self._side, lambda: self.target1(obs), lambda: self.target2(obs)))
+        return torch.min(*self.target_pair(obs))
+
+    def target_pair(self, obs: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Both target critics' Q(s, .) (the fused critic loss takes their minimum itself)."""
+        return _concurrently(self._side, lambda: self.target1(obs), lambda: self.target2(obs))
 
 
 class EntropyModuleDiscrete:
@@ -261,6 +265,7 @@ class EntropyModuleDiscrete:
     def __init__(self, action_dim: int, *, initial_alpha: float = 1.0, optim: Type[optim.Optimizer] = optim.Adam,
                  lr: float = 3e-4, device: torch.device | None = None, optim_kwargs: dict | None = None):
         self.target = 0.98 * torch.tensor(1 / action_dim, device=device).log()
+        self.target_value = float(self.target)       # host copy for the fused loss kernel (no device read inside a graph capture)
         self.log_alpha = nn.Parameter(torch.tensor(initial_alpha, device=device).log())
         self.optim = optim([self.log_alpha], lr=lr, **(optim_kwargs or {}))
 

@@ -7,16 +7,38 @@ from torch.distributions import Categorical
 
 from velora_b200.models.lnn.ncp import LiquidNCPNetwork, NCPNetwork
 
+_TORCH_CATEGORICAL_SAMPLE = Categorical.sample      # the fused head steps aside when somebody (a test replaying recorded draws) patched it
+
 
 class SACActorDiscrete(nn.Module):
     """Liquid actor emitting a categorical distribution over actions (discrete.py:10-96)."""
 
-    def __init__(self, num_obs: int, n_neurons: int, num_actions: int, *, device: torch.device | None = None) -> None:
+    def __init__(self, num_obs: int, n_neurons: int, num_actions: int, *, device: torch.device | None = None,
+                 fused_head: bool = False) -> None:
         super().__init__()
         self.device = device
         self.ncp = LiquidNCPNetwork(num_obs, n_neurons, num_actions, device=device).to(device)
         self.num_actions = num_actions
         self.softmax = nn.Softmax(dim=-1)
+        self.fused_head = fused_head
+
+    @torch.jit.ignore
+    def _head(self, logits: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """logits -> (actions, probs, log_prob of the actions): softmax + `get_sample`, or with `fused_head` one kernel
+        (functional.CategoricalHeadFn) fed with the Exp(1) noise torch.multinomial would draw - same generator consumption, same draw."""
+        from velora_b200 import dataparallel as _dp
+
+        if (self.fused_head and logits.is_cuda and logits.dim() == 2 and logits.shape[1] <= 64
+                and Categorical.sample is _TORCH_CATEGORICAL_SAMPLE and not (_dp.is_enabled() and _dp.world_size() > 1)):
+            from velora_b200 import functional as VF
+
+            noise = torch.empty_like(logits, requires_grad=False).exponential_(1.0)
+            actions, probs, log_prob = VF.CategoricalHeadFn.apply(logits, noise)
+            return actions, probs, log_prob
+        probs = torch.softmax(logits, dim=-1)        # (self.softmax is a scripted submodule here, not callable from an ignored method)
+        # (forward no longer calls get_sample, so the scripted module does not bind it: call it through the class)
+        actions, log_prob = SACActorDiscrete.get_sample(self, probs)
+        return actions, probs, log_prob
 
     @torch.jit.ignore
     def get_sample(self, probs: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -49,8 +71,7 @@ class SACActorDiscrete(nn.Module):
     def forward(self, obs: torch.Tensor, hidden: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
         """(obs, hidden) -> (actions, probs, log_prob of the actions, new hidden)   (discrete.py:80-101)"""
         logits, new_hidden = self.ncp(obs, hidden)
-        probs = self.softmax(logits)
-        actions, log_prob = self.get_sample(probs)
+        actions, probs, log_prob = self._head(logits)
         return actions, probs, log_prob, new_hidden
 
 
