@@ -44,9 +44,11 @@ class ReplayBuffer(BufferBase):
             indices = indices[lo:hi]
         return self.gather(indices)
 
-    def gather(self, indices: torch.Tensor) -> BatchExperience:
+    def gather(self, indices: torch.Tensor, n_rows: int | None = None) -> BatchExperience:
         """The gather half of `sample` for a caller-supplied int64 index vector (used by the data-parallel path,
-        where every rank draws the same global vector and gathers its own slice)."""
+        where every rank draws the same global vector and gathers its own slice).  `n_rows` bounds the valid indices (default: the
+        rows holding data; a graph capture that must stay valid while the buffer fills passes the capacity)."""
+        n_rows = self.size if n_rows is None else int(n_rows)
         arrays = [getattr(self, name) for name in FIELDS]
         if not arrays[0].is_cuda:
             raise RuntimeError(
@@ -54,9 +56,9 @@ class ReplayBuffer(BufferBase):
             )
         if self.use_shadow and not torch.cuda.is_current_stream_capturing():
             table, offsets, stride = self._shadow_table()
-            out = VF.gather_packed(table, offsets, stride, [a.shape[1] for a in arrays], indices, self.size)
+            out = VF.gather_packed(table, offsets, stride, [a.shape[1] for a in arrays], indices, n_rows)
         else:
-            out = VF.gather_rows(arrays, indices, self.size)
+            out = VF.gather_rows(arrays, indices, n_rows)
         return BatchExperience(*out)
 
     def warm(self, agent: "Any", n_samples: int, num_envs: int = 8) -> None:
