@@ -31,7 +31,6 @@ class NeuroFlowCTCore:
         # fused=True also takes the loss arithmetic around the networks (critic target + both MSE losses, actor loss, entropy loss) as
         # one launch forward / one backward each (velora_b200/csrc/sac_loss.cu) instead of ~40 framework kernels per step
         self.fused_losses = bool(fused)
-        self.graph_capable = bool(fused or capturable)      # optimizer state on the device: a whole train step can be captured
         # capturable=True keeps the optimizer state on the device so that a whole train step can be captured in a CUDA graph
         okw = {"capturable": True} if capturable else None
         if fused:   # one-launch Adam and Polyak updates (velora_b200/optim.py); same optimizer state layout as Adam(capturable=True)
@@ -239,7 +238,6 @@ class NeuroFlowCore(NeuroFlowCTCore):
         self.entropy = EntropyModuleDiscrete(action_dim, initial_alpha=initial_alpha, optim=optim, lr=alpha_lr, device=device, optim_kwargs=okw)
         self.loss = nn.MSELoss()
         self.fused_losses = bool(fused)
-        self.graph_capable = bool(fused or capturable)
         self.buffer = ReplayBuffer(buffer_size, state_dim, 1, self.actor.hidden_size, device=device)   # action index stored as one float
 
     def _update_critics(self, batch: BatchExperience) -> torch.Tensor:
