@@ -85,12 +85,12 @@ def _worker(rank, world, port, out):
 
     # ---- whole agents: two train steps data-parallel == single process on the whole batch (same indices, same noise), with NCCL and
     #      with the one-shot NVLink kernel as the gradient exchange
-    def agent_params(kind, parallel, oneshot):
+    def agent_params(kind, parallel, oneshot, fused=False):
         dp.configure(parallel, reduce="mean", oneshot=oneshot)
         if kind == "ct":
-            a = NeuroFlowCTCore(4, 1, 20, 128, torch.tensor([3.0]), torch.tensor([0.0]), buffer_size=2048, seed=64, device=dev)
+            a = NeuroFlowCTCore(4, 1, 20, 128, torch.tensor([3.0]), torch.tensor([0.0]), buffer_size=2048, seed=64, device=dev, fused=fused)
         else:
-            a = NeuroFlowCore(4, 2, 20, 128, buffer_size=2048, seed=64, device=dev)
+            a = NeuroFlowCore(4, 2, 20, 128, buffer_size=2048, seed=64, device=dev, fused=fused)
         gg = torch.Generator().manual_seed(3)
         b = a.buffer
         b.states.copy_(torch.randn(b.states.shape, generator=gg))
@@ -118,6 +118,11 @@ def _worker(rank, world, port, out):
             pair = [torch.empty_like(p_dp) for _ in range(world)]
             dist.all_gather(pair, p_dp)
             res[f"{kind}_{name}_replicas_equal"] = bool(torch.equal(pair[0], pair[1]))      # includes log_alpha (discrete: all-reduced too)
+        # the fused agents (one-launch optimizer / policy-head / loss kernels, frozen critics in the actor loss): data-parallel == single process
+        f_one = agent_params(kind, False, None, fused=True)
+        f_dp = agent_params(kind, True, None, fused=True)
+        res[f"{kind}_fused_max_abs"] = float((f_dp - f_one).abs().max())
+        res[f"{kind}_fused_vs_unfused"] = float((f_one - p_one).abs().max())
     if rank == 0:
         torch.save(res, out)
     dist.barrier()
@@ -141,3 +146,5 @@ def test_two_rank_nccl_gradients_equal_single_process(tmp_path):
         for name in ("nccl", "oneshot"):
             assert r[f"{kind}_{name}_max_abs"] < 1e-6, r               # two Adam steps of 3e-4
             assert r[f"{kind}_{name}_replicas_equal"], r
+        assert r[f"{kind}_fused_max_abs"] < 1e-6, r
+        assert r[f"{kind}_fused_vs_unfused"] < 2e-6, r                 # the fused kernels follow the framework ops to fp32 round-off
