@@ -237,7 +237,10 @@ struct BwdSmem {
 template <class C>
 __global__ void __launch_bounds__(2 * TM, 1) ncp_bwd_tc_kernel(const float* __restrict__ packed, const float* __restrict__ x,
                                                            const float* __restrict__ dy, float* __restrict__ dx,
-                                                           float* __restrict__ partials, float* __restrict__ d3buf, int64_t B) {
+                                                           float* __restrict__ partials, float* __restrict__ d3buf, int64_t B,
+                                                           int want_dw) {
+    // want_dw == 0: dL/dx only (a critic inside the actor loss): the sixteen dW2 MMAs per tile, the dW1 / dW3 row sums and the accumulator
+    // flushes are skipped
     using S = BwdSmem<C>;
     constexpr int DC = S::DC;
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -447,7 +450,7 @@ __global__ void __launch_bounds__(2 * TM, 1) ncp_bwd_tc_kernel(const float* __re
                                  make_desc(w_addr + (pb * C::NP + ks * 16) * 16, 128, 3 * C::NP * 16), idesc2, (p | ks) != 0);
                 }
                 mma_commit(bar2);
-            } else if (warp == 2) {     // dW2 (+ db2 through the constant-1 feature)
+            } else if (warp == 2 && want_dw) {     // dW2 (+ db2 through the constant-1 feature)
                 tc_fence_after();
                 constexpr uint32_t idescA = make_idesc(128, 3 * C::KF, 1, 1);
                 constexpr uint32_t idescB = make_idesc(128, C::KF, 1, 1);
@@ -464,7 +467,7 @@ __global__ void __launch_bounds__(2 * TM, 1) ncp_bwd_tc_kernel(const float* __re
         }
         since_flush += 1;
         mbar_wait(bar2, ph);
-        mbar_wait(bar3, ph);        // the du2 planes are free: the du1 strip may overwrite them
+        if (want_dw) mbar_wait(bar3, ph);        // the du2 planes are free: the du1 strip may overwrite them (without dW2 the da1 MMAs were their only reader)
         ph ^= 1;
         tc_fence_after();
         // ---------------- du1 = da1 * Mish'(u1) (u1 recomputed), dx = du1 W1, du1 -> strip
@@ -510,7 +513,7 @@ __global__ void __launch_bounds__(2 * TM, 1) ncp_bwd_tc_kernel(const float* __re
             for (int i = 0; i < C::I; ++i) dx[b * C::I + i] = dxr[i] + dxs[i * SS + row];
         }
         // ---------------- row sums: dW1 / db1 (thread j < KF), dW3 / db3 (the last 8 EC threads)
-        if (tid < C::KF) {
+        if (want_dw && tid < C::KF) {
             const float4* dr = reinterpret_cast<const float4*>(du1s + tid * SS);
 #pragma unroll 4
             for (int q = 0; q < TM / 4; ++q) {
@@ -523,7 +526,7 @@ __global__ void __launch_bounds__(2 * TM, 1) ncp_bwd_tc_kernel(const float* __re
                 acc1[C::I] += (d.x + d.y) + (d.z + d.w);
             }
         }
-        if (n3 >= 0) {
+        if (want_dw && n3 >= 0) {
             const float4* ar = reinterpret_cast<const float4*>(a2s + n3 * SS);
 #pragma unroll 4
             for (int q = 0; q < TM / 4; ++q) {
@@ -536,10 +539,10 @@ __global__ void __launch_bounds__(2 * TM, 1) ncp_bwd_tc_kernel(const float* __re
                 }
             }
         }
-        if (since_flush >= kFlushTiles) flush_dw();
+        if (want_dw && since_flush >= kFlushTiles) flush_dw();
         __syncthreads();      // strips and planes are rewritten by the next tile
     }
-    if (since_flush > 0) flush_dw();
+    if (want_dw && since_flush > 0) flush_dw();
     tc_fence_before();
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
@@ -650,7 +653,7 @@ static int launch_bwd(const float* packed, const float* x, const float* dy, floa
                  (long long)need);
     float* partials = reinterpret_cast<float*>(ws);
     float* d3buf = partials + (int64_t)grid * C::F_TOTAL;
-    ncp_bwd_tc_kernel<C><<<grid, 2 * TM, S::BYTES, stream>>>(packed, x, dy, dx, partials, d3buf, B);
+    ncp_bwd_tc_kernel<C><<<grid, 2 * TM, S::BYTES, stream>>>(packed, x, dy, dx, partials, d3buf, B, dpacked != nullptr);
     VB_LAUNCH_CHECK();
     if (dpacked)      // NULL: dL/dx only; the per-CTA partial rows stay in the workspace, unread
         reduce_rows_tc_kernel<<<(C::F_TOTAL + 31) / 32, 1024, 0, stream>>>(partials, grid, C::F_TOTAL, dpacked);
