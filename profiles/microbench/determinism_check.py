@@ -25,10 +25,16 @@ def run(kind, use_graph, steps=40):
     else:
         b.actions.copy_(torch.randint(0, 2, b.actions.shape, device=dev, generator=g).float())
     b.rewards.fill_(1.0)
-    b.size, b.position = (2048, 0) if use_graph else (128, 128)      # capture_train_step needs a full buffer
+    b.size, b.position = 2048, 0      # capture_train_step needs a full buffer; the eager runs start from the same state
     torch.manual_seed(99)
     state, hidden = torch.randn(4, device=dev), None
-    replay = a.capture_train_step(64, warmup=0) if use_graph else None
+    # three eager steps first in both modes (capture_train_step's warm-up: the optimizer state must exist before the capture)
+    if use_graph:
+        replay = a.capture_train_step(64, warmup=3)
+    else:
+        replay = None
+        for _ in range(3):
+            a._train_step(64)
     for s in range(steps):
         action, hidden = a.predict(state, hidden, train_mode=True)
         b.add(torch.randn(4, device=dev), action.reshape(-1).float(), 1.0, torch.randn(4, device=dev), False, hidden.reshape(-1))
@@ -39,7 +45,9 @@ def run(kind, use_graph, steps=40):
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 6
 for kind in ("ct", "disc"):
+    bases = {}
     for use_graph in (False, True):
-        base = run(kind, use_graph)
+        base = bases[use_graph] = run(kind, use_graph)
         diffs = [float((run(kind, use_graph) - base).abs().max()) for _ in range(n)]
         print(kind, "graph" if use_graph else "eager", "max |param diff| to the first run over", n, "repeats:", max(diffs), flush=True)
+    print(kind, "graph replays vs eager steps from the same state and seed: max |param diff|", float((bases[True] - bases[False]).abs().max()), flush=True)

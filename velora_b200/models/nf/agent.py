@@ -31,6 +31,7 @@ class NeuroFlowCTCore:
         # fused=True also takes the loss arithmetic around the networks (critic target + both MSE losses, actor loss, entropy loss) as
         # one launch forward / one backward each (velora_b200/csrc/sac_loss.cu) instead of ~40 framework kernels per step
         self.fused_losses = bool(fused)
+        self.graph_capable = bool(fused or capturable)      # optimizer state on the device: a whole train step can be captured
         # capturable=True keeps the optimizer state on the device so that a whole train step can be captured in a CUDA graph
         okw = {"capturable": True} if capturable else None
         if fused:   # one-launch Adam and Polyak updates (velora_b200/optim.py); same optimizer state layout as Adam(capturable=True)
@@ -208,6 +209,41 @@ class NeuroFlowCTCore:
         return replay
 
 
+    def capture_train_on_indices(self, batch_size: int):
+        """`_train_step` minus the index draw as one CUDA graph: returns (indices, replay) - write the minibatch's int64 row indices into
+        the static `indices` tensor, then `replay()`.  Unlike `capture_train_step` this graph stays valid while the buffer FILLS: the
+        sampling range lives outside it (`indices.copy_(torch.randint(0, len(buffer), (batch_size,), device=...))` per step is exactly
+        what `ReplayBuffer.sample` draws, so a replay loop consumes the generator like the eager loop).  As for every capture of a
+        backward pass, a few train steps must have run on a SIDE stream first (`warm_train_step`): autograd accumulates a parameter's
+        gradient on the stream that created it, and a capture cannot synchronise with the legacy default stream."""
+        if self.device is None or torch.device(self.device).type != "cuda":
+            raise RuntimeError("capture_train_on_indices needs a CUDA device")
+        indices = torch.zeros(batch_size, dtype=torch.int64, device=self.device)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = self._train_on(self.buffer.gather(indices, n_rows=self.buffer.capacity))
+
+        def replay():
+            graph.replay()
+            return out
+
+        replay.graph = graph
+        return indices, replay
+
+    def warm_train_step(self, batch_size: int):
+        """One eager `_train_step` on a side stream (the warm-up a later graph capture needs, see `capture_train_on_indices`)."""
+        side = getattr(self, "_warm_stream", None)
+        if side is None:
+            side = self._warm_stream = torch.cuda.Stream(device=self.device)
+        cur = torch.cuda.current_stream(self.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            out = self._train_step(batch_size)
+        cur.wait_stream(side)
+        return out
+
+
 class NeuroFlowCore(NeuroFlowCTCore):
     """The environment-free core of the reference's discrete agent NeuroFlow (velora/models/nf/agent.py:411-650): liquid
     actor with a softmax head, two NCP critics emitting Q for every action, discrete-SAC entropy tuning.  BASELINE config 1
@@ -238,6 +274,7 @@ class NeuroFlowCore(NeuroFlowCTCore):
         self.entropy = EntropyModuleDiscrete(action_dim, initial_alpha=initial_alpha, optim=optim, lr=alpha_lr, device=device, optim_kwargs=okw)
         self.loss = nn.MSELoss()
         self.fused_losses = bool(fused)
+        self.graph_capable = bool(fused or capturable)
         self.buffer = ReplayBuffer(buffer_size, state_dim, 1, self.actor.hidden_size, device=device)   # action index stored as one float
 
     def _update_critics(self, batch: BatchExperience) -> torch.Tensor:

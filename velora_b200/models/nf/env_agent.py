@@ -70,12 +70,41 @@ class _EnvLoop:
                 state, _ = self.env.reset()
                 state, hidden = self._obs(state), None
 
+    def _graph_train_step(self, batch_size: int):
+        """One train step of the episode loop on a graph-capable agent (`fused=True` or `capturable=True`, CUDA, no data parallelism): the
+        first three steps run eagerly on a side stream (the warm-up a capture of a backward pass needs), then the step minus its index
+        draw is ONE graph replay (`capture_train_on_indices`); the indices are drawn per step with the same `torch.randint` call as
+        `ReplayBuffer.sample`, so the loop consumes the generator exactly like the eager loop.  A batch-64 eager step is ~4 ms of Python
+        dispatch, a replay ~0.2 ms."""
+        st = self._graph_state
+        if st is None or st["batch"] != batch_size:
+            st = self._graph_state = dict(batch=batch_size, eager_left=3, indices=None, replay=None)
+        if st["replay"] is None:
+            if st["eager_left"] > 0:
+                st["eager_left"] -= 1
+                return self.warm_train_step(batch_size)
+            st["indices"], st["replay"] = self.capture_train_on_indices(batch_size)
+        if len(self.buffer) < batch_size:
+            raise ValueError(f"Buffer does not contain enough experiences. Available: {len(self.buffer)}, Requested: {batch_size}")
+        st["indices"].copy_(torch.randint(0, self.buffer.size, (batch_size,), device=self.device))
+        return st["replay"]()
+
     def train(self, batch_size: int, *, n_episodes: int = 10_000, max_steps: int = 1000, warmup_steps: int | None = None,
-              on_episode=None) -> List[float]:
-        """The episode loop of the reference's `train` (agent.py:258-355 / 638-697).  Returns the episode returns."""
+              on_episode=None, use_graph: bool | None = None) -> List[float]:
+        """The episode loop of the reference's `train` (agent.py:258-355 / 638-697).  Returns the episode returns.  `use_graph`
+        (default: whenever the agent can be captured) replays the train step as a CUDA graph, see `_graph_train_step`."""
+        from velora_b200 import dataparallel as _dp
+
         warmup_steps = batch_size * 2 if warmup_steps is None else warmup_steps
         if warmup_steps > 0:
             self._collect(max(warmup_steps, batch_size))
+        capable = (self.device is not None and torch.device(self.device).type == "cuda" and getattr(self, "graph_capable", False)
+                   and not _dp.is_enabled())
+        if use_graph and not capable:
+            raise RuntimeError("train(use_graph=True) needs a CUDA agent built with fused=True or capturable=True, without data parallelism")
+        use_graph = capable if use_graph is None else use_graph
+        self._graph_state = None
+        step = (lambda: self._graph_train_step(batch_size)) if use_graph else (lambda: self._train_step(batch_size))
         returns: List[float] = []
         for ep in range(1, n_episodes + 1):
             state, _ = self.env.reset()
@@ -86,7 +115,7 @@ class _EnvLoop:
                 nxt = self._obs(nxt)
                 done = bool(term or trunc)
                 self.buffer.add(state, action.reshape(-1).float(), float(reward), nxt, done, hidden.reshape(-1))
-                self.last_losses = self._train_step(batch_size)
+                self.last_losses = step()
                 ep_return += float(reward)
                 state = nxt
                 if done:
