@@ -55,6 +55,33 @@ class ActorModule:
         self.network.train()
 
 
+def _side_stream(fused: bool, device) -> "torch.cuda.Stream | None":
+    dev = torch.device(device) if device is not None else None
+    return torch.cuda.Stream(dev) if fused and dev is not None and dev.type == "cuda" else None
+
+
+def _concurrently(side, f1, f2):
+    """f1() on the current stream, f2() on `side`: the twin critics share no state, and at batch 64 each of their kernels fills a few SMs
+    only, so the pair (and, since autograd replays a node on its forward stream, the pair of backward passes) overlaps instead of
+    queueing.  Works inside a CUDA-graph capture: the two waits become graph dependencies."""
+    from velora_b200 import dataparallel as _dp
+
+    # data-parallel: every rank must issue its gradient exchanges in one order on one stream (the one-shot kernel numbers its calls on
+    # the device), so the twins stay on the current stream there
+    if side is None or _dp.is_enabled():
+        return f1(), f2()
+    cur = torch.cuda.current_stream(side.device)
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        b = f2()
+    a = f1()
+    cur.wait_stream(side)
+    for t in (b if isinstance(b, tuple) else (b,)):
+        if isinstance(t, torch.Tensor):
+            t.record_stream(cur)
+    return a, b
+
+
 class CriticModule:
     def __init__(self, state_dim: int, n_neurons: int, action_dim: int, *, optim: Type[optim.Optimizer] = optim.Adam,
                  lr: float = 3e-4, tau: float = 0.005, device: torch.device | None = None, optim_kwargs: dict | None = None,
@@ -62,6 +89,7 @@ class CriticModule:
         self.tau = tau
         self.fused_update = fused_update
         self.device = device
+        self._side = _side_stream(fused_update, device)
         self.network1 = SACCriticNCP(state_dim, n_neurons, action_dim, device=device).to(device)
         self.network2 = SACCriticNCP(state_dim, n_neurons, action_dim, device=device).to(device)
         self.target1 = deepcopy(self.network1)
@@ -116,10 +144,10 @@ class CriticModule:
         self.optim2.load_state_dict(state_dict["critic2_optim"])
 
     def predict(self, obs: torch.Tensor, actions: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-        return self.network1(obs, actions), self.network2(obs, actions)
+        return _concurrently(self._side, lambda: self.network1(obs, actions), lambda: self.network2(obs, actions))
 
     def target_predict(self, obs: torch.Tensor, actions: torch.Tensor) -> torch.Tensor:
-        return torch.min(self.target1(obs, actions), self.target2(obs, actions))
+        return torch.min(*_concurrently(self._side, lambda: self.target1(obs, actions), lambda: self.target2(obs, actions)))
 
 
 class EntropyModule:
@@ -201,6 +229,7 @@ class CriticModuleDiscrete:
         self.tau = tau
         self.fused_update = fused_update
         self.device = device
+        self._side = _side_stream(fused_update, device)
         self.network1 = SACCriticNCPDiscrete(state_dim, n_neurons, action_dim, device=device).to(device)
         self.network2 = SACCriticNCPDiscrete(state_dim, n_neurons, action_dim, device=device).to(device)
         self.target1 = deepcopy(self.network1)
@@ -220,14 +249,14 @@ class CriticModuleDiscrete:
     load_state_dict = CriticModule.load_state_dict
 
     def predict(self, obs: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-        return self.network1(obs), self.network2(obs)
+        return _concurrently(self._side, lambda: self.network1(obs), lambda: self.network2(obs))
 
     def target_predict(self, obs: torch.Tensor) -> torch.Tensor:
         return torch.min(*self.target_pair(obs))
 
     def target_pair(self, obs: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         """Both target critics' Q(s, .) (the fused critic loss takes their minimum itself)."""
-        return self.target1(obs), self.target2(obs)
+        return _concurrently(self._side, lambda: self.target1(obs), lambda: self.target2(obs))
 
 
 class EntropyModuleDiscrete:
