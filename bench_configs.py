@@ -299,7 +299,7 @@ def main():
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
         n_env_steps = int(sum(returns))
-        emit(config="cfg1 NeuroFlow(CartPole shim, 20, 128).train(64, n_episodes=50): act + env.step + buffer.add + one fused train step per env step (the train step replayed as an index-fed CUDA graph after three warm-up steps)",
+        emit(config="cfg1 NeuroFlow(CartPole shim, 20, 128).train(64, n_episodes=50): act + env.step + buffer.add + one fused train step per env step (after three eager warm-up steps the act and the train step are graph replays)",
              metric="wall_s_for_50_episodes", value=wall, env_steps=n_env_steps, ms_per_env_step=1e3 * wall / max(n_env_steps, 1),
              mean_return_first10=sum(returns[:10]) / 10, mean_return_last10=sum(returns[-10:]) / 10,
              note="environment = baseline/envs_shim.py (gymnasium is not installed); includes the 128-transition warm-up")

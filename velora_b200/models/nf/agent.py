@@ -135,13 +135,14 @@ class NeuroFlowCTCore:
         self.actor.train_mode()
         return action, hidden
 
-    def capture_predict(self, num_envs: int = 1, *, train_mode: bool = False):
+    def capture_predict(self, num_envs: int = 1, *, train_mode: bool = False, warmup: int = 3):
         """The per-environment-step `predict` as ONE CUDA graph (pack + forward kernel + the policy head) with static buffers.
 
         Returns `act(state [num_envs, S] or [S], hidden [num_envs, H] | None) -> (action, hidden)`; the outputs are the
         graph's static tensors (overwritten by the next call).  The graph reads the live parameters, so it stays valid
         across `_train_step` / graph replays of the train step.  An eager batch-1 `predict` is ~100 us of Python dispatch
-        and ~270 us on the device timeline; the replay is two tiny copies and one graph launch.
+        and ~270 us on the device timeline; the replay is two tiny copies and one graph launch.  `warmup` eager calls run first
+        (with `train_mode` they consume the generator: a caller that has already acted eagerly a few times passes 0).
         """
         if self.device is None or torch.device(self.device).type != "cuda":
             raise RuntimeError("capture_predict needs a CUDA device")
@@ -152,7 +153,7 @@ class NeuroFlowCTCore:
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(cur)
         with torch.cuda.stream(side):
-            for _ in range(3):
+            for _ in range(warmup):
                 self.predict(s_state, s_hidden, train_mode=train_mode)
         cur.wait_stream(side)
         torch.cuda.synchronize(dev)

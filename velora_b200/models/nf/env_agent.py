@@ -54,13 +54,26 @@ class _EnvLoop:
             return int(a[0].item())
         return a.cpu().numpy()
 
+    def _act(self, state: torch.Tensor, hidden):
+        """The stochastic action of one environment step.  In graph mode (see `train`) the first calls are eager, then `predict` is one
+        graph replay (`capture_predict`); the capture draws nothing from the generator, so the loop's random stream is the eager one."""
+        st = getattr(self, "_act_state", None)
+        if st is None:
+            return self.predict(state, hidden, train_mode=True)
+        if st["act"] is None:
+            if st["eager_left"] > 0:
+                st["eager_left"] -= 1
+                return self.predict(state, hidden, train_mode=True)
+            st["act"] = self.capture_predict(1, train_mode=True, warmup=0)
+        return st["act"](state, hidden)
+
     def _collect(self, n_samples: int) -> None:
         """Role of `ReplayBuffer.warm` (velora/buffer/replay.py:90-125) on the agent's own single environment: act stochastically
         with the current policy until the buffer holds `n_samples` transitions."""
         state, _ = self.env.reset(seed=self.seed)
         state, hidden = self._obs(state), None
         while len(self.buffer) < n_samples:
-            action, new_hidden = self.predict(state, hidden, train_mode=True)
+            action, new_hidden = self._act(state, hidden)
             nxt, reward, term, trunc, _ = self.env.step(self._env_action(action))
             nxt = self._obs(nxt)
             done = bool(term or trunc)
@@ -95,22 +108,23 @@ class _EnvLoop:
         (default: whenever the agent can be captured) replays the train step as a CUDA graph, see `_graph_train_step`."""
         from velora_b200 import dataparallel as _dp
 
-        warmup_steps = batch_size * 2 if warmup_steps is None else warmup_steps
-        if warmup_steps > 0:
-            self._collect(max(warmup_steps, batch_size))
         capable = (self.device is not None and torch.device(self.device).type == "cuda" and getattr(self, "graph_capable", False)
                    and not _dp.is_enabled())
         if use_graph and not capable:
             raise RuntimeError("train(use_graph=True) needs a CUDA agent built with fused=True or capturable=True, without data parallelism")
         use_graph = capable if use_graph is None else use_graph
         self._graph_state = None
+        self._act_state = dict(eager_left=3, act=None) if use_graph else None
+        warmup_steps = batch_size * 2 if warmup_steps is None else warmup_steps
+        if warmup_steps > 0:
+            self._collect(max(warmup_steps, batch_size))
         step = (lambda: self._graph_train_step(batch_size)) if use_graph else (lambda: self._train_step(batch_size))
         returns: List[float] = []
         for ep in range(1, n_episodes + 1):
             state, _ = self.env.reset()
             state, hidden, ep_return = self._obs(state), None, 0.0
             for _ in range(max_steps):
-                action, hidden = self.predict(state, hidden, train_mode=True)
+                action, hidden = self._act(state, hidden)
                 nxt, reward, term, trunc, _ = self.env.step(self._env_action(action))
                 nxt = self._obs(nxt)
                 done = bool(term or trunc)
