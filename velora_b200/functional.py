@@ -474,28 +474,9 @@ def pack_rows(arrays: Sequence[torch.Tensor], packed: torch.Tensor, offsets: Seq
         )
 
 
-def buffer_add_row(arrays: Sequence[torch.Tensor], values: Sequence, row: int, shadow: Optional[torch.Tensor] = None,
-                   offsets: Optional[Sequence[int]] = None, stride: int = 0) -> None:
-    """arrays[k][row] = values[k] for all k in ONE launch (and the packed shadow row with it).  values[k]: a float32 CUDA tensor of
-    arrays[k].shape[1] elements, or a Python number broadcast over the row."""
-    L = _lib.lib()
-    dev = arrays[0].device
-    n = len(arrays)
-    widths = [a.shape[1] for a in arrays]
-    srcs = [v if isinstance(v, torch.Tensor) else None for v in values]
-    scal = [0.0 if isinstance(v, torch.Tensor) else float(v) for v in values]
-    with torch.cuda.device(dev):
-        _count(1)
-        _lib.check(
-            L.vb_buffer_add_row(_lib.ptr_array(list(arrays)), (C.c_int * n)(*widths), _lib.ptr_array(srcs), (C.c_float * n)(*scal), n,
-                                int(row), int(arrays[0].shape[0]), _lib.ptr(shadow), int(stride),
-                                (C.c_int * n)(*offsets) if offsets is not None else None, _lib.stream_ptr(dev)),
-            "vb_buffer_add_row",
-        )
-
-
 def buffer_add_args(arrays: Sequence[torch.Tensor], shadow: Optional[torch.Tensor], offsets: Optional[Sequence[int]], stride: int):
-    """The call-invariant ctypes arguments of vb_buffer_add_row for one buffer (see buffer_add_row_cached)."""
+    """The call-invariant ctypes arguments of vb_buffer_add_row for one buffer: arrays[k][row] = values[k] for all k in ONE launch (and the
+    packed shadow row with it); see buffer_add_row_cached."""
     n = len(arrays)
     widths = [a.shape[1] for a in arrays]
     dev = arrays[0].device
@@ -505,7 +486,8 @@ def buffer_add_args(arrays: Sequence[torch.Tensor], shadow: Optional[torch.Tenso
 
 
 def buffer_add_row_cached(args, values: Sequence, row: int) -> None:
-    """buffer_add_row with the per-buffer arguments prepared once: the per-call work is six pointer / scalar stores and one launch."""
+    """One transition into the buffer (vb_buffer_add_row) with the per-buffer arguments prepared once: values[k] is a float32 CUDA tensor of
+    arrays[k].shape[1] elements or a Python number broadcast over the row; the per-call work is six pointer / scalar stores and one launch."""
     src, scal = args["src"], args["scal"]
     for k, v in enumerate(values):
         if isinstance(v, torch.Tensor):
