@@ -49,7 +49,8 @@
 extern "C" {
 #endif
 
-#define VB_ABI_VERSION 4      /* 4: standalone NCPLiquidCell entry points (vb_cell_fwd / vb_cell_bwd), absent layers in vb_liquid_pack;
+#define VB_ABI_VERSION 5      /* 5: additive - vb_transpose_rows, vb_buffer_add_row, vb_sacd_*, vb_categorical_head_*; vb_ncp_bwd accepts dpacked = NULL;
+                               *    4: standalone NCPLiquidCell entry points (vb_cell_fwd / vb_cell_bwd), absent layers in vb_liquid_pack;
                                *    3: the liquid forward saves gate factors for the backward (vb_liquid_saved_bytes, `saved` arguments);
                                *    2: layout flags, optimizer / policy-head / packed-gather / bf16-forward entry points added */
 
