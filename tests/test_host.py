@@ -347,3 +347,43 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["value"] > 0 and d["higher_is_better"] is True and d["vs_baseline"] is None
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+
+
+def test_frozen_parameters_flag_is_scoped_and_thread_local():
+    """functional.frozen_parameters(): nests, restores the previous state on exit (also on an exception) and is invisible to other threads
+    (autograd's backward thread never sees the caller's flag)."""
+    import threading
+
+    from velora_b200 import functional as VF
+
+    assert not VF.parameters_frozen()
+    with VF.frozen_parameters():
+        assert VF.parameters_frozen()
+        with VF.frozen_parameters():
+            assert VF.parameters_frozen()
+        assert VF.parameters_frozen()
+        seen = []
+        t = threading.Thread(target=lambda: seen.append(VF.parameters_frozen()))
+        t.start()
+        t.join()
+        assert seen == [False]
+    assert not VF.parameters_frozen()
+    with pytest.raises(ValueError):
+        with VF.frozen_parameters():
+            raise ValueError("boom")
+    assert not VF.parameters_frozen()
+
+
+def test_relayout_leaves_small_or_non_contiguous_tensors_alone():
+    """functional._relayout transposes only contiguous batch-major tensors of at least RELAYOUT_MIN_ROWS sample-steps, and only when the
+    kernel path accepts time-major storage; everything else is passed through untouched (no kernel call: this runs without a GPU)."""
+    from velora_b200 import functional as VF
+
+    small = torch.zeros(8, 4, 3)
+    assert VF._relayout(small, False, True)[0] is small
+    assert VF._relayout(None, False, True) == (None, False)
+    big = torch.zeros(VF.RELAYOUT_MIN_ROWS, 2, 3)
+    assert VF._relayout(big, False, False)[0] is big                      # the kernel path takes batch-major only
+    assert VF._relayout(big, True, True)[0] is big                        # already time-major
+    view = torch.zeros(2, VF.RELAYOUT_MIN_ROWS, 3).permute(1, 0, 2)
+    assert VF._relayout(view, False, True)[0] is view                     # not contiguous: the caller's _seq() decides
